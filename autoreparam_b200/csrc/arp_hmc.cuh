@@ -1,0 +1,201 @@
+// Generic (FP32 / FP64 SIMT) kernels: batched log-joint+gradient and the
+// persistent HMC kernel.  One launch runs EVERY transition of EVERY chain:
+// Philox momenta, L fused leapfrog steps, Metropolis accept, per-chain dual
+// averaging, burn-in / thinning, centred-sample store.
+//
+// Restates [TFP 0.7] HamiltonianMonteCarlo.one_step / _leapfrog_integrator_one_step
+// / MetropolisHastings.one_step / DualAveragingStepSizeAdaptation.one_step /
+// sample_chain as called from reference inference.py:218-234.
+#pragma once
+#include "arp_models.cuh"
+
+namespace arp {
+
+#define ARP_BLOCK 128
+
+// Workspace: per-chain vectors, element (d, c) at base[d * sd + c * sc].
+struct HmcWs {
+  real *z, *g, *xc;     // current state, its gradient, its centred values
+  real *x, *gx, *xcx;   // proposal
+  real *v;              // momentum
+  real *lp, *H, *lavg, *mult;  // [Cpad] current log-prob and dual-averaging state
+  int* nacc;            // [Cpad] accepted-transition counter
+  int sd, sc;
+};
+
+struct HmcArgs {
+  int C, D, L;
+  int T;          // transitions in this launch
+  int t_begin;    // global index of the first transition
+  int num_adapt, num_burnin, stride;  // stride = 1 + num_steps_between_results
+  int S;          // kept samples in total
+  unsigned long long seed;
+  unsigned int chain_offset;
+  real target_accept;
+  const real* eps0;          // [D]
+  const real* a;             // [D]
+  const real* b;             // [D]
+  const real* ext_momenta;   // [T_total, C, D] or null
+  const real* ext_log_u;     // [T_total, C] or null
+  real* samples;             // [S, C, D] or null
+  real* samples_orig;        // [S, C, D] or null
+  unsigned char* is_accepted;  // [S, C] or null
+};
+
+template <int KIND, int LPC, bool WITH_A, int FP>
+__global__ void __launch_bounds__(ARP_BLOCK)
+k_log_joint_grad(DevModel m, const real* __restrict__ a, const real* __restrict__ b,
+                 const real* z, int C, real* lp_out, real* g_scratch, real* xc_scratch, real* abar_scratch) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = gtid / LPC;
+  const int sub = gtid % LPC;
+  // padded chains (chain >= C) still run: scratch buffers are padded to the grid
+  const size_t off = (size_t)chain * m.D;
+  const int zc = chain < C ? chain : C - 1;
+  Vec vz{const_cast<real*>(z) + (size_t)zc * m.D, 1};
+  Vec vg_{g_scratch + off, 1}, vxc{xc_scratch + off, 1};
+  Vec vab{abar_scratch ? abar_scratch + off : nullptr, 1};
+  real lp = vg<KIND, LPC, WITH_A, FP>(m, a, b, vz, vg_, vxc, vab, sub, true);
+  if (chain < C && sub == 0 && lp_out) lp_out[chain] = lp;
+}
+
+template <int KIND, int LPC, int FP>
+__global__ void __launch_bounds__(ARP_BLOCK)
+k_hmc_init(DevModel m, HmcWs ws, HmcArgs p, const real* z0) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = gtid / LPC;
+  const int sub = gtid % LPC;
+  const bool valid = chain < p.C;
+  const size_t co = (size_t)chain * ws.sc;
+  Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
+  for (int d = sub; d < p.D; d += LPC) Z(d) = valid ? z0[(size_t)chain * p.D + d] : (real)0;
+  __syncwarp();
+  real lp = vg<KIND, LPC, false, FP>(m, p.a, p.b, Z, G, XC, Vec{nullptr, 1}, sub, true);
+  if (sub == 0) {
+    ws.lp[chain] = lp;
+    ws.H[chain] = 0;
+    ws.lavg[chain] = 0;
+    ws.mult[chain] = 1;
+    ws.nacc[chain] = 0;
+  }
+}
+
+template <int KIND, int LPC, int FP>
+__global__ void __launch_bounds__(ARP_BLOCK)
+k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = gtid / LPC;
+  const int sub = gtid % LPC;
+  const bool valid = chain < p.C;
+  const int D = p.D;
+  const size_t co = (size_t)chain * ws.sc;
+  Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
+  Vec X{ws.x + co, ws.sd}, GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
+  Vec V{ws.v + co, ws.sd};
+  const real* __restrict__ eps0 = p.eps0;
+  real lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
+  int nacc = ws.nacc[chain];
+  const unsigned int gchain = p.chain_offset + (unsigned int)chain;
+
+  for (int t = 0; t < p.T; ++t) {
+    const int tg = p.t_begin + t;
+    // ---- momenta v0 ~ N(0, I); proposal starts at the current state
+    real ke0 = 0;
+    if (p.ext_momenta) {
+      const real* mom = p.ext_momenta + ((size_t)tg * p.C + (valid ? chain : 0)) * D;
+      for (int d = sub; d < D; d += LPC) {
+        const real v = mom[d];
+        V(d) = v;
+        ke0 = fma(v, v, ke0);
+      }
+    } else {
+      const int nb = (D + 3) >> 2;
+      for (int j = sub; j < nb; j += LPC) {
+        real n4[4];
+        philox_normal4(p.seed, gchain, (unsigned int)tg, (unsigned int)j, ARP_STREAM_MOMENTUM, n4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int d = 4 * j + q;
+          if (d < D) {
+            V(d) = n4[q];
+            ke0 = fma(n4[q], n4[q], ke0);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    ke0 = group_sum<LPC>(ke0);
+    for (int d = sub; d < D; d += LPC) {
+      X(d) = Z(d);
+      GX(d) = G(d);
+    }
+    // ---- L leapfrog steps, two half kicks per step as TFP 0.7 does
+    real lpx = 0, ke1 = 0;
+    for (int l = 0; l < p.L; ++l) {
+      for (int d = sub; d < D; d += LPC) {
+        const real e = ldg(eps0 + d) * mult;
+        const real v = V(d) + (real)0.5 * e * GX(d);
+        V(d) = v;
+        X(d) = X(d) + e * v;
+      }
+      __syncwarp();
+      const bool last = (l == p.L - 1);
+      lpx = vg<KIND, LPC, false, FP>(m, p.a, p.b, X, GX, XCX, Vec{nullptr, 1}, sub, last);
+      __syncwarp();
+      for (int d = sub; d < D; d += LPC) {
+        const real e = ldg(eps0 + d) * mult;
+        const real v = V(d) + (real)0.5 * e * GX(d);
+        V(d) = v;
+        if (last) ke1 = fma(v, v, ke1);
+      }
+    }
+    ke1 = group_sum<LPC>(ke1);
+    // ---- Metropolis-Hastings
+    real log_alpha = lpx - lp_cur + (real)0.5 * ke0 - (real)0.5 * ke1;
+    if (!(log_alpha == log_alpha) || log_alpha == -INFINITY) log_alpha = -INFINITY;  // safe_sum: nan -> reject
+    real log_u;
+    if (p.ext_log_u) log_u = p.ext_log_u[(size_t)tg * p.C + (valid ? chain : 0)];
+    else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
+    const bool acc = log_u < log_alpha;
+    if (acc) {
+      for (int d = sub; d < D; d += LPC) {
+        Z(d) = X(d);
+        G(d) = GX(d);
+        XC(d) = XCX(d);
+      }
+      lp_cur = lpx;
+      ++nacc;
+    }
+    // ---- per-chain dual averaging (TFP defaults: gamma 0.05, t0 10, kappa 0.75)
+    const int t1 = tg + 1;
+    if (t1 <= p.num_adapt) {
+      const real ft = (real)t1;
+      Hc += p.target_accept - r_exp(log_alpha < (real)0 ? log_alpha : (real)0);
+      const real log_step = ARP_LOG_10 - Hc * r_sqrt(ft) / ((ft + (real)10) * (real)0.05);
+      const real eta = r_pow(ft, (real)-0.75);
+      lavg = eta * log_step + ((real)1 - eta) * lavg;
+      mult = (t1 < p.num_adapt) ? r_exp(log_step) : r_exp(lavg);
+    }
+    // ---- keep every `stride`-th state after burn-in
+    const int since = tg - p.num_burnin;
+    if (since >= 0 && (since % p.stride) == 0 && valid) {
+      const int s = since / p.stride;
+      if (s < p.S) {
+        const size_t o = ((size_t)s * p.C + chain) * D;
+        if (p.samples) for (int d = sub; d < D; d += LPC) p.samples[o + d] = XC(d);
+        if (p.samples_orig) for (int d = sub; d < D; d += LPC) p.samples_orig[o + d] = Z(d);
+        if (p.is_accepted && sub == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
+      }
+    }
+    __syncwarp();
+  }
+  if (sub == 0) {
+    ws.lp[chain] = lp_cur;
+    ws.H[chain] = Hc;
+    ws.lavg[chain] = lavg;
+    ws.mult[chain] = mult;
+    ws.nacc[chain] = nacc;
+  }
+}
+
+}  // namespace arp

@@ -1,0 +1,459 @@
+// C ABI of the autoreparam B200 library (see include/autoreparam_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared
+//        -Xcompiler -fPIC [-DARP_FP64] arp_lib.cu -o libarp_f32.so | libarp_f64.so
+#include "../../include/autoreparam_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "arp_host.cuh"
+#include "arp_hmc.cuh"
+#include "arp_ess.cuh"
+#include "arp_vi.cuh"
+#ifndef ARP_FP64
+#include "arp_german_tc.cuh"
+#endif
+
+using namespace arp;
+
+static_assert(sizeof(arp_real) == sizeof(real), "arp_real / real mismatch");
+
+// ------------------------------------------------------------------ errors ---
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+#define ARP_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                  std::to_string(__LINE__) + ")");                                           \
+  } while (0)
+#define ARP_LAUNCH_CHECK()                  \
+  do {                                      \
+    g_launches.fetch_add(1);                \
+    ARP_CUDA(cudaGetLastError());           \
+  } while (0)
+
+extern "C" const char* arp_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t arp_kernel_launch_count(void) { return g_launches.load(); }
+extern "C" const char* arp_precision(void) { return ARP_REAL_IS_DOUBLE ? "f64" : "f32"; }
+
+struct arp_model {
+  DevModel dev{};
+  std::string name;
+  DevBuf X, y, x1, x2, w, u, offs, gidx, pidx;
+  int fp = 32;  // german: register-resident padded feature count of the SIMT engine
+#ifndef ARP_FP64
+  GermanTc tc;  // german: operands of the tcgen05 engine
+#endif
+};
+
+static std::vector<real> to_real(const float* p, size_t n) {
+  std::vector<real> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = (real)p[i];
+  return v;
+}
+
+// --------------------------------------------------------------- model create ---
+extern "C" int arp_model_create(const char* model_name, const arp_model_data* d, arp_model** out) {
+  if (!model_name || !d || !out) return fail("arp_model_create: null argument");
+  const std::string name(model_name);
+  arp_model* m = new arp_model();
+  m->name = name;
+  DevModel& dm = m->dev;
+  auto bail = [&](const std::string& msg) { delete m; return fail("arp_model_create(" + name + "): " + msg); };
+#define UP(buf, vec) do { cudaError_t _e = upload(m->buf, vec); if (_e != cudaSuccess) return bail(cudaGetErrorString(_e)); } while (0)
+
+  if (name == "8schools") {
+    if (d->n != 8 || !d->y || !d->x1) return bail("needs n=8, y, x1 (stddevs)");
+    dm.kind = MODEL_8SCHOOLS; dm.N = 8; dm.D = 10;
+    UP(y, to_real(d->y, 8)); UP(x1, to_real(d->x1, 8));
+  } else if (name == "german_credit_lognormalcentered" || name == "german_credit_gammascale") {
+    if (d->n <= 0 || d->f <= 0 || !d->X || !d->y) return bail("needs n, f, X, y");
+    dm.kind = (name == "german_credit_gammascale") ? MODEL_GERMAN_GAMMA : MODEL_GERMAN_LOGNORMAL;
+    dm.N = (int)d->n; dm.F = (int)d->f; dm.D = 1 + 2 * dm.F;
+    if (dm.F > 64) return bail("more than 64 features is not supported");
+    m->fp = dm.F <= 32 ? 32 : 64;
+    dm.Fpad = m->fp;
+    std::vector<real> X((size_t)dm.N * dm.Fpad, (real)0);
+    for (int n = 0; n < dm.N; ++n)
+      for (int f = 0; f < dm.F; ++f) X[(size_t)n * dm.Fpad + f] = (real)d->X[(size_t)n * dm.F + f];
+    UP(X, X); UP(y, to_real(d->y, dm.N));
+#ifndef ARP_FP64
+    if (dm.kind == MODEL_GERMAN_LOGNORMAL) {
+      std::string err;
+      if (!m->tc.build(d->X, d->y, dm.N, dm.F, &err)) return bail("tcgen05 operand build: " + err);
+    }
+#endif
+  } else if (name == "radon" || name == "radon_stddvs") {
+    if (d->n <= 0 || d->j <= 0 || !d->idx0 || !d->u || !d->x1 || !d->y) return bail("needs n, j, idx0 (county), u, x1, y");
+    const bool sd = (name == "radon_stddvs");
+    dm.kind = sd ? MODEL_RADON_STDDVS : MODEL_RADON;
+    dm.N = (int)d->n; dm.J = (int)d->j; dm.D = 3 + (sd ? 2 : 1) * dm.J;
+    std::vector<int> offs(dm.J + 1, 0);
+    for (int n = 0; n < dm.N; ++n) {
+      if (d->idx0[n] < 0 || d->idx0[n] >= dm.J) return bail("county index out of range");
+      offs[d->idx0[n] + 1]++;
+    }
+    for (int j = 0; j < dm.J; ++j) offs[j + 1] += offs[j];
+    std::vector<int> cur(offs.begin(), offs.end() - 1);
+    std::vector<real> xs(dm.N), ys(dm.N);
+    for (int n = 0; n < dm.N; ++n) {  // stable counting sort by county
+      const int pos = cur[d->idx0[n]]++;
+      xs[pos] = (real)d->x1[n]; ys[pos] = (real)d->y[n];
+    }
+    UP(offs, offs); UP(x1, xs); UP(y, ys); UP(u, to_real(d->u, dm.J));
+  } else if (name == "election") {
+    if (d->n <= 0 || d->j <= 0 || !d->idx0 || !d->x1 || !d->x2 || !d->y) return bail("needs n, j (n_state), idx0 (state), x1 (female), x2 (black), y");
+    dm.kind = MODEL_ELECTION; dm.K = (int)d->j; dm.J = dm.K + 1; dm.D = dm.K + 4;
+    // tf.one_hot(state, K): only 0 <= state < K hits a column (reference models.py:978)
+    std::map<std::tuple<int, float, float>, std::pair<double, double>> cells;
+    for (int64_t n = 0; n < d->n; ++n) {
+      const int s = d->idx0[n];
+      const int k = (s >= 0 && s < dm.K) ? s : dm.K;
+      auto& c = cells[std::make_tuple(k, d->x1[n], d->x2[n])];
+      c.first += 1.0; c.second += (double)d->y[n];
+    }
+    std::vector<int> offs(dm.J + 1, 0);
+    std::vector<real> fe, bl, w, ys;
+    for (auto& kv : cells) {  // std::map iterates sorted by group first
+      offs[std::get<0>(kv.first) + 1]++;
+      fe.push_back((real)std::get<1>(kv.first)); bl.push_back((real)std::get<2>(kv.first));
+      w.push_back((real)kv.second.first); ys.push_back((real)kv.second.second);
+    }
+    for (int j = 0; j < dm.J; ++j) offs[j + 1] += offs[j];
+    dm.N = (int)w.size();
+    UP(offs, offs); UP(x1, fe); UP(x2, bl); UP(w, w); UP(y, ys);
+  } else if (name == "electric") {
+    if (d->n <= 0 || d->j <= 0 || d->k != 4 || d->k2 != 4 || !d->idx0 || !d->idx1 || !d->idx2 || !d->x1 || !d->y)
+      return bail("needs n, j (n_pair), k = k2 = 4, idx0 (pair), idx1 (grade), idx2 (grade_pair), x1 (treatment), y");
+    dm.kind = MODEL_ELECTRIC; dm.N = (int)d->n; dm.K = (int)d->j; dm.J = dm.K + 1; dm.D = 12 + dm.K;
+    std::vector<int> offs(dm.J + 1, 0), grp(dm.N);
+    for (int n = 0; n < dm.N; ++n) {
+      const int p = d->idx0[n];
+      grp[n] = (p >= 0 && p < dm.K) ? p : dm.K;
+      offs[grp[n] + 1]++;
+    }
+    for (int j = 0; j < dm.J; ++j) offs[j + 1] += offs[j];
+    std::vector<int> cur(offs.begin(), offs.end() - 1), gidx(dm.N), pidx(dm.K);
+    std::vector<real> tr(dm.N), ys(dm.N);
+    for (int n = 0; n < dm.N; ++n) {
+      const int pos = cur[grp[n]]++;
+      const int g = d->idx1[n];
+      gidx[pos] = (g >= 0 && g < 4) ? g : -1;
+      tr[pos] = (real)d->x1[n]; ys[pos] = (real)d->y[n];
+    }
+    for (int p = 0; p < dm.K; ++p) {
+      const int g = d->idx2[p];
+      pidx[p] = (g >= 0 && g < 4) ? g : -1;
+    }
+    UP(offs, offs); UP(gidx, gidx); UP(pidx, pidx); UP(x1, tr); UP(y, ys);
+  } else if (name == "time_series") {
+    if (d->n <= 0 || !d->x1 || !d->y) return bail("needs n (T), x1 (x), y");
+    dm.kind = MODEL_TIME_SERIES; dm.N = (int)d->n; dm.K = dm.N; dm.D = 3 + 2 * dm.N;
+    UP(x1, to_real(d->x1, dm.N)); UP(y, to_real(d->y, dm.N));
+  } else {
+    delete m;
+    return fail("unknown model " + name);  // mirrors models.py:1173-1174
+  }
+#undef UP
+  dm.X = m->X.as<real>(); dm.y = m->y.as<real>(); dm.x1 = m->x1.as<real>(); dm.x2 = m->x2.as<real>();
+  dm.w = m->w.as<real>(); dm.u = m->u.as<real>(); dm.offs = m->offs.as<int>();
+  dm.gidx = m->gidx.as<int>(); dm.pidx = m->pidx.as<int>();
+  *out = m;
+  return 0;
+}
+
+extern "C" void arp_model_destroy(arp_model* m) { delete m; }
+extern "C" int arp_model_num_coords(const arp_model* m) { return m ? m->dev.D : -1; }
+
+// ------------------------------------------------------------------ dispatch ---
+static int pick_lpc(const arp_model* m, long long C, int forced) {
+  if (forced == 1 || forced == 8 || forced == 32) return forced;
+  if (m->dev.kind == MODEL_TIME_SERIES) return 1;  // sequential scan: extra lanes would idle
+  const long long target = 148LL * 4 * 32 * 4;      // ~4 warps per SM sub-partition
+  if (C >= target) return 1;
+  if (C * 8 >= target) return 8;
+  return 32;
+}
+
+// expands BODY(KIND, LPC, FP) for the runtime (kind, lpc, fp)
+#define ARP_DISPATCH_LPC(KIND, FP, lpc, BODY)                   \
+  switch (lpc) {                                                \
+    case 1: { BODY(KIND, 1, FP); } break;                       \
+    case 8: { BODY(KIND, 8, FP); } break;                       \
+    default: { BODY(KIND, 32, FP); } break;                     \
+  }
+#define ARP_DISPATCH(kind, lpc, fp, BODY)                                                        \
+  switch (kind) {                                                                                \
+    case MODEL_8SCHOOLS: ARP_DISPATCH_LPC(MODEL_8SCHOOLS, 32, lpc, BODY) break;                  \
+    case MODEL_GERMAN_LOGNORMAL:                                                                 \
+      if (fp == 32) { ARP_DISPATCH_LPC(MODEL_GERMAN_LOGNORMAL, 32, lpc, BODY) }                  \
+      else { ARP_DISPATCH_LPC(MODEL_GERMAN_LOGNORMAL, 64, lpc, BODY) } break;                    \
+    case MODEL_GERMAN_GAMMA:                                                                     \
+      if (fp == 32) { ARP_DISPATCH_LPC(MODEL_GERMAN_GAMMA, 32, lpc, BODY) }                      \
+      else { ARP_DISPATCH_LPC(MODEL_GERMAN_GAMMA, 64, lpc, BODY) } break;                        \
+    case MODEL_RADON: ARP_DISPATCH_LPC(MODEL_RADON, 32, lpc, BODY) break;                        \
+    case MODEL_RADON_STDDVS: ARP_DISPATCH_LPC(MODEL_RADON_STDDVS, 32, lpc, BODY) break;          \
+    case MODEL_ELECTION: ARP_DISPATCH_LPC(MODEL_ELECTION, 32, lpc, BODY) break;                  \
+    case MODEL_ELECTRIC: ARP_DISPATCH_LPC(MODEL_ELECTRIC, 32, lpc, BODY) break;                  \
+    default: ARP_DISPATCH_LPC(MODEL_TIME_SERIES, 32, lpc, BODY) break;                           \
+  }
+
+static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+// copies `n` reals from a caller buffer (host or device) into a fresh device buffer
+static int stage_in(DevBuf& buf, const void* src, size_t bytes, int mem, cudaStream_t st) {
+  ARP_CUDA(buf.alloc(bytes));
+  ARP_CUDA(cudaMemcpyAsync(buf.p, src, bytes, mem == ARP_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// -------------------------------------------------------- log joint + gradient ---
+extern "C" int arp_log_joint_grad(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
+                                  arp_real* lp, arp_real* grad, arp_real* centered, arp_real* abar, int mem,
+                                  void* stream) {
+  if (!m || !a || !b || !z || C <= 0) return fail("arp_log_joint_grad: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->dev.D;
+  const int lpc = pick_lpc(m, C, 0);
+  const int cpb = ARP_BLOCK / lpc;
+  const long long Cpad = round_up(C, cpb);
+  DevBuf da, db, dz, dlp, dg, dxc, dab;
+  if (stage_in(da, a, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  if (stage_in(db, b, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  const real* zdev = z;
+  if (mem == ARP_MEM_HOST) {
+    if (stage_in(dz, z, (size_t)C * D * sizeof(real), mem, st)) return 1;
+    zdev = dz.as<real>();
+  }
+  ARP_CUDA(dlp.alloc(Cpad * sizeof(real)));
+  ARP_CUDA(dg.alloc((size_t)Cpad * D * sizeof(real)));
+  ARP_CUDA(dxc.alloc((size_t)Cpad * D * sizeof(real)));
+  if (abar) ARP_CUDA(dab.alloc((size_t)Cpad * D * sizeof(real)));
+  const dim3 grid((unsigned)(Cpad / cpb)), block(ARP_BLOCK);
+  const DevModel dm = m->dev;
+  const int fp = m->fp;
+  const bool with_a = abar != nullptr;
+#define BODY(KIND, LPC, FP)                                                                              \
+  if (with_a) k_log_joint_grad<KIND, LPC, true, FP><<<grid, block, 0, st>>>(                              \
+      dm, da.as<real>(), db.as<real>(), zdev, (int)C, dlp.as<real>(), dg.as<real>(), dxc.as<real>(), dab.as<real>()); \
+  else k_log_joint_grad<KIND, LPC, false, FP><<<grid, block, 0, st>>>(                                    \
+      dm, da.as<real>(), db.as<real>(), zdev, (int)C, dlp.as<real>(), dg.as<real>(), dxc.as<real>(), nullptr);
+  ARP_DISPATCH(dm.kind, lpc, fp, BODY)
+#undef BODY
+  ARP_LAUNCH_CHECK();
+  const cudaMemcpyKind kd = mem == ARP_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (lp) ARP_CUDA(cudaMemcpyAsync(lp, dlp.p, C * sizeof(real), kd, st));
+  if (grad) ARP_CUDA(cudaMemcpyAsync(grad, dg.p, (size_t)C * D * sizeof(real), kd, st));
+  if (centered) ARP_CUDA(cudaMemcpyAsync(centered, dxc.p, (size_t)C * D * sizeof(real), kd, st));
+  if (abar) ARP_CUDA(cudaMemcpyAsync(abar, dab.p, (size_t)C * D * sizeof(real), kd, st));
+  ARP_CUDA(cudaStreamSynchronize(st));  // temporaries are freed on return
+  return 0;
+}
+
+// ------------------------------------------------------------------------ HMC ---
+extern "C" int64_t arp_hmc_num_transitions(const arp_hmc_config* cfg) {
+  if (!cfg || cfg->num_results <= 0) return 0;
+  return 1 + (int64_t)cfg->num_burnin_steps + (1 + (int64_t)cfg->num_steps_between_results) * (cfg->num_results - 1);
+}
+
+__global__ void k_gather_ws(const real* ws, int sd, int sc, int C, int D, real* out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)C * D) return;
+  const int c = (int)(i / D), d = (int)(i % D);
+  out[i] = ws[(size_t)d * sd + (size_t)c * sc];
+}
+
+extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_real* a, const arp_real* b, int64_t C,
+                           const arp_hmc_buffers* buf, int mem, void* stream) {
+  if (!m || !cfg || !a || !b || !buf || C <= 0) return fail("arp_hmc_run: bad argument");
+  if (!buf->z0 || !buf->eps0) return fail("arp_hmc_run: z0 and eps0 are required");
+  if (cfg->num_leapfrog_steps < 1 || cfg->num_results < 1 || cfg->num_burnin_steps < 0 ||
+      cfg->num_steps_between_results < 0)
+    return fail("arp_hmc_run: bad configuration");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->dev.D;
+  const long long T = arp_hmc_num_transitions(cfg);
+  const long long S = cfg->num_results;
+  const bool host = mem == ARP_MEM_HOST;
+
+#ifndef ARP_FP64
+  const bool tc_ok = m->dev.kind == MODEL_GERMAN_LOGNORMAL && m->tc.ready();
+  if (cfg->engine == 2 && !tc_ok) return fail("arp_hmc_run: tcgen05 engine is only available for german_credit_lognormalcentered");
+  const bool use_tc = tc_ok && (cfg->engine == 2 || (cfg->engine == 0 && german_tc_auto(C)));
+#else
+  if (cfg->engine == 2) return fail("arp_hmc_run: the fp64 check build has no tcgen05 engine");
+  const bool use_tc = false;
+#endif
+
+  // ---- stage inputs
+  DevBuf da, db, dz0, deps, dmom, dlu, dsamp, dorig, dacc;
+  if (stage_in(da, a, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  if (stage_in(db, b, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  const real *z0 = buf->z0, *eps0 = buf->eps0, *mom = buf->ext_momenta, *lu = buf->ext_log_u;
+  real *samples = buf->samples, *samples_orig = buf->samples_orig;
+  unsigned char* is_acc = buf->is_accepted;
+  if (host) {
+    if (stage_in(dz0, z0, (size_t)C * D * sizeof(real), mem, st)) return 1;
+    if (stage_in(deps, eps0, D * sizeof(real), mem, st)) return 1;
+    z0 = dz0.as<real>(); eps0 = deps.as<real>();
+    if (mom) { if (stage_in(dmom, mom, (size_t)T * C * D * sizeof(real), mem, st)) return 1; mom = dmom.as<real>(); }
+    if (lu) { if (stage_in(dlu, lu, (size_t)T * C * sizeof(real), mem, st)) return 1; lu = dlu.as<real>(); }
+    if (samples) { ARP_CUDA(dsamp.alloc((size_t)S * C * D * sizeof(real))); samples = dsamp.as<real>(); }
+    if (samples_orig) { ARP_CUDA(dorig.alloc((size_t)S * C * D * sizeof(real))); samples_orig = dorig.as<real>(); }
+    if (is_acc) { ARP_CUDA(dacc.alloc((size_t)S * C)); is_acc = dacc.as<unsigned char>(); }
+  }
+
+  HmcArgs p{};
+  p.C = (int)C; p.D = D; p.L = cfg->num_leapfrog_steps; p.T = (int)T; p.t_begin = 0;
+  p.num_adapt = cfg->num_adaptation_steps; p.num_burnin = cfg->num_burnin_steps;
+  p.stride = 1 + cfg->num_steps_between_results; p.S = (int)S;
+  p.seed = cfg->seed; p.chain_offset = (unsigned int)cfg->chain_offset;
+  p.target_accept = (real)(cfg->target_accept_prob > 0 ? cfg->target_accept_prob : 0.75);
+  p.eps0 = eps0; p.a = da.as<real>(); p.b = db.as<real>();
+  p.ext_momenta = mom; p.ext_log_u = lu;
+  p.samples = samples; p.samples_orig = samples_orig; p.is_accepted = is_acc;
+
+  DevBuf wsbuf, scal, nacc;
+  DevBuf dfz;
+  real* out_mult_dev = nullptr;
+  int* out_nacc_dev = nullptr;
+  real* final_z_dev = nullptr;
+
+#ifndef ARP_FP64
+  if (use_tc) {
+    int rc = german_tc_hmc(m->tc, p, z0, st, &dfz, &scal, &nacc, &g_launches, &g_last_error);
+    if (rc) return rc;
+    final_z_dev = dfz.as<real>();
+    out_mult_dev = scal.as<real>();
+    out_nacc_dev = nacc.as<int>();
+  } else
+#endif
+  {
+    const int lpc = pick_lpc(m, C, cfg->lanes_per_chain);
+    const int cpb = ARP_BLOCK / lpc;
+    const long long Cpad = round_up(C, cpb);
+    const long long Dpad = round_up(D, 8);
+    HmcWs ws{};
+    const size_t vec = (size_t)Cpad * Dpad;
+    ARP_CUDA(wsbuf.alloc(7 * vec * sizeof(real)));
+    ARP_CUDA(cudaMemsetAsync(wsbuf.p, 0, 7 * vec * sizeof(real), st));
+    real* base = wsbuf.as<real>();
+    ws.z = base; ws.g = base + vec; ws.xc = base + 2 * vec; ws.x = base + 3 * vec;
+    ws.gx = base + 4 * vec; ws.xcx = base + 5 * vec; ws.v = base + 6 * vec;
+    ARP_CUDA(scal.alloc(4 * Cpad * sizeof(real)));
+    ARP_CUDA(nacc.alloc(Cpad * sizeof(int)));
+    real* sb = scal.as<real>();
+    ws.mult = sb; ws.lp = sb + Cpad; ws.H = sb + 2 * Cpad; ws.lavg = sb + 3 * Cpad;
+    ws.nacc = nacc.as<int>();
+    if (lpc == 1) { ws.sd = (int)Cpad; ws.sc = 1; } else { ws.sd = 1; ws.sc = (int)Dpad; }
+    const dim3 grid((unsigned)(Cpad / cpb)), block(ARP_BLOCK);
+    const DevModel dm = m->dev;
+    const int fp = m->fp;
+#define BODY(KIND, LPC, FP)                                          \
+    k_hmc_init<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p, z0); \
+    k_hmc_run<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p);
+    ARP_DISPATCH(dm.kind, lpc, fp, BODY)
+#undef BODY
+    g_launches.fetch_add(1);
+    ARP_LAUNCH_CHECK();
+    out_mult_dev = ws.mult;
+    out_nacc_dev = ws.nacc;
+    if (buf->final_z) {
+      ARP_CUDA(dfz.alloc((size_t)C * D * sizeof(real)));
+      const long long n = (long long)C * D;
+      k_gather_ws<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.z, ws.sd, ws.sc, (int)C, D, dfz.as<real>());
+      ARP_LAUNCH_CHECK();
+      final_z_dev = dfz.as<real>();
+    }
+  }
+
+  // ---- outputs
+  const cudaMemcpyKind kd = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (host) {
+    if (buf->samples) ARP_CUDA(cudaMemcpyAsync(buf->samples, samples, (size_t)S * C * D * sizeof(real), kd, st));
+    if (buf->samples_orig) ARP_CUDA(cudaMemcpyAsync(buf->samples_orig, samples_orig, (size_t)S * C * D * sizeof(real), kd, st));
+    if (buf->is_accepted) ARP_CUDA(cudaMemcpyAsync(buf->is_accepted, is_acc, (size_t)S * C, kd, st));
+  }
+  if (buf->final_z && final_z_dev) ARP_CUDA(cudaMemcpyAsync(buf->final_z, final_z_dev, (size_t)C * D * sizeof(real), kd, st));
+  if (buf->step_mult) ARP_CUDA(cudaMemcpyAsync(buf->step_mult, out_mult_dev, C * sizeof(real), kd, st));
+  if (buf->accept_count) ARP_CUDA(cudaMemcpyAsync(buf->accept_count, out_nacc_dev, C * sizeof(int), kd, st));
+  ARP_CUDA(cudaStreamSynchronize(st));  // workspace is freed on return
+  return 0;
+}
+
+// ------------------------------------------------------------------------ ESS ---
+extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* ess, int mem, void* stream) {
+  if (!samples || !ess || S < 2 || C <= 0 || D <= 0) return fail("arp_ess: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DevBuf din, dout;
+  const real* in = samples;
+  real* out = ess;
+  const size_t n = (size_t)C * D;
+  if (mem == ARP_MEM_HOST) {
+    if (stage_in(din, samples, (size_t)S * n * sizeof(real), mem, st)) return 1;
+    ARP_CUDA(dout.alloc(n * sizeof(real)));
+    in = din.as<real>(); out = dout.as<real>();
+  }
+  k_ess<<<(unsigned)((n + ARP_ESS_BLOCK - 1) / ARP_ESS_BLOCK), ARP_ESS_BLOCK, 0, st>>>(in, (int)S, (long long)n, out);
+  ARP_LAUNCH_CHECK();
+  if (mem == ARP_MEM_HOST) ARP_CUDA(cudaMemcpyAsync(ess, out, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+  ARP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------- VI ---
+extern "C" int arp_vi_run(arp_model* m, const arp_vi_config* cfg, const arp_real* a, const arp_real* b,
+                          const arp_vi_buffers* buf, int mem, void* stream) {
+  if (!m || !cfg || !a || !b || !buf || !buf->loc || !buf->rho || !buf->elbo) return fail("arp_vi_run: bad argument");
+  if (cfg->learn_a && !buf->a_logit) return fail("arp_vi_run: learn_a needs a_logit");
+  if (cfg->num_mc_samples < 1 || cfg->num_mc_samples > ARP_VI_MAX_S || cfg->num_optimization_steps < 1)
+    return fail("arp_vi_run: num_mc_samples must be in [1, " + std::to_string(ARP_VI_MAX_S) + "]");
+  if (cfg->num_runs < 1 || cfg->num_runs > ARP_VI_MAX_RUNS) return fail("arp_vi_run: num_runs out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->dev.D, R = cfg->num_runs;
+  const int S = cfg->num_mc_samples, steps = cfg->num_optimization_steps;
+  const bool host = mem == ARP_MEM_HOST;
+  DevBuf da, db, dloc, drho, dal, deps, delbo, dws;
+  if (stage_in(da, a, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  if (stage_in(db, b, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  real *loc = buf->loc, *rho = buf->rho, *al = buf->a_logit, *elbo = buf->elbo;
+  const real* eps = buf->ext_eps;
+  const size_t pbytes = (size_t)R * D * sizeof(real);
+  if (host) {
+    if (stage_in(dloc, loc, pbytes, mem, st)) return 1;
+    if (stage_in(drho, rho, pbytes, mem, st)) return 1;
+    loc = dloc.as<real>(); rho = drho.as<real>();
+    if (cfg->learn_a) { if (stage_in(dal, al, pbytes, mem, st)) return 1; al = dal.as<real>(); }
+    if (eps) { if (stage_in(deps, eps, (size_t)steps * S * D * sizeof(real), mem, st)) return 1; eps = deps.as<real>(); }
+    ARP_CUDA(delbo.alloc((size_t)R * steps * sizeof(real)));
+    elbo = delbo.as<real>();
+  }
+  ViArgs v{};
+  v.D = D; v.S = S; v.steps = steps; v.R = R; v.seed = cfg->seed; v.learn_a = cfg->learn_a;
+  for (int r = 0; r < R; ++r) v.lrs[r] = (real)cfg->learning_rates[r];
+  v.loc = loc; v.rho = rho; v.a_logit = al; v.ext_eps = eps; v.elbo = elbo;
+  v.a_in = da.as<real>(); v.b_in = db.as<real>();
+  int rc = vi_launch(m->dev, m->fp, v, st, &dws, &g_launches, &g_last_error);
+  if (rc) return rc;
+  if (host) {
+    ARP_CUDA(cudaMemcpyAsync(buf->loc, loc, pbytes, cudaMemcpyDeviceToHost, st));
+    ARP_CUDA(cudaMemcpyAsync(buf->rho, rho, pbytes, cudaMemcpyDeviceToHost, st));
+    if (cfg->learn_a) ARP_CUDA(cudaMemcpyAsync(buf->a_logit, al, pbytes, cudaMemcpyDeviceToHost, st));
+    ARP_CUDA(cudaMemcpyAsync(buf->elbo, elbo, (size_t)R * steps * sizeof(real), cudaMemcpyDeviceToHost, st));
+  }
+  ARP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}

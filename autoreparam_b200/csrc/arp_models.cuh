@@ -1,0 +1,538 @@
+// Per-model log-joint + hand-derived adjoint under the (a, b) site rule.
+//
+// Every function evaluates ONE chain cooperatively on LPC consecutive lanes of a
+// warp (LPC = 1 .. 32): per-site / per-observation loops are strided over the
+// lanes, cross-lane sums are xor-butterflies (so every lane of the group ends up
+// with bit-identical scalars), and the state vectors live in (L1/L2-cached)
+// global memory behind a strided accessor.
+//
+//   lp = vg<KIND, LPC, WITH_A, FP>(m, a, b, z, g, xc, abar, sub, want_lp)
+//     z     in   state coordinates (trace order)
+//     g     out  d log_joint / d z
+//     xc    out  centred value of every coordinate (= make_to_centered(z),
+//                reference models.py:59-81); also used as scratch between lanes
+//     abar  out  d log_joint / d a per coordinate (only if WITH_A; cVIP VI)
+//     returns log_joint (valid only if want_lp; the gradient never needs it)
+//
+// Model bodies follow reference models.py (line ranges per function) with the
+// group look-ups done as gathers / segmented sums instead of the reference's
+// dense one-hot matmuls.
+#pragma once
+#include "arp_common.cuh"
+
+namespace arp {
+
+enum ModelKind {
+  MODEL_8SCHOOLS = 0,
+  MODEL_GERMAN_LOGNORMAL = 1,
+  MODEL_GERMAN_GAMMA = 2,
+  MODEL_RADON = 3,
+  MODEL_RADON_STDDVS = 4,
+  MODEL_ELECTION = 5,
+  MODEL_ELECTRIC = 6,
+  MODEL_TIME_SERIES = 7,
+  MODEL_COUNT = 8
+};
+
+// Device-resident model data (all pointers are device pointers owned by arp_model).
+struct DevModel {
+  int kind;
+  int D;     // number of state coordinates
+  int N;     // observations (election: weighted cells)
+  int F;     // german: features
+  int Fpad;  // german: row stride of X (multiple of 4, zero padded)
+  int J;     // groups: radon counties | election states (+1 NONE group) | electric pairs (+1 NONE)
+  int K;     // election: n_state | electric: n_pair | time series: T
+  const real* X;    // german [N][Fpad]
+  const real* y;    // observations (election: sum of y per cell)
+  const real* x1;   // radon floor | election female | electric treatment | time_series year | 8schools sigma
+  const real* x2;   // election black
+  const real* w;    // election: cell count
+  const real* u;    // radon: log uranium [J]
+  const int* offs;  // CSR offsets of the groups into the (sorted) observations [J+1]
+  const int* gidx;  // electric: grade index per observation (-1 = one-hot out of range)
+  const int* pidx;  // electric: grade_pair index per pair (-1 = out of range)
+};
+
+template <typename T>
+__device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+
+// ------------------------------------------------------------- 8 schools ---
+// reference models.py:139-147.  z = [mu, log_tau, theta[8]]
+template <int LPC, bool WITH_A>
+__device__ real vg_8schools(const DevModel& m, const real* a, const real* b,
+                            Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+  real lp_top = 0;
+  const real a0 = (*(a + 0)), b0 = (*(b + 0)), a1 = (*(a + 1)), b1 = (*(b + 1));
+  Site smu = site_fwd(z(0), (real)0, ARP_LOG_5, a0, b0, lp_top);
+  Site slt = site_fwd(z(1), (real)0, ARP_LOG_5, a1, b1, lp_top);
+  const real mu = smu.x, lt = slt.x;
+  real lp = 0, acc_mu = 0, acc_lt = 0;
+  for (int i = sub; i < 8; i += LPC) {
+    const real ai = (*(a + 2 + i)), bi = (*(b + 2 + i));
+    Site st = site_fwd(z(2 + i), mu, lt, ai, bi, lp);
+    const real sig = ldg(m.x1 + i);
+    const real e = (ldg(m.y + i) - st.x) / sig;
+    lp += (real)-0.5 * e * e - r_log(sig) - ARP_HALF_LOG_2PI;
+    real zb, mb, lb, ab;
+    site_rev(st, e / sig, mu, ai, bi, zb, mb, lb, ab);
+    g(2 + i) = zb;
+    xc(2 + i) = st.x;
+    if (WITH_A) abar(2 + i) = ab;
+    acc_mu += mb;
+    acc_lt += lb;
+  }
+  acc_mu = group_sum<LPC>(acc_mu);
+  acc_lt = group_sum<LPC>(acc_lt);
+  lp = group_sum<LPC>(lp) + lp_top;
+  if (sub == 0) {
+    real zb, mb, lb, ab;
+    site_rev(smu, acc_mu, (real)0, a0, b0, zb, mb, lb, ab);
+    g(0) = zb;
+    xc(0) = mu;
+    site_rev(slt, acc_lt, (real)0, a1, b1, zb, mb, lb, ab);
+    g(1) = zb;
+    xc(1) = lt;
+    if (WITH_A) { abar(0) = 0; abar(1) = 0; }
+  }
+  return lp;
+}
+
+// ---------------------------------------------------------- German credit ---
+// Bernoulli-logit likelihood over the design matrix: eta = X beta,
+// r = y - sigmoid(eta), gbeta = X^T r  (reference models.py:903-904 einsum +
+// ed.Bernoulli; autodiff gives X^T r).  beta is read from xc(beta_off + f);
+// the reduced gradient is left in g(beta_off + f).  FP = padded feature count
+// held in registers.
+template <int LPC, int FP>
+__device__ real german_likelihood(const DevModel& m, Vec xc, Vec g, int beta_off, int sub, bool want_lp) {
+  real be[FP], gb[FP];
+#pragma unroll
+  for (int f = 0; f < FP; ++f) {
+    be[f] = (f < m.F) ? xc(beta_off + f) : (real)0;
+    gb[f] = 0;
+  }
+  real lp = 0;
+  const real* __restrict__ X = m.X;
+  const real* __restrict__ y = m.y;
+#pragma unroll 2
+  for (int n = sub; n < m.N; n += LPC) {
+    const real* row = X + (size_t)n * FP;
+    real xr[FP];
+#if ARP_REAL_IS_DOUBLE
+#pragma unroll
+    for (int f = 0; f < FP; f += 2) {
+      double2 v = __ldg(reinterpret_cast<const double2*>(row + f));
+      xr[f] = v.x; xr[f + 1] = v.y;
+    }
+#else
+#pragma unroll
+    for (int f = 0; f < FP; f += 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(row + f));
+      xr[f] = v.x; xr[f + 1] = v.y; xr[f + 2] = v.z; xr[f + 3] = v.w;
+    }
+#endif
+    real e0 = 0, e1 = 0;
+#pragma unroll
+    for (int f = 0; f < FP; f += 2) {
+      e0 = fma(xr[f], be[f], e0);
+      e1 = fma(xr[f + 1], be[f + 1], e1);
+    }
+    const real eta = e0 + e1;
+    const real yn = ldg(y + n);
+    const real r = yn - r_sigmoid(eta);
+    if (want_lp) lp += yn * eta - r_softplus(eta);
+#pragma unroll
+    for (int f = 0; f < FP; ++f) gb[f] = fma(xr[f], r, gb[f]);
+  }
+#pragma unroll
+  for (int f = 0; f < FP; ++f) {
+    real v = group_sum<LPC>(gb[f]);
+    if ((f % LPC) == sub && f < m.F) g(beta_off + f) = v;
+  }
+  return group_sum<LPC>(lp);
+}
+
+// reference models.py:888-904 (lognormalcentered) and :930-945 (gammascale).
+// z = [overall_log_scale, beta_log_scales[F], beta[F]]
+template <int LPC, bool WITH_A, int FP, bool GAMMA>
+__device__ real vg_german(const DevModel& m, const real* a, const real* b,
+                          Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+  const int F = m.F;
+  real lp_top = 0;
+  const real a0 = (*a), b0 = (*b);
+  Site s0 = site_fwd(z(0), (real)0, ARP_LOG_10, a0, b0, lp_top);
+  const real s0x = s0.x;
+  real lp = 0;
+  // forward: centred log-scales and coefficients
+  for (int f = sub; f < F; f += LPC) {
+    real dummy = 0;
+    real ls;
+    if (GAMMA) {
+      const real v = z(1 + f);
+      ls = s0x + v;
+      xc(1 + f) = v;
+    } else {
+      Site ss = site_fwd_unit(z(1 + f), s0x, (*(a + 1 + f)), dummy);
+      ls = ss.x;
+      xc(1 + f) = ls;
+    }
+    Site sb = site_fwd(z(1 + F + f), (real)0, ls, (*(a + 1 + F + f)), (*(b + 1 + F + f)), dummy);
+    xc(1 + F + f) = sb.x;
+  }
+  __syncwarp();
+  lp = german_likelihood<LPC, FP>(m, xc, g, 1 + F, sub, want_lp);
+  // reverse through beta -> log-scales -> overall scale
+  real acc0 = 0, lp_sites = 0;
+  for (int f = sub; f < F; f += LPC) {
+    const real af = (*(a + 1 + f)), ab_ = (*(a + 1 + F + f)), bb_ = (*(b + 1 + F + f));
+    real zb, mb, lb, ab;
+    if (GAMMA) {
+      const real v = z(1 + f);
+      const real ls = s0x + v;
+      Site sb = site_fwd(z(1 + F + f), (real)0, ls, ab_, bb_, lp_sites);
+      site_rev(sb, g(1 + F + f), (real)0, ab_, bb_, zb, mb, lb, ab);
+      g(1 + F + f) = zb;
+      if (WITH_A) { abar(1 + F + f) = 0; abar(1 + f) = 0; }
+      // log Gamma(1/2, 1/2) density of v: 0.5 v - 0.5 e^v + 0.5 log 0.5 - lgamma(0.5)
+      const real ev = r_exp(v);
+      lp_sites += (real)0.5 * v - (real)0.5 * ev + (real)(-0.34657359027997264 - 0.57236494292470008);
+      g(1 + f) = (real)0.5 - (real)0.5 * ev + lb;
+      acc0 += lb;
+    } else {
+      Site ss = site_fwd_unit(z(1 + f), s0x, af, lp_sites);
+      Site sb = site_fwd(z(1 + F + f), (real)0, ss.x, ab_, bb_, lp_sites);
+      site_rev(sb, g(1 + F + f), (real)0, ab_, bb_, zb, mb, lb, ab);
+      g(1 + F + f) = zb;
+      if (WITH_A) abar(1 + F + f) = 0;
+      real zb2, mb2, lb2, ab2;
+      site_rev(ss, lb, s0x, af, (real)1, zb2, mb2, lb2, ab2);
+      g(1 + f) = zb2;
+      if (WITH_A) abar(1 + f) = ab2;
+      acc0 += mb2;
+    }
+  }
+  acc0 = group_sum<LPC>(acc0);
+  lp += group_sum<LPC>(lp_sites) + lp_top;
+  if (sub == 0) {
+    real zb, mb, lb, ab;
+    site_rev(s0, acc0, (real)0, a0, b0, zb, mb, lb, ab);
+    g(0) = zb;
+    xc(0) = s0x;
+    if (WITH_A) abar(0) = 0;
+  }
+  return lp;
+}
+
+// ------------------------------------------------------------------ radon ---
+// reference models.py:826-837 (sigma_y = 1) and :772-788 (per-county scales).
+// z = [mua, b1, b2, m[J]] (+ log_m_stddv[J]); observations sorted by county, CSR.
+template <int LPC, bool WITH_A, bool STDDVS>
+__device__ real vg_radon(const DevModel& m, const real* a, const real* b,
+                         Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+  const int J = m.J;
+  real lp_top = 0;
+  const real a0 = (*a), a1 = (*(a + 1)), a2 = (*(a + 2));
+  Site smua = site_fwd_unit(z(0), (real)0, a0, lp_top);
+  Site sb1 = site_fwd_unit(z(1), (real)0, a1, lp_top);
+  Site sb2 = site_fwd_unit(z(2), (real)0, a2, lp_top);
+  const real mua = smua.x, b1 = sb1.x, b2 = sb2.x;
+  real lp = 0, acc_mua = 0, acc_b1 = 0, acc_b2 = 0;
+  for (int j = sub; j < J; j += LPC) {
+    const real uj = ldg(m.u + j);
+    const real mu_j = mua + uj * b1;
+    const real aj = (*(a + 3 + j));
+    Site sm = site_fwd_unit(z(3 + j), mu_j, aj, lp);
+    const real mj = sm.x;
+    real lsj = 0, inv = 1, inv2 = 1;
+    Site sl;
+    if (STDDVS) {
+      sl = site_fwd_unit(z(3 + J + j), (real)0, (*(a + 3 + J + j)), lp);
+      lsj = sl.x;
+      inv = r_exp(-lsj);
+      inv2 = inv * inv;
+    }
+    const int n0 = ldg(m.offs + j), n1 = ldg(m.offs + j + 1);
+    real se = 0, sex = 0, see = 0;
+    for (int n = n0; n < n1; ++n) {
+      const real xn = ldg(m.x1 + n);
+      const real e = ldg(m.y + n) - mj - xn * b2;
+      se += e;
+      sex = fma(e, xn, sex);
+      see = fma(e, e, see);
+    }
+    const real cnt = (real)(n1 - n0);
+    lp += (real)-0.5 * see * inv2 - cnt * (lsj + ARP_HALF_LOG_2PI);
+    acc_b2 += sex * inv2;
+    real zb, mb, lb, ab;
+    site_rev(sm, se * inv2, mu_j, aj, (real)1, zb, mb, lb, ab);
+    g(3 + j) = zb;
+    xc(3 + j) = mj;
+    if (WITH_A) abar(3 + j) = ab;
+    acc_mua += mb;
+    acc_b1 += uj * mb;
+    if (STDDVS) {
+      site_rev(sl, see * inv2 - cnt, (real)0, (real)0, (real)1, zb, mb, lb, ab);
+      g(3 + J + j) = zb;
+      xc(3 + J + j) = lsj;
+      if (WITH_A) abar(3 + J + j) = 0;
+    }
+  }
+  acc_mua = group_sum<LPC>(acc_mua);
+  acc_b1 = group_sum<LPC>(acc_b1);
+  acc_b2 = group_sum<LPC>(acc_b2);
+  lp = group_sum<LPC>(lp) + lp_top;
+  if (sub == 0) {
+    real zb, mb, lb, ab;
+    site_rev(smua, acc_mua, (real)0, a0, (real)1, zb, mb, lb, ab);
+    g(0) = zb; xc(0) = mua;
+    site_rev(sb1, acc_b1, (real)0, a1, (real)1, zb, mb, lb, ab);
+    g(1) = zb; xc(1) = b1;
+    site_rev(sb2, acc_b2, (real)0, a2, (real)1, zb, mb, lb, ab);
+    g(2) = zb; xc(2) = b2;
+    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(2) = 0; }
+  }
+  return lp;
+}
+
+// --------------------------------------------------------------- election ---
+// reference models.py:969-982.  z = [mua, log_sigma_a, a[K], b1, b2].
+// Observations are grouped by the one-hot index of `state` (group K = "no
+// column hit", reference feeds 1-based indices to tf.one_hot(depth=K)) and
+// identical (group, female, black) rows are merged into weighted cells
+// (w = count, y = sum of y): sum over equal-eta observations, exact.
+template <int LPC, bool WITH_A>
+__device__ real vg_election(const DevModel& m, const real* a, const real* b,
+                            Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+  const int K = m.K;
+  real lp_top = 0;
+  const real a0 = (*a), b0 = (*b), a1 = (*(a + 1)), bb1 = (*(b + 1));
+  const real a3 = (*(a + 2 + K)), b3 = (*(b + 2 + K)), a4 = (*(a + 3 + K)), b4 = (*(b + 3 + K));
+  Site smua = site_fwd(z(0), (real)0, ARP_LOG_100, a0, b0, lp_top);
+  Site slsa = site_fwd(z(1), (real)0, ARP_LOG_10, a1, bb1, lp_top);
+  Site sb1 = site_fwd(z(2 + K), (real)0, ARP_LOG_100, a3, b3, lp_top);
+  Site sb2 = site_fwd(z(3 + K), (real)0, ARP_LOG_100, a4, b4, lp_top);
+  const real mua = smua.x, lsa = slsa.x, b1 = sb1.x, b2 = sb2.x;
+  real lp = 0, acc_mua = 0, acc_lsa = 0, acc_b1 = 0, acc_b2 = 0;
+  for (int k = sub; k < m.J; k += LPC) {
+    real ak = 0, aa = 0, ba = 0;
+    Site sa;
+    if (k < K) {
+      aa = (*(a + 2 + k));
+      ba = (*(b + 2 + k));
+      sa = site_fwd(z(2 + k), mua, lsa, aa, ba, lp);
+      ak = sa.x;
+    }
+    const int c0 = ldg(m.offs + k), c1 = ldg(m.offs + k + 1);
+    real abar_k = 0;
+    for (int c = c0; c < c1; ++c) {
+      const real fe = ldg(m.x1 + c), bl = ldg(m.x2 + c), w = ldg(m.w + c), ys = ldg(m.y + c);
+      const real eta = ak + fe * b2 + bl * b1;
+      const real r = ys - w * r_sigmoid(eta);
+      if (want_lp) lp += ys * eta - w * r_softplus(eta);
+      abar_k += r;
+      acc_b2 = fma(fe, r, acc_b2);
+      acc_b1 = fma(bl, r, acc_b1);
+    }
+    if (k < K) {
+      real zb, mb, lb, ab;
+      site_rev(sa, abar_k, mua, aa, ba, zb, mb, lb, ab);
+      g(2 + k) = zb;
+      xc(2 + k) = ak;
+      if (WITH_A) abar(2 + k) = ab;
+      acc_mua += mb;
+      acc_lsa += lb;
+    }
+  }
+  acc_mua = group_sum<LPC>(acc_mua);
+  acc_lsa = group_sum<LPC>(acc_lsa);
+  acc_b1 = group_sum<LPC>(acc_b1);
+  acc_b2 = group_sum<LPC>(acc_b2);
+  lp = group_sum<LPC>(lp) + lp_top;
+  if (sub == 0) {
+    real zb, mb, lb, ab;
+    site_rev(smua, acc_mua, (real)0, a0, b0, zb, mb, lb, ab);
+    g(0) = zb; xc(0) = mua;
+    site_rev(slsa, acc_lsa, (real)0, a1, bb1, zb, mb, lb, ab);
+    g(1) = zb; xc(1) = lsa;
+    site_rev(sb1, acc_b1, (real)0, a3, b3, zb, mb, lb, ab);
+    g(2 + K) = zb; xc(2 + K) = b1;
+    site_rev(sb2, acc_b2, (real)0, a4, b4, zb, mb, lb, ab);
+    g(3 + K) = zb; xc(3 + K) = b2;
+    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(2 + K) = 0; abar(3 + K) = 0; }
+  }
+  return lp;
+}
+
+// --------------------------------------------------------------- electric ---
+// reference models.py:1013-1035.  z = [mua[4], sigma_y[4], a[K=96], b[4]];
+// observations grouped by pair index (group K = out of range); grade /
+// grade_pair indices are -1 where the reference's one-hot row is all zero.
+template <int LPC, bool WITH_A>
+__device__ real vg_electric(const DevModel& m, const real* a, const real* b,
+                            Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+  const int K = m.K;
+  const int oB = 8 + K;
+  real lp_top = 0;
+  real mua[4], sy[4], bx[4];
+  Site s_mua[4], s_sy[4], s_b[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    s_mua[q] = site_fwd_unit(z(q), (real)0, (*(a + q)), lp_top);
+    s_sy[q] = site_fwd_unit(z(4 + q), (real)0, (*(a + 4 + q)), lp_top);
+    s_b[q] = site_fwd(z(oB + q), (real)0, ARP_LOG_100, (*(a + oB + q)), (*(b + oB + q)), lp_top);
+    mua[q] = s_mua[q].x; sy[q] = s_sy[q].x; bx[q] = s_b[q].x;
+  }
+  real lp = 0;
+  real acc_mua[4] = {0, 0, 0, 0}, acc_sy[4] = {0, 0, 0, 0}, acc_b[4] = {0, 0, 0, 0};
+  for (int p = sub; p < m.J; p += LPC) {
+    real ap = 0, ap_a = 0, mu_p = 0;
+    int gp = -1;
+    Site sa;
+    if (p < K) {
+      gp = ldg(m.pidx + p);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (gp == q) mu_p = (real)100 * mua[q];
+      ap_a = (*(a + 8 + p));
+      sa = site_fwd_unit(z(8 + p), mu_p, ap_a, lp);
+      ap = sa.x;
+    }
+    const int n0 = ldg(m.offs + p), n1 = ldg(m.offs + p + 1);
+    real abar_p = 0;
+    for (int n = n0; n < n1; ++n) {
+      const int gi = ldg(m.gidx + n);
+      real bb = 0, lsy = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (gi == q) { bb = bx[q]; lsy = sy[q]; }
+      const real tr = ldg(m.x1 + n);
+      const real inv = r_exp(-lsy);
+      const real e = (ldg(m.y + n) - ap - bb * tr) * inv;
+      lp += (real)-0.5 * e * e - lsy - ARP_HALF_LOG_2PI;
+      const real eb = e * inv;
+      abar_p += eb;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (gi == q) { acc_b[q] = fma(eb, tr, acc_b[q]); acc_sy[q] += e * e - (real)1; }
+    }
+    if (p < K) {
+      real zb, mb, lb, ab;
+      site_rev(sa, abar_p, mu_p, ap_a, (real)1, zb, mb, lb, ab);
+      g(8 + p) = zb;
+      xc(8 + p) = ap;
+      if (WITH_A) abar(8 + p) = ab;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (gp == q) acc_mua[q] += (real)100 * mb;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    acc_mua[q] = group_sum<LPC>(acc_mua[q]);
+    acc_sy[q] = group_sum<LPC>(acc_sy[q]);
+    acc_b[q] = group_sum<LPC>(acc_b[q]);
+  }
+  lp = group_sum<LPC>(lp) + lp_top;
+  if (sub == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      real zb, mb, lb, ab;
+      site_rev(s_mua[q], acc_mua[q], (real)0, (*(a + q)), (real)1, zb, mb, lb, ab);
+      g(q) = zb; xc(q) = mua[q];
+      site_rev(s_sy[q], acc_sy[q], (real)0, (*(a + 4 + q)), (real)1, zb, mb, lb, ab);
+      g(4 + q) = zb; xc(4 + q) = sy[q];
+      site_rev(s_b[q], acc_b[q], (real)0, (*(a + oB + q)), (*(b + oB + q)), zb, mb, lb, ab);
+      g(oB + q) = zb; xc(oB + q) = bx[q];
+      if (WITH_A) { abar(q) = 0; abar(4 + q) = 0; abar(oB + q) = 0; }
+    }
+  }
+  return lp;
+}
+
+// ------------------------------------------------------------ time series ---
+// reference models.py:1071-1096.  z = [sigma_alpha, sigma_mu, alpha0, mu0,
+// alpha1, mu1, ..., alpha_{T-1}, mu_{T-1}, beta]; local linear trend, forward
+// scan for the centred values and reverse scan for the adjoints.  The scan is
+// sequential per chain: with LPC > 1 every lane runs it redundantly and lane 0
+// writes.
+template <int LPC, bool WITH_A>
+__device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
+                               Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+  const int T = m.K;
+  const int oBeta = 2 + 2 * T;
+  const bool wr = (sub == 0);
+  real lp = 0;
+  Site s_sa = site_fwd_unit(z(0), (real)0, (*(a + 0)), lp);
+  Site s_sm = site_fwd_unit(z(1), (real)0, (*(a + 1)), lp);
+  Site s_be = site_fwd_unit(z(oBeta), (real)0, (*(a + oBeta)), lp);
+  const real sa = s_sa.x, sm = s_sm.x, be = s_be.x;
+  const real sig_a = r_softplus(sa), sig_m = r_softplus(sm);
+  const real lsa = r_log(sig_a), lsm = r_log(sig_m);
+  const real inv_obs = (real)(1.0 / 0.12);
+  const real log_obs = (real)-2.1202635362000910;  // log(0.12)
+  // forward scan
+  real al_prev = 0, mu_prev = 0;
+  for (int t = 0; t < T; ++t) {
+    const int ia = 2 + 2 * t, im = 3 + 2 * t;
+    Site s_al = site_fwd(z(ia), al_prev + mu_prev, lsa, (*(a + ia)), (*(b + ia)), lp);
+    Site s_mu = site_fwd(z(im), mu_prev, lsm, (*(a + im)), (*(b + im)), lp);
+    if (wr) { xc(ia) = s_al.x; xc(im) = s_mu.x; }
+    al_prev = s_al.x;
+    mu_prev = s_mu.x;
+    const real e = (ldg(m.y + t) - s_al.x - be * ldg(m.x1 + t)) * inv_obs;
+    lp += (real)-0.5 * e * e - log_obs - ARP_HALF_LOG_2PI;
+  }
+  __syncwarp();
+  // reverse scan
+  real carry_al = 0, carry_mu = 0, acc_lsa = 0, acc_lsm = 0, acc_be = 0;
+  for (int t = T - 1; t >= 0; --t) {
+    const int ia = 2 + 2 * t, im = 3 + 2 * t;
+    const real alp = (t > 0) ? xc(ia - 2) : (real)0;
+    const real mup = (t > 0) ? xc(im - 2) : (real)0;
+    const real aa = (*(a + ia)), ba = (*(b + ia)), am = (*(a + im)), bm = (*(b + im));
+    real dummy = 0;
+    Site s_al = site_fwd(z(ia), alp + mup, lsa, aa, ba, dummy);
+    Site s_mu = site_fwd(z(im), mup, lsm, am, bm, dummy);
+    const real xt = ldg(m.x1 + t);
+    const real e = (ldg(m.y + t) - s_al.x - be * xt) * inv_obs;
+    const real lik = e * inv_obs;
+    acc_be = fma(lik, xt, acc_be);
+    real zb, mb_al, lb, ab;
+    site_rev(s_al, lik + carry_al, alp + mup, aa, ba, zb, mb_al, lb, ab);
+    if (wr) { g(ia) = zb; if (WITH_A) abar(ia) = ab; }
+    acc_lsa += lb;
+    real mb_mu;
+    site_rev(s_mu, carry_mu, mup, am, bm, zb, mb_mu, lb, ab);
+    if (wr) { g(im) = zb; if (WITH_A) abar(im) = ab; }
+    acc_lsm += lb;
+    carry_al = mb_al;
+    carry_mu = mb_al + mb_mu;
+  }
+  if (wr) {
+    real zb, mb, lb, ab;
+    // d log softplus(s) / d s = sigmoid(s) / softplus(s)
+    const real dsa = ((real)1 / ((real)1 + r_exp(-sa))) / sig_a;
+    const real dsm = ((real)1 / ((real)1 + r_exp(-sm))) / sig_m;
+    site_rev(s_sa, acc_lsa * dsa, (real)0, (*(a + 0)), (real)1, zb, mb, lb, ab);
+    g(0) = zb; xc(0) = sa;
+    site_rev(s_sm, acc_lsm * dsm, (real)0, (*(a + 1)), (real)1, zb, mb, lb, ab);
+    g(1) = zb; xc(1) = sm;
+    site_rev(s_be, acc_be, (real)0, (*(a + oBeta)), (real)1, zb, mb, lb, ab);
+    g(oBeta) = zb; xc(oBeta) = be;
+    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(oBeta) = 0; }
+  }
+  return lp;
+}
+
+// --------------------------------------------------------------- dispatch ---
+template <int KIND, int LPC, bool WITH_A, int FP>
+__device__ __forceinline__ real vg(const DevModel& m, const real* a, const real* b,
+                                   Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+  if (KIND == MODEL_8SCHOOLS) return vg_8schools<LPC, WITH_A>(m, a, b, z, g, xc, abar, sub, want_lp);
+  if (KIND == MODEL_GERMAN_LOGNORMAL) return vg_german<LPC, WITH_A, FP, false>(m, a, b, z, g, xc, abar, sub, want_lp);
+  if (KIND == MODEL_GERMAN_GAMMA) return vg_german<LPC, WITH_A, FP, true>(m, a, b, z, g, xc, abar, sub, want_lp);
+  if (KIND == MODEL_RADON) return vg_radon<LPC, WITH_A, false>(m, a, b, z, g, xc, abar, sub, want_lp);
+  if (KIND == MODEL_RADON_STDDVS) return vg_radon<LPC, WITH_A, true>(m, a, b, z, g, xc, abar, sub, want_lp);
+  if (KIND == MODEL_ELECTION) return vg_election<LPC, WITH_A>(m, a, b, z, g, xc, abar, sub, want_lp);
+  if (KIND == MODEL_ELECTRIC) return vg_electric<LPC, WITH_A>(m, a, b, z, g, xc, abar, sub, want_lp);
+  return vg_time_series<LPC, WITH_A>(m, a, b, z, g, xc, abar, sub, want_lp);
+}
+
+}  // namespace arp

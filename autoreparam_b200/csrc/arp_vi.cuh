@@ -1,0 +1,207 @@
+// Fused mean-field VI: reparameterised sample -> ELBO gradient -> Adam, every
+// optimisation step of every learning rate in ONE persistent kernel launch.
+//
+// Replaces util.get_mean_field_elbo (reference util.py:232-268), the mean-field
+// guide of program_transformations.make_variational_model (:192-241: q = prod
+// N(loc, softplus(rho))) and the Adam loop of inference.find_best_learning_rate
+// (inference.py:26-154: TF1 Adam, lr/5 after 1/3 and lr/20 after 2/3 of the
+// steps, NaN gradients zeroed).  The reference crosses the host<->runtime
+// boundary once per step (sess.run, inference.py:93); here a CTA owns one
+// learning rate, a thread owns one Monte-Carlo sample, parameters and Adam
+// moments stay in shared memory, and nothing leaves the GPU until the end.
+//
+// ELBO = mean_s [ log_joint(z_s) + sum_d (eps^2/2 + log scale_d + log(2 pi)/2) ],
+// z_s = loc + scale * eps_s; gradients of -ELBO:
+//   d loc = -mean_s g_s          d scale = -mean_s g_s eps_s - 1/scale
+//   d rho = d scale * sigmoid(rho)   d a_logit = -mean_s abar_s * a (1 - a)
+#pragma once
+#include <atomic>
+#include <string>
+#include "arp_host.cuh"
+#include "arp_models.cuh"
+
+namespace arp {
+
+#define ARP_VI_MAX_S 4096
+#define ARP_VI_BLOCK 256
+#ifndef ARP_VI_MAX_RUNS
+#define ARP_VI_MAX_RUNS 16
+#endif
+
+struct ViArgs {
+  int D, S, steps, R;
+  int learn_a;
+  real lrs[ARP_VI_MAX_RUNS];
+  unsigned long long seed;
+  real* loc;            // [R, D] in/out
+  real* rho;            // [R, D] in/out
+  real* a_logit;        // [R, D] in/out (learn_a)
+  const real* ext_eps;  // [steps, S, D] or null (shared by all runs)
+  real* elbo;           // [R, steps]
+  const real* a_in;     // [D]
+  const real* b_in;     // [D]
+};
+
+__device__ __forceinline__ void adam_update(real& theta, real grad, real& m1, real& m2, real lr_t) {
+  if (grad != grad) grad = 0;  // inference.py:62 remove_nans
+  m1 = (real)0.9 * m1 + (real)0.1 * grad;
+  m2 = (real)0.999 * m2 + (real)0.001 * grad * grad;
+  theta -= lr_t * m1 / (r_sqrt(m2) + (real)1e-8);
+}
+
+template <int KIND, bool LEARN_A, int FP>
+__global__ void __launch_bounds__(ARP_VI_BLOCK)
+k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
+  extern __shared__ unsigned char smem_raw[];
+  real* sm = reinterpret_cast<real*>(smem_raw);
+  const int D = v.D, S = v.S, nthr = blockDim.x;  // Spad = samples rounded up to a multiple of nthr
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int run = blockIdx.x;
+  real* loc = sm;          real* rho = loc + D;    real* ul = rho + D;
+  real* scale = ul + D;    real* a_s = scale + D;  real* b_s = a_s + D;
+  real* gl = b_s + D;      real* gs = gl + D;      real* ga = gs + D;
+  real* mom = ga + D;      // [6][D] Adam first/second moments of loc, rho, a_logit
+  real* red = mom + 6 * D; // [32] block-reduction scratch
+  real* ws = ws_all + (size_t)run * 5 * D * Spad;
+  for (int d = tid; d < D; d += nthr) {
+    loc[d] = v.loc[(size_t)run * D + d];
+    rho[d] = v.rho[(size_t)run * D + d];
+    ul[d] = LEARN_A ? v.a_logit[(size_t)run * D + d] : (real)0;
+    b_s[d] = v.b_in[d];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) mom[q * D + d] = 0;
+  }
+  const real base_lr = v.lrs[run];
+  __syncthreads();
+  for (int step = 0; step < v.steps; ++step) {
+    for (int d = tid; d < D; d += nthr) {
+      scale[d] = r_softplus(rho[d]);
+      a_s[d] = LEARN_A ? (real)1 / ((real)1 + r_exp(-ul[d])) : v.a_in[d];
+    }
+    __syncthreads();
+    // ---- reparameterised samples: thread tid owns samples tid, tid + nthr, ...
+    real el = 0;
+    for (int smp = tid; smp < Spad; smp += nthr) {
+      const bool live = smp < S;
+      Vec Z{ws + smp, Spad}, G{ws + (size_t)D * Spad + smp, Spad}, XC{ws + (size_t)2 * D * Spad + smp, Spad};
+      Vec AB{ws + (size_t)3 * D * Spad + smp, Spad}, E{ws + (size_t)4 * D * Spad + smp, Spad};
+      real ent = 0;
+      if (v.ext_eps) {
+        const real* e = v.ext_eps + ((size_t)step * S + (live ? smp : 0)) * D;
+        for (int d = 0; d < D; ++d) {
+          const real ee = live ? e[d] : (real)0;
+          E(d) = ee;
+          Z(d) = loc[d] + scale[d] * ee;
+          ent += (real)0.5 * ee * ee + r_log(scale[d]) + ARP_HALF_LOG_2PI;
+        }
+      } else {
+        const int nb = (D + 3) >> 2;
+        for (int j = 0; j < nb; ++j) {
+          real n4[4];
+          philox_normal4(v.seed, (unsigned int)smp, (unsigned int)step, (unsigned int)j, ARP_STREAM_VI, n4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int d = 4 * j + q;
+            if (d < D) {
+              E(d) = n4[q];
+              Z(d) = loc[d] + scale[d] * n4[q];
+              ent += (real)0.5 * n4[q] * n4[q] + r_log(scale[d]) + ARP_HALF_LOG_2PI;
+            }
+          }
+        }
+      }
+      const real lp = vg<KIND, 1, LEARN_A, FP>(m, a_s, b_s, Z, G, XC, AB, 0, true);
+      if (live) el += lp + ent;
+    }
+    // ---- ELBO: block sum
+    el = group_sum<32>(el);
+    if (lane == 0) red[warp] = el;
+    __syncthreads();  // also publishes G / E / AB of every sample to the block
+    if (tid == 0) {
+      real tot = 0;
+      for (int w = 0; w < nwarp; ++w) tot += red[w];
+      v.elbo[(size_t)run * v.steps + step] = tot / (real)S;
+    }
+    // ---- gradient sums over the S samples: one warp per coordinate
+    for (int d = warp; d < D; d += nwarp) {
+      const real* gd = ws + (size_t)D * Spad + (size_t)d * Spad;
+      const real* ed = ws + (size_t)4 * D * Spad + (size_t)d * Spad;
+      const real* ad = ws + (size_t)3 * D * Spad + (size_t)d * Spad;
+      real s_l = 0, s_s = 0, s_a = 0;
+      for (int s = lane; s < S; s += 32) {
+        const real gg = gd[s];
+        s_l += gg;
+        s_s = fma(gg, ed[s], s_s);
+        if (LEARN_A) s_a += ad[s];
+      }
+      s_l = group_sum<32>(s_l);
+      s_s = group_sum<32>(s_s);
+      if (LEARN_A) s_a = group_sum<32>(s_a);
+      if (lane == 0) { gl[d] = s_l; gs[d] = s_s; ga[d] = s_a; }
+    }
+    __syncthreads();
+    // ---- Adam (TF1 formulation, inference.py:47) with the reference's lr schedule (:69-75)
+    real lr = base_lr;
+    if (3LL * step > 2LL * v.steps) lr = base_lr / (real)20;
+    else if (3LL * step > (long long)v.steps) lr = base_lr / (real)5;
+    const double t = (double)(step + 1);
+    const real lr_t = (real)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+    const real inv_S = (real)1 / (real)S;
+    for (int d = tid; d < D; d += nthr) {
+      const real g_loc = -gl[d] * inv_S;
+      const real g_scale = -gs[d] * inv_S - (real)1 / scale[d];
+      const real sig_rho = (real)1 / ((real)1 + r_exp(-rho[d]));
+      adam_update(loc[d], g_loc, mom[d], mom[D + d], lr_t);
+      adam_update(rho[d], g_scale * sig_rho, mom[2 * D + d], mom[3 * D + d], lr_t);
+      if (LEARN_A) {
+        const real aa = a_s[d];
+        adam_update(ul[d], -ga[d] * inv_S * aa * ((real)1 - aa), mom[4 * D + d], mom[5 * D + d], lr_t);
+      }
+    }
+    __syncthreads();
+  }
+  for (int d = tid; d < D; d += nthr) {
+    v.loc[(size_t)run * D + d] = loc[d];
+    v.rho[(size_t)run * D + d] = rho[d];
+    if (LEARN_A) v.a_logit[(size_t)run * D + d] = ul[d];
+  }
+}
+
+static inline int vi_launch(const DevModel& dm, int fp, const ViArgs& v, cudaStream_t st, DevBuf* ws,
+                            std::atomic<long long>* launches, std::string* err) {
+  const int nthr = v.S >= ARP_VI_BLOCK ? ARP_VI_BLOCK : (v.S + 31) / 32 * 32;
+  const int Spad = (v.S + nthr - 1) / nthr * nthr;
+  const size_t ws_bytes = (size_t)v.R * 5 * v.D * Spad * sizeof(real);
+  cudaError_t e = ws->alloc(ws_bytes);
+  if (e != cudaSuccess) { *err = std::string("vi workspace: ") + cudaGetErrorString(e); return 1; }
+  cudaMemsetAsync(ws->p, 0, ws_bytes, st);
+  const size_t smem = (size_t)(15 * v.D + 32) * sizeof(real);
+  if (smem > 200 * 1024) { *err = "vi: model too large for the shared-memory parameter block"; return 1; }
+#define ARP_VI_GO(KIND, FP)                                                                              \
+  do {                                                                                                   \
+    if (v.learn_a) {                                                                                     \
+      cudaFuncSetAttribute(k_vi<KIND, true, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      k_vi<KIND, true, FP><<<v.R, nthr, smem, st>>>(dm, v, ws->as<real>(), Spad);                              \
+    } else {                                                                                             \
+      cudaFuncSetAttribute(k_vi<KIND, false, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      k_vi<KIND, false, FP><<<v.R, nthr, smem, st>>>(dm, v, ws->as<real>(), Spad);                             \
+    }                                                                                                    \
+  } while (0)
+  switch (dm.kind) {
+    case MODEL_8SCHOOLS: ARP_VI_GO(MODEL_8SCHOOLS, 32); break;
+    case MODEL_GERMAN_LOGNORMAL: if (fp == 32) ARP_VI_GO(MODEL_GERMAN_LOGNORMAL, 32); else ARP_VI_GO(MODEL_GERMAN_LOGNORMAL, 64); break;
+    case MODEL_GERMAN_GAMMA: if (fp == 32) ARP_VI_GO(MODEL_GERMAN_GAMMA, 32); else ARP_VI_GO(MODEL_GERMAN_GAMMA, 64); break;
+    case MODEL_RADON: ARP_VI_GO(MODEL_RADON, 32); break;
+    case MODEL_RADON_STDDVS: ARP_VI_GO(MODEL_RADON_STDDVS, 32); break;
+    case MODEL_ELECTION: ARP_VI_GO(MODEL_ELECTION, 32); break;
+    case MODEL_ELECTRIC: ARP_VI_GO(MODEL_ELECTRIC, 32); break;
+    default: ARP_VI_GO(MODEL_TIME_SERIES, 32); break;
+  }
+#undef ARP_VI_GO
+  launches->fetch_add(1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("k_vi launch: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+}  // namespace arp

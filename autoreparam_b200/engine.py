@@ -1,0 +1,190 @@
+"""Thin Python layer over the C ABI: numpy (host buffers) or torch.cuda tensors
+(device buffers, current torch stream).  No arithmetic happens here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+
+
+def _is_torch(x):
+    return x is not None and type(x).__module__.startswith("torch")
+
+
+def _np(x, dtype):
+    return None if x is None else np.ascontiguousarray(np.asarray(x, dtype=dtype))
+
+
+def _p(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return x.ctypes.data_as(C.c_void_p)
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _torch_dtype(precision):
+    import torch
+    return torch.float32 if precision == "f32" else torch.float64
+
+
+def log_joint_grad(model, z, a, b, precision="f32", want_abar=False):
+    """``z`` [C, D] -> (lp [C], grad [C, D], centered [C, D][, abar [C, D]])."""
+    lib = _lib.load(precision)
+    dt = _lib.np_dtype(precision)
+    a_h, b_h = _np(a, dt), _np(b, dt)
+    D = model.num_coords
+    assert a_h.shape == (D,) and b_h.shape == (D,)
+    if _is_torch(z):
+        import torch
+        z = z.contiguous()
+        assert z.dtype == _torch_dtype(precision) and z.is_cuda
+        Cn = z.shape[0]
+        lp = torch.empty(Cn, dtype=z.dtype, device=z.device)
+        g, xc = torch.empty_like(z), torch.empty_like(z)
+        ab = torch.empty_like(z) if want_abar else None
+        mem, st = _lib.ARP_MEM_DEVICE, _stream()
+    else:
+        z = _np(z, dt)
+        Cn = z.shape[0]
+        lp = np.empty(Cn, dtype=dt)
+        g, xc = np.empty_like(z), np.empty_like(z)
+        ab = np.empty_like(z) if want_abar else None
+        mem, st = _lib.ARP_MEM_HOST, None
+    assert z.shape == (Cn, D)
+    rc = lib.arp_log_joint_grad(model.handle(precision), _p(a_h), _p(b_h), _p(z), Cn, _p(lp), _p(g), _p(xc), _p(ab),
+                                mem, st)
+    _lib.check(lib, rc, "arp_log_joint_grad")
+    return (lp, g, xc, ab) if want_abar else (lp, g, xc)
+
+
+def hmc_num_transitions(num_results, num_burnin_steps, num_steps_between_results=1):
+    return 1 + num_burnin_steps + (1 + num_steps_between_results) * (num_results - 1)
+
+
+def hmc_run(model, z0, eps0, a, b, *, num_leapfrog_steps, num_results, num_burnin_steps, num_adaptation_steps,
+            num_steps_between_results=1, seed=0, chain_offset=0, target_accept_prob=0.75, ext_momenta=None,
+            ext_log_u=None, want_samples=True, want_orig=False, want_final=True, engine=ENGINE_AUTO,
+            lanes_per_chain=0, precision="f32", out=None):
+    """Run every transition of every chain in one launch (``arp_hmc_run``).
+
+    Host mode: numpy in, numpy out.  Device mode: ``z0`` is a torch.cuda tensor;
+    outputs are torch.cuda tensors (``out`` may carry preallocated ``samples`` /
+    ``is_accepted`` tensors to reuse across calls).
+    Returns a dict: samples [S,C,D] (centred), samples_orig, is_accepted [S,C] uint8,
+    final_z [C,D], step_mult [C], accept_count [C].
+    """
+    lib = _lib.load(precision)
+    dt = _lib.np_dtype(precision)
+    D = model.num_coords
+    cfg = _lib.HmcConfig(num_leapfrog_steps, num_results, num_burnin_steps, num_adaptation_steps,
+                         num_steps_between_results, seed, chain_offset, target_accept_prob, lanes_per_chain, engine)
+    T = lib.arp_hmc_num_transitions(C.byref(cfg))
+    a_h, b_h = _np(a, dt), _np(b, dt)
+    out = dict(out or {})
+    S = num_results
+    if _is_torch(z0):
+        import torch
+        tdt = _torch_dtype(precision)
+        z0 = z0.contiguous()
+        Cn = z0.shape[0]
+        dev = z0.device
+        eps0 = torch.as_tensor(eps0, dtype=tdt, device=dev).contiguous()
+        mom = None if ext_momenta is None else torch.as_tensor(ext_momenta, dtype=tdt, device=dev).contiguous()
+        lu = None if ext_log_u is None else torch.as_tensor(ext_log_u, dtype=tdt, device=dev).contiguous()
+        mk = lambda shape, dtype: torch.empty(shape, dtype=dtype, device=dev)
+        u8, i32 = torch.uint8, torch.int32
+        mem, st = _lib.ARP_MEM_DEVICE, _stream()
+    else:
+        tdt = dt
+        z0 = _np(z0, dt)
+        Cn = z0.shape[0]
+        eps0 = _np(eps0, dt)
+        mom, lu = _np(ext_momenta, dt), _np(ext_log_u, dt)
+        mk = lambda shape, dtype: np.empty(shape, dtype=dtype)
+        u8, i32 = np.uint8, np.int32
+        mem, st = _lib.ARP_MEM_HOST, None
+    assert tuple(z0.shape) == (Cn, D) and tuple(eps0.shape) == (D,)
+    if mom is not None:
+        assert tuple(mom.shape) == (T, Cn, D)
+    if lu is not None:
+        assert tuple(lu.shape) == (T, Cn)
+    if want_samples and "samples" not in out:
+        out["samples"] = mk((S, Cn, D), tdt)
+    if want_samples and "is_accepted" not in out:
+        out["is_accepted"] = mk((S, Cn), u8)
+    if want_orig and "samples_orig" not in out:
+        out["samples_orig"] = mk((S, Cn, D), tdt)
+    if want_final:
+        out["final_z"] = mk((Cn, D), tdt)
+    out["step_mult"] = mk((Cn,), tdt)
+    out["accept_count"] = mk((Cn,), i32)
+    buf = _lib.HmcBuffers(_p(z0), _p(eps0), _p(mom), _p(lu), _p(out.get("samples")), _p(out.get("samples_orig")),
+                          _p(out.get("is_accepted")), _p(out.get("final_z")), _p(out["step_mult"]),
+                          _p(out["accept_count"]))
+    rc = lib.arp_hmc_run(model.handle(precision), C.byref(cfg), _p(a_h), _p(b_h), Cn, C.byref(buf), mem, st)
+    _lib.check(lib, rc, "arp_hmc_run")
+    out["num_transitions"] = int(T)
+    return out
+
+
+def ess(samples, precision="f32"):
+    """samples [S, C, D] -> ESS [C, D] (``arp_ess``; TFP effective_sample_size semantics)."""
+    lib = _lib.load(precision)
+    dt = _lib.np_dtype(precision)
+    if _is_torch(samples):
+        import torch
+        samples = samples.contiguous()
+        S, Cn, D = samples.shape
+        out = torch.empty((Cn, D), dtype=samples.dtype, device=samples.device)
+        mem, st = _lib.ARP_MEM_DEVICE, _stream()
+    else:
+        samples = _np(samples, dt)
+        S, Cn, D = samples.shape
+        out = np.empty((Cn, D), dtype=dt)
+        mem, st = _lib.ARP_MEM_HOST, None
+    _lib.check(lib, lib.arp_ess(_p(samples), S, Cn, D, _p(out), mem, st), "arp_ess")
+    return out
+
+
+def vi_run(model, a, b, loc, rho, learning_rates, *, num_mc_samples, num_optimization_steps, a_logit=None,
+           seed=0, ext_eps=None, precision="f32"):
+    """All learning rates at once (``arp_vi_run``), host buffers.
+
+    loc / rho / a_logit: [R, D] initial values (copied, not modified).
+    Returns dict(loc, rho, a_logit, elbo [R, steps])."""
+    lib = _lib.load(precision)
+    dt = _lib.np_dtype(precision)
+    D = model.num_coords
+    R = len(learning_rates)
+    cfg = _lib.ViConfig()
+    cfg.num_mc_samples, cfg.num_optimization_steps, cfg.num_runs = num_mc_samples, num_optimization_steps, R
+    for i, lr in enumerate(learning_rates):
+        cfg.learning_rates[i] = float(lr)
+    cfg.seed = seed
+    cfg.learn_a = 0 if a_logit is None else 1
+    loc = np.array(np.broadcast_to(np.asarray(loc, dtype=dt), (R, D)))
+    rho = np.array(np.broadcast_to(np.asarray(rho, dtype=dt), (R, D)))
+    al = None if a_logit is None else np.array(np.broadcast_to(np.asarray(a_logit, dtype=dt), (R, D)))
+    eps = _np(ext_eps, dt)
+    if eps is not None:
+        assert eps.shape == (num_optimization_steps, num_mc_samples, D)
+    elbo = np.empty((R, num_optimization_steps), dtype=dt)
+    buf = _lib.ViBuffers(_p(loc), _p(rho), _p(al), _p(eps), _p(elbo))
+    a_h, b_h = _np(a, dt), _np(b, dt)
+    rc = lib.arp_vi_run(model.handle(precision), C.byref(cfg), _p(a_h), _p(b_h), C.byref(buf), _lib.ARP_MEM_HOST, None)
+    _lib.check(lib, rc, "arp_vi_run")
+    return dict(loc=loc, rho=rho, a_logit=al, elbo=elbo)
+
+
+def kernel_launch_count(precision="f32"):
+    return int(_lib.load(precision).arp_kernel_launch_count())

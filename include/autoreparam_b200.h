@@ -1,0 +1,181 @@
+/* autoreparam_b200 -- C ABI of the B200-native HMC / VI hot path.
+ *
+ * This is the drop-in boundary for the hot path of mgorinova/autoreparam.  The
+ * reference has no FFI of its own (it is pure Python on TF 1.14 / TFP 0.7); each
+ * entry point below names the reference interface it replaces (file:line in the
+ * reference tree) -- INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no C++/torch types; `stream` is a cudaStream_t
+ *    passed as void* (NULL = default stream).
+ *  - `mem` says where the caller's buffers live: ARP_MEM_DEVICE (device pointers,
+ *    asynchronous on `stream`) or ARP_MEM_HOST (host pointers; the call copies
+ *    H2D, runs, copies D2H and synchronises).
+ *  - per-chain arrays are row-major [C, D]: chain-major, the D coordinates of a
+ *    chain in the reference's trace order (graphs.py:29-44) -- i.e. the
+ *    concatenation of the reference's list of [C, *site_shape] state parts.
+ *  - `a`, `b` are the per-coordinate parameters of the reparameterisation rule
+ *    (program_transformations.py:555-600): CP a=b=1, NCP a=b=0, VIP anything in
+ *    [0,1].  They are always HOST arrays of length D (small, copied per call).
+ *  - precision: libarp_f32.so computes in float (arp_real = float);
+ *    libarp_f64.so is the -DARP_FP64 check build with arp_real = double and the
+ *    same symbols.
+ *  - every function returns 0 on success, non-zero on error (never throws /
+ *    exits); arp_last_error() returns the message of the calling thread's last
+ *    failure.
+ *  - a handle is used by one host thread at a time; kernels are re-entrant
+ *    across streams.
+ */
+#ifndef AUTOREPARAM_B200_H_
+#define AUTOREPARAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef ARP_FP64
+typedef double arp_real;
+#else
+typedef float arp_real;
+#endif
+
+#define ARP_MEM_HOST 0
+#define ARP_MEM_DEVICE 1
+
+typedef struct arp_model arp_model;
+
+/* Raw model data, as the reference's ModelConfig.model_args / observed_data hold
+ * it (models.py:51-54).  Host pointers; copied (and re-organised) at create time.
+ * Unused fields are NULL / 0.
+ *
+ *  8schools   (models.py:131-166)   n=8;  y = treatment_effects, x1 = treatment_stddevs
+ *  german_credit_lognormalcentered / german_credit_gammascale (models.py:884-964)
+ *             n, f;  X [n, f] row-major design matrix (intercept | numerics | one-hots,
+ *             models.py:889-892), y [n] in {0,1}
+ *  radon / radon_stddvs (models.py:763-857)
+ *             n, j;  idx0 = county [n] 0-based, u [j], x1 = floor x [n], y = log radon [n]
+ *  election   (models.py:967-1008)  n, j = n_state;  idx0 = state [n] AS STORED (1-based,
+ *             fed to one_hot(depth=j): out-of-range rows select nothing), x1 = female,
+ *             x2 = black, y [n]
+ *  electric   (models.py:1011-1066) n, j = n_pair, k = n_grade, k2 = n_grade_pair;
+ *             idx0 = pair [n], idx1 = grade [n], idx2 = grade_pair [j] (all as stored,
+ *             1-based), x1 = treatment [n], y [n]
+ *  time_series(models.py:1069-1141) n = T;  x1 = year x [n], y [n]
+ */
+typedef struct arp_model_data {
+  int64_t n, f, j, k, k2;
+  const float* X;
+  const float* y;
+  const float* x1;
+  const float* x2;
+  const float* u;
+  const int32_t* idx0;
+  const int32_t* idx1;
+  const int32_t* idx2;
+} arp_model_data;
+
+/* replaces models.get_model_by_name (models.py:1144-1175) for the in-scope models */
+int arp_model_create(const char* model_name, const arp_model_data* data, arp_model** out);
+void arp_model_destroy(arp_model* m);
+/* number of state coordinates D (sum of the latent site sizes in trace order) */
+int arp_model_num_coords(const arp_model* m);
+
+/* replaces target(*params) of graphs.py:37-44 / 84-91 / 139-145 / 197-203 vectorised
+ * over chains (inference.vectorize_log_joint_fn, inference.py:172-195) plus the
+ * tf.gradients call TFP's HMC makes on it, plus make_to_centered (models.py:59-81).
+ *   z [C,D] in;  lp [C], grad [C,D], centered [C,D], abar [C,D] out (each may be NULL).
+ *   abar = d log_joint / d a per coordinate (what the cVIP ELBO differentiates). */
+int arp_log_joint_grad(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
+                       arp_real* lp, arp_real* grad, arp_real* centered, arp_real* abar, int mem, void* stream);
+
+/* HMC configuration: inference.hmc (inference.py:198-242) + main.py flags. */
+typedef struct arp_hmc_config {
+  int32_t num_leapfrog_steps;   /* --num_leapfrog_steps */
+  int32_t num_results;          /* --num_samples : kept samples S */
+  int32_t num_burnin_steps;     /* --num_burnin_steps */
+  int32_t num_adaptation_steps; /* --num_adaptation_steps (dual averaging, per chain) */
+  int32_t num_steps_between_results; /* 1 in the reference (inference.py:234) */
+  uint64_t seed;                /* Philox key */
+  int64_t chain_offset;         /* global id of chain 0 (multi-GPU sharding: RNG is keyed by global id) */
+  double target_accept_prob;    /* 0.75 [TFP default] */
+  int32_t lanes_per_chain;      /* 0 = auto; 1,8,32 = force */
+  int32_t engine;               /* 0 = auto, 1 = generic FP32 SIMT kernels, 2 = tcgen05 (german credit) */
+} arp_hmc_config;
+
+/* Buffers of one HMC run.  `mem` applies to every non-NULL pointer here.
+ *   z0            [C,D]  in   initial states (util.variational_inits_from_params, util.py:394-410)
+ *   eps0          [D]    in   per-coordinate initial step size sigma_q / (L/4)^2 (inference.py:212-216)
+ *   ext_momenta   [T,C,D] in  optional injected momenta (T = arp_hmc_num_transitions), else Philox
+ *   ext_log_u     [T,C]  in   optional injected log-uniforms for the Metropolis test
+ *   samples       [S,C,D] out centred samples (= states_transformed of inference.py:238-239)
+ *   samples_orig  [S,C,D] out optional raw (reparameterised-space) samples (= states_orig)
+ *   is_accepted   [S,C]  out  uint8, is_accepted of the transition that produced each kept sample
+ *   final_z       [C,D]  out  optional final state
+ *   step_mult     [C]    out  optional final per-chain step-size multiplier (eps = eps0 * mult)
+ *   accept_count  [C]    out  optional number of accepted transitions per chain (all transitions)
+ */
+typedef struct arp_hmc_buffers {
+  const arp_real* z0;
+  const arp_real* eps0;
+  const arp_real* ext_momenta;
+  const arp_real* ext_log_u;
+  arp_real* samples;
+  arp_real* samples_orig;
+  uint8_t* is_accepted;
+  arp_real* final_z;
+  arp_real* step_mult;
+  int32_t* accept_count;
+} arp_hmc_buffers;
+
+/* total transitions of a run: 1 + burnin + (1+between)*(S-1)  [TFP sample_chain] */
+int64_t arp_hmc_num_transitions(const arp_hmc_config* cfg);
+
+/* replaces inference.hmc (inference.py:198-242): HamiltonianMonteCarlo +
+ * DualAveragingStepSizeAdaptation + sample_chain + transform_mcmc_states, all
+ * chains, all transitions, in one persistent kernel launch. */
+int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_real* a, const arp_real* b, int64_t C,
+                const arp_hmc_buffers* buf, int mem, void* stream);
+
+/* replaces tfp.mcmc.effective_sample_size (inference.py:240,327):
+ * samples [S,C,D] -> ess [C,D]. */
+int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* ess, int mem, void* stream);
+
+/* VI: replaces util.get_mean_field_elbo (util.py:232-268) + the Adam loops of
+ * inference.find_best_learning_rate (inference.py:26-154): all `num_runs`
+ * learning rates are optimised concurrently (one CTA each) in one launch. */
+#define ARP_VI_MAX_RUNS 16
+typedef struct arp_vi_config {
+  int32_t num_mc_samples;         /* --num_mc_samples (256) */
+  int32_t num_optimization_steps; /* --num_optimization_steps (3000) */
+  int32_t num_runs;               /* number of learning rates R (<= ARP_VI_MAX_RUNS) */
+  double learning_rates[ARP_VI_MAX_RUNS]; /* --learning_rates; each is /5 after 1/3 and /20 after 2/3
+                                             of the steps (inference.py:69-75) */
+  uint64_t seed;
+  int32_t learn_a;                /* 1 = cVIP: a = sigmoid(a_logit) is optimised too
+                                     (program_transformations.py:507-510); b stays as passed, which is
+                                     what the reference's tied mode does as written */
+} arp_vi_config;
+
+typedef struct arp_vi_buffers {
+  arp_real* loc;           /* [R,D] in/out  variational means (init 0.01*randn, program_transformations.py:207-210) */
+  arp_real* rho;           /* [R,D] in/out  unconstrained scales, scale = softplus(rho) (init -2, :212-215) */
+  arp_real* a_logit;       /* [R,D] in/out  only if learn_a (init 0) */
+  const arp_real* ext_eps; /* [steps,S,D] optional injected standard normals (shared by the R runs) */
+  arp_real* elbo;          /* [R,steps] out  ELBO timeline (value at the pre-update parameters) */
+} arp_vi_buffers;
+
+int arp_vi_run(arp_model* m, const arp_vi_config* cfg, const arp_real* a, const arp_real* b,
+               const arp_vi_buffers* buf, int mem, void* stream);
+
+/* number of kernels this library has launched in this process (bench accounting) */
+int64_t arp_kernel_launch_count(void);
+const char* arp_last_error(void);
+/* "f32" or "f64" */
+const char* arp_precision(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOREPARAM_B200_H_ */

@@ -1,0 +1,94 @@
+"""GPU parity: effective sample size and the fused VI kernel."""
+import numpy as np
+import pytest
+
+from autoreparam_b200 import engine
+from oracle import oracle as O
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _ar1(S, shape, phi, rng):
+    x = np.zeros((S,) + shape)
+    e = rng.standard_normal((S,) + shape)
+    for t in range(1, S):
+        x[t] = phi * x[t - 1] + e[t]
+    return x
+
+
+@pytest.mark.parametrize("S", [50, 1000, 4097])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_ess_matches_fft_oracle(S, precision):
+    rng = np.random.default_rng(S)
+    C, D = 5, 7
+    phi = rng.uniform(-0.5, 0.95, (C, D))
+    x = _ar1(S, (C, D), phi, rng) + 3.0
+    x = x.astype(np.float32).astype(np.float64)
+    ref = O.effective_sample_size(x)
+    got = engine.ess(x, precision=precision)
+    tol = 2e-3 if precision == "f32" else 1e-8
+    assert np.abs(got / ref - 1).max() < tol, np.abs(got / ref - 1).max()
+
+
+def test_ess_edge_cases():
+    S, C, D = 64, 2, 3
+    x = np.zeros((S, C, D))
+    x[:, 0, 0] = 1.5                                   # constant series -> NaN (nan_to_num'd by get_min_ess)
+    x[:, 0, 1] = np.arange(S) % 2                      # perfectly anti-correlated: rho_1 < 0 -> ESS = S
+    x[:, 0, 2] = np.arange(S)                          # trend: long positive autocorrelation
+    x[:, 1] = np.random.default_rng(0).standard_normal((S, D))
+    ref = O.effective_sample_size(x)
+    got = engine.ess(x, precision="f64")
+    assert np.isnan(got[0, 0]) and np.isnan(ref[0, 0])
+    ok = ~np.isnan(ref)
+    assert np.abs(got[ok] / ref[ok] - 1).max() < 1e-8
+    assert abs(got[0, 1] - S) < 1e-9
+
+
+@pytest.mark.parametrize("model,method", [("8schools", "cVIP"), ("8schools", "NCP"), ("radon", "cVIP"),
+                                          ("election", "dVIP"), ("electric", "cVIP"),
+                                          ("german_credit_lognormalcentered", "cVIP"), ("time_series", "CP")])
+def test_vi_steps_match_oracle_fp64(model, method):
+    """A few Adam steps on the ELBO with injected normals: ELBO timeline and
+    parameters equal the autograd oracle (fp64 build)."""
+    mc = common.model_config(model, "MN")
+    raw = common.raw_data(model, "MN")
+    D = mc.num_coords
+    S, steps, lr = 4, 6, 0.05
+    rng = np.random.default_rng(21)
+    eps = rng.standard_normal((steps, S, D))
+    loc0 = 0.01 * rng.standard_normal(D)
+    rho0 = np.full(D, -2.0)
+    if method == "cVIP":
+        a, b, al0 = np.full(D, 0.5), np.ones(D), np.zeros(D)
+    else:
+        a, b = common.ab_for(method, D)
+        al0 = None
+    ref = O.vi_run(model, raw, loc0, rho0, eps, lr, steps, a=a, b=b, a_logit0=al0)
+    out = engine.vi_run(mc, a, b, loc0[None], rho0[None], [lr], num_mc_samples=S, num_optimization_steps=steps,
+                        a_logit=None if al0 is None else al0[None], ext_eps=eps, precision="f64")
+    assert np.abs(out["elbo"][0] / ref["elbo"] - 1).max() < 1e-8, np.abs(out["elbo"][0] / ref["elbo"] - 1).max()
+    assert np.abs(out["loc"][0] - ref["loc"]).max() < 1e-7
+    assert np.abs(out["rho"][0] - ref["rho"]).max() < 1e-7
+    if al0 is not None:
+        assert np.abs(out["a_logit"][0] - ref["a_logit"]).max() < 1e-7
+        assert np.abs(out["a_logit"][0]).max() > 1e-3   # the parameterisation really moved
+
+
+def test_vi_learning_rates_run_concurrently_and_converge():
+    """All learning rates in one launch; 8schools CP ELBO improves and the
+    schedule / ELBO bookkeeping of find_best_learning_rate can be applied."""
+    mc = common.model_config("8schools")
+    D = mc.num_coords
+    lrs = [0.02, 0.05, 0.1, 0.2, 0.4]
+    rng = np.random.default_rng(2)
+    loc0 = 0.01 * rng.standard_normal((len(lrs), D))
+    out = engine.vi_run(mc, np.zeros(D), np.zeros(D), loc0, np.full((len(lrs), D), -2.0), lrs, num_mc_samples=256,
+                        num_optimization_steps=600, seed=5, precision="f32")
+    elbo = out["elbo"]
+    assert elbo.shape == (5, 600) and np.isfinite(elbo).all()
+    final = elbo[:, -32:].mean(axis=1)
+    assert (final > elbo[:, :5].mean(axis=1)).all()
+    # 8 schools: ELBO of a good mean-field fit in the non-centred parameterisation is about -31.7
+    assert -33.5 < final.max() < -30.5, final

@@ -1,0 +1,130 @@
+"""GPU parity of the persistent HMC kernel against the TFP-order oracle."""
+import numpy as np
+import pytest
+
+from autoreparam_b200 import engine
+from oracle import oracle as O
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(model, method, C, seed):
+    mc = common.model_config(model)
+    raw = common.raw_data(model)
+    D = mc.num_coords
+    a, b = common.ab_for(method, D)
+    z0 = common.random_states(model, D, C, seed=seed, scale=0.3).astype(np.float32).astype(np.float64)
+    return mc, raw, D, a, b, z0
+
+
+CASES = [("8schools", "CP", 0.15), ("8schools", "NCP", 0.2), ("german_credit_lognormalcentered", "VIP_a", 0.01),
+         ("german_credit_gammascale", "NCP", 0.002), ("radon", "NCP", 0.02), ("radon_stddvs", "VIP_a", 0.01),
+         ("election", "dVIP", 0.01), ("electric", "NCP", 0.01), ("time_series", "NCP", 2e-5),
+         ("german_synth", "CP", 0.01)]
+
+
+@pytest.mark.parametrize("model,method,eps", CASES)
+def test_fixed_momenta_trajectory_fp64(model, method, eps):
+    """Identical leapfrog trajectories, accept decisions, step-size adaptation and
+    thinning given identical momenta / uniforms: fp64 check build vs fp64 oracle."""
+    C, L, S, burn, adapt = 5, 3, 4, 3, 5
+    mc, raw, D, a, b, z0 = _setup(model, method, C, seed=11)
+    omodel = "german_credit_lognormalcentered" if model == "german_synth" else model
+    T = O.num_transitions(S, burn)
+    rng = np.random.default_rng(5)
+    mom = rng.standard_normal((T, C, D))
+    lu = np.log(rng.uniform(size=(T, C)))
+    eps0 = np.full(D, eps) * rng.uniform(0.5, 1.5, D)
+    ref = O.hmc_chain(omodel, raw, z0, eps0, L, S, burn, adapt, a, b, momenta=mom, log_u=lu)
+    out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn,
+                         num_adaptation_steps=adapt, ext_momenta=mom, ext_log_u=lu, want_orig=True, precision="f64",
+                         engine=engine.ENGINE_SIMT)
+    assert out["num_transitions"] == T
+    assert (out["is_accepted"].astype(bool) == ref["is_accepted"]).all()
+    assert 0 < ref["is_accepted"].mean()  # the case must exercise accepted moves
+    assert common.rel_err(out["samples_orig"].reshape(S * C, D), ref["samples_orig"].reshape(S * C, D)).max() < 1e-9
+    assert common.rel_err(out["samples"].reshape(S * C, D), ref["samples_centered"].reshape(S * C, D)).max() < 1e-9
+    assert common.rel_err(out["final_z"], ref["z"]).max() < 1e-9
+    assert common.rel_err(out["step_mult"], ref["step_mult"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("model,method,eps", CASES)
+def test_fixed_momenta_trajectory_fp32(model, method, eps):
+    """Same, product (fp32) build: trajectories agree to fp32 round-off over a
+    short horizon and every accept decision matches."""
+    C, L, S, burn, adapt = 5, 3, 3, 2, 4
+    mc, raw, D, a, b, z0 = _setup(model, method, C, seed=12)
+    omodel = "german_credit_lognormalcentered" if model == "german_synth" else model
+    T = O.num_transitions(S, burn)
+    rng = np.random.default_rng(6)
+    mom = rng.standard_normal((T, C, D)).astype(np.float32).astype(np.float64)
+    lu = np.log(rng.uniform(size=(T, C))).astype(np.float32).astype(np.float64)
+    eps0 = (np.full(D, eps) * rng.uniform(0.5, 1.5, D)).astype(np.float32).astype(np.float64)
+    ref = O.hmc_chain(omodel, raw, z0, eps0, L, S, burn, adapt, a, b, momenta=mom, log_u=lu)
+    for lpc in (1, 8, 32):
+        out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn,
+                             num_adaptation_steps=adapt, ext_momenta=mom, ext_log_u=lu, want_orig=True,
+                             precision="f32", lanes_per_chain=lpc, engine=engine.ENGINE_SIMT)
+        # an accept decision may legitimately flip only if log_alpha is within fp32 noise of log_u
+        same = out["is_accepted"].astype(bool) == ref["is_accepted"]
+        assert same.all(), (lpc, np.argwhere(~same))
+        tol = 5e-3 if model == "time_series" else 2e-4
+        err = common.rel_err(out["samples"].reshape(S * C, D), ref["samples_centered"].reshape(S * C, D)).max()
+        assert err < tol, (lpc, err)
+
+
+def test_philox_stream_matches_oracle():
+    """Internal counter-based RNG: the fp64 build draws the same momenta and
+    uniforms as the oracle's numpy Philox, so whole chains coincide."""
+    model, method = "8schools", "NCP"
+    C, L, S, burn, adapt = 7, 4, 5, 4, 6
+    mc, raw, D, a, b, z0 = _setup(model, method, C, seed=13)
+    eps0 = np.full(D, 0.2)
+    seed, off = 0x1234ABCD5678, 1000
+    ref = O.hmc_chain(model, raw, z0, eps0, L, S, burn, adapt, a, b, seed=seed, chain_ids=np.arange(C) + off)
+    out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn,
+                         num_adaptation_steps=adapt, seed=seed, chain_offset=off, precision="f64")
+    assert (out["is_accepted"].astype(bool) == ref["is_accepted"]).all()
+    assert common.rel_err(out["samples"].reshape(S * C, D), ref["samples_centered"].reshape(S * C, D)).max() < 1e-6
+    # sharding invariance: chains [3, 7) run alone with chain_offset give the same samples
+    sub = engine.hmc_run(mc, z0[3:], eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn,
+                         num_adaptation_steps=adapt, seed=seed, chain_offset=off + 3, precision="f64")
+    assert np.array_equal(sub["samples"], out["samples"][:, 3:])
+
+
+def test_radon_posterior_matches_closed_form():
+    """radon with sigma_y = 1 is linear-Gaussian: the exact posterior mean / sd is
+    available in closed form -- an absolute pin for the sampler."""
+    import torch
+    model = "radon"
+    mc = common.model_config(model, "MN")
+    raw = common.raw_data(model, "MN")
+    D = mc.num_coords
+    J = len(raw["u"])
+    # posterior precision / mean in the CENTRED space: theta = [mua, b1, b2, m_1..m_J]
+    A = np.zeros((D, D)); rhs = np.zeros(D)
+    A[0, 0] += 1; A[1, 1] += 1; A[2, 2] += 1                      # N(0,1) priors
+    for j in range(J):                                             # m_j ~ N(mua + u_j b1, 1)
+        v = np.zeros(D); v[3 + j] = 1; v[0] = -1; v[1] = -raw["u"][j]
+        A += np.outer(v, v)
+    for n in range(len(raw["y"])):                                 # y_n ~ N(m_c + x_n b2, 1)
+        v = np.zeros(D); v[3 + raw["county"][n]] = 1; v[2] = raw["x"][n]
+        A += np.outer(v, v); rhs += v * raw["y"][n]
+    cov = np.linalg.inv(A); mean = cov @ rhs; sd = np.sqrt(np.diag(cov))
+    for method in ("CP", "NCP"):
+        a, b = common.ab_for(method, D)
+        C, S = 256, 400
+        rng = np.random.default_rng(1)
+        z0 = rng.standard_normal((C, D)) * 0.1
+        eps0 = np.full(D, 0.05) if method == "CP" else np.full(D, 0.03)
+        out = engine.hmc_run(mc, z0.astype(np.float32), eps0, a, b, num_leapfrog_steps=8, num_results=S,
+                             num_burnin_steps=600, num_adaptation_steps=500, seed=7, precision="f32")
+        x = out["samples"].astype(np.float64)            # centred samples [S, C, D]
+        acc = out["is_accepted"].mean()
+        assert 0.5 < acc < 0.95, acc
+        m_hat = x.mean(axis=(0, 1)); s_hat = x.std(axis=(0, 1))
+        # Monte-Carlo error: >= C independent chains, thinned samples
+        z_score = np.abs(m_hat - mean) / (sd / np.sqrt(C))
+        assert z_score.max() < 6.0, (method, z_score.max())
+        assert np.abs(s_hat / sd - 1).max() < 0.08, (method, np.abs(s_hat / sd - 1).max())
