@@ -80,7 +80,7 @@ def load(precision="f32"):
     lib.arp_hmc_num_transitions.restype = i64
     lib.arp_hmc_run.argtypes = [vp, C.POINTER(HmcConfig), vp, vp, i64, C.POINTER(HmcBuffers), i32, vp]
     lib.arp_hmc_run.restype = i32
-    lib.arp_ess.argtypes = [vp, i64, i64, i64, vp, i32, vp]
+    lib.arp_ess.argtypes = [vp, i64, i64, i64, vp, vp, vp, i32, vp]
     lib.arp_ess.restype = i32
     lib.arp_vi_run.argtypes = [vp, C.POINTER(ViConfig), vp, vp, C.POINTER(ViBuffers), i32, vp]
     lib.arp_vi_run.restype = i32

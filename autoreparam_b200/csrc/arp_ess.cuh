@@ -22,13 +22,15 @@ namespace arp {
 #define ARP_ESS_W 16
 
 __global__ void __launch_bounds__(ARP_ESS_BLOCK)
-k_ess(const real* __restrict__ x, int S, long long n, real* __restrict__ ess) {
+k_ess(const real* __restrict__ x, int S, long long n, real* __restrict__ ess, real* __restrict__ mean_out,
+      real* __restrict__ var_out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const real* xs = x + i;
   double mean = 0;
   for (int t = 0; t < S; ++t) mean += (double)xs[(size_t)t * n];
   mean /= S;
+  if (mean_out) mean_out[i] = (real)mean;
 
   double sum = 0;       // sum_k (S-k)/S rho_k over the kept lags
   double acov0 = 0;
@@ -56,6 +58,7 @@ k_ess(const real* __restrict__ x, int S, long long n, real* __restrict__ ess) {
     }
     if (k0 == 0) {
       acov0 = acc[0] / S;
+      if (var_out) var_out[i] = (real)acov0;
       if (!(acov0 > 0.0)) {  // constant (or non-finite) series: TFP yields NaN
         ess[i] = (real)NAN;
         return;

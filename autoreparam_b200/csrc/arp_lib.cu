@@ -395,22 +395,28 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
 }
 
 // ------------------------------------------------------------------------ ESS ---
-extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* ess, int mem, void* stream) {
+extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* ess, arp_real* mean,
+                       arp_real* var, int mem, void* stream) {
   if (!samples || !ess || S < 2 || C <= 0 || D <= 0) return fail("arp_ess: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   DevBuf din, dout;
   const real* in = samples;
-  real* out = ess;
   const size_t n = (size_t)C * D;
+  real *out = ess, *omean = mean, *ovar = var;
   if (mem == ARP_MEM_HOST) {
     if (stage_in(din, samples, (size_t)S * n * sizeof(real), mem, st)) return 1;
-    ARP_CUDA(dout.alloc(n * sizeof(real)));
+    ARP_CUDA(dout.alloc(3 * n * sizeof(real)));
     in = din.as<real>(); out = dout.as<real>();
+    omean = mean ? out + n : nullptr; ovar = var ? out + 2 * n : nullptr;
   }
-  k_ess<<<(unsigned)((n + ARP_ESS_BLOCK - 1) / ARP_ESS_BLOCK), ARP_ESS_BLOCK, 0, st>>>(in, (int)S, (long long)n, out);
+  k_ess<<<(unsigned)((n + ARP_ESS_BLOCK - 1) / ARP_ESS_BLOCK), ARP_ESS_BLOCK, 0, st>>>(in, (int)S, (long long)n, out, omean, ovar);
   ARP_LAUNCH_CHECK();
-  if (mem == ARP_MEM_HOST) ARP_CUDA(cudaMemcpyAsync(ess, out, n * sizeof(real), cudaMemcpyDeviceToHost, st));
-  ARP_CUDA(cudaStreamSynchronize(st));
+  if (mem == ARP_MEM_HOST) {
+    ARP_CUDA(cudaMemcpyAsync(ess, out, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+    if (mean) ARP_CUDA(cudaMemcpyAsync(mean, omean, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+    if (var) ARP_CUDA(cudaMemcpyAsync(var, ovar, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+    ARP_CUDA(cudaStreamSynchronize(st));
+  }
   return 0;
 }
 

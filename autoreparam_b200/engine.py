@@ -137,23 +137,27 @@ def hmc_run(model, z0, eps0, a, b, *, num_leapfrog_steps, num_results, num_burni
     return out
 
 
-def ess(samples, precision="f32"):
-    """samples [S, C, D] -> ESS [C, D] (``arp_ess``; TFP effective_sample_size semantics)."""
+def ess(samples, precision="f32", want_moments=False):
+    """samples [S, C, D] -> ESS [C, D] (``arp_ess``; TFP effective_sample_size semantics).
+    With ``want_moments`` also returns the per-chain mean and (biased) variance [C, D]."""
     lib = _lib.load(precision)
     dt = _lib.np_dtype(precision)
     if _is_torch(samples):
         import torch
         samples = samples.contiguous()
         S, Cn, D = samples.shape
-        out = torch.empty((Cn, D), dtype=samples.dtype, device=samples.device)
+        mk = lambda: torch.empty((Cn, D), dtype=samples.dtype, device=samples.device)
         mem, st = _lib.ARP_MEM_DEVICE, _stream()
     else:
         samples = _np(samples, dt)
         S, Cn, D = samples.shape
-        out = np.empty((Cn, D), dtype=dt)
+        mk = lambda: np.empty((Cn, D), dtype=dt)
         mem, st = _lib.ARP_MEM_HOST, None
-    _lib.check(lib, lib.arp_ess(_p(samples), S, Cn, D, _p(out), mem, st), "arp_ess")
-    return out
+    out = mk()
+    mean = mk() if want_moments else None
+    var = mk() if want_moments else None
+    _lib.check(lib, lib.arp_ess(_p(samples), S, Cn, D, _p(out), _p(mean), _p(var), mem, st), "arp_ess")
+    return (out, mean, var) if want_moments else out
 
 
 def vi_run(model, a, b, loc, rho, learning_rates, *, num_mc_samples, num_optimization_steps, a_logit=None,

@@ -1,0 +1,128 @@
+"""Inference engines: host-side mirror of the reference's ``inference.py``.
+
+``hmc`` replaces ``inference.hmc`` (``inference.py:198-242``) and
+``find_best_learning_rate`` replaces ``inference.find_best_learning_rate``
+(``inference.py:26-154``).  Both are thin: every transition / optimisation step
+runs inside the CUDA library; this module stages buffers, calls the C ABI and
+shapes the results the way ``main.py`` consumes them.  The reference reads its
+sizes from global absl FLAGS; here they are keyword arguments with the flag
+names.
+"""
+from __future__ import annotations
+
+import collections
+
+import numpy as np
+
+from . import engine, util
+
+
+class HmcResult(collections.namedtuple(
+        "HmcResult", "ess is_accepted samples rhat step_mult accept_count num_transitions ess_flat")):
+    """ess: list of [C, *site] (un-normalised, as tfp.mcmc.effective_sample_size);
+    is_accepted [S, C] bool; samples: list of [S, n_save, *site] centred traces
+    (None unless chains were requested); rhat [D] per coordinate."""
+
+
+def _flat_step_sizes(model_config, step_size_init):
+    """initial_step_size is a list per site in trace order (main.py:283-284)."""
+    if isinstance(step_size_init, np.ndarray) and step_size_init.shape == (model_config.num_coords,):
+        return step_size_init.astype(np.float64)
+    parts = []
+    for (name, shape), s in zip(model_config.sites, step_size_init):
+        parts.append(np.broadcast_to(np.asarray(s, dtype=np.float64), shape).reshape(-1))
+    return np.concatenate(parts)
+
+
+def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, num_leapfrog_steps, num_samples,
+        num_burnin_steps, num_adaptation_steps, num_chains_to_save=0, seed=0, chain_offset=0, device="cuda",
+        engine_kind=engine.ENGINE_AUTO, precision="f32", keep_on_device=False):
+    """HMC + dual-averaging adaptation + thinning + to-centred + ESS (``inference.py:198-242``).
+
+    target            TargetGraph (graphs.py) -- carries the (a, b) rule, so ``reparam`` is accepted
+                      for signature parity only.
+    step_size_init    list per site (VI's sigma_q); eps0 = sigma_q / (L / 4)**2  (inference.py:212-216)
+    initial_states    list of [C, *site] arrays (util.variational_inits_from_params) or flat [C, D]
+    """
+    import torch
+
+    mc = model_config
+    if isinstance(initial_states, np.ndarray) and initial_states.ndim == 2:
+        z0 = initial_states
+    else:
+        z0 = mc.join(list(initial_states))
+    C, D = z0.shape
+    eps0 = _flat_step_sizes(mc, step_size_init) / (float(num_leapfrog_steps) / 4.0) ** 2
+    tdt = torch.float32 if precision == "f32" else torch.float64
+    dev = torch.device(device)
+    # host -> device from pinned memory
+    z_pin = torch.from_numpy(np.ascontiguousarray(z0, dtype=np.float32 if precision == "f32" else np.float64)).pin_memory()
+    z_dev = z_pin.to(dev, non_blocking=True)
+    out = engine.hmc_run(mc, z_dev, eps0, target.a, target.b, num_leapfrog_steps=num_leapfrog_steps,
+                         num_results=num_samples, num_burnin_steps=num_burnin_steps,
+                         num_adaptation_steps=num_adaptation_steps, seed=seed, chain_offset=chain_offset,
+                         want_final=False, engine=engine_kind, precision=precision)
+    ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
+    # device -> host: only what the caller consumes
+    ess_flat = ess_dev.cpu().numpy()
+    is_acc = out["is_accepted"].cpu().numpy().astype(bool)
+    mean_h, var_h = mean_dev.cpu().numpy(), var_dev.cpu().numpy()
+    samples = None
+    if num_chains_to_save > 0:
+        samples = mc.split(out["samples"][:, :num_chains_to_save].cpu().numpy())
+    res = HmcResult(ess=mc.split(ess_flat), is_accepted=is_acc, samples=samples,
+                    rhat=util.rhat_from_moments(mean_h, var_h, num_samples) if C > 1 else None,
+                    step_mult=out["step_mult"].cpu().numpy(), accept_count=out["accept_count"].cpu().numpy(),
+                    num_transitions=out["num_transitions"], ess_flat=ess_flat)
+    if keep_on_device:
+        return res, out
+    return res
+
+
+def find_best_learning_rate(target, model_config, *, learning_rates, num_optimization_steps, num_mc_samples,
+                            seed=0, precision="f32", init_rng=None, log_fn=None):
+    """Adam on the mean-field ELBO for every learning rate (``inference.py:26-154``).
+
+    All learning rates run concurrently in one kernel launch.  Returns the
+    reference's tuple ``(best_elbo, best_timeline, best_lr, step_size_init,
+    learned_variational_params, learned_reparam)``; ``learned_reparam`` is None
+    unless ``target.learnable`` (cVIP)."""
+    mc = model_config
+    D = mc.num_coords
+    R = len(learning_rates)
+    rng = np.random.default_rng(seed) if init_rng is None else init_rng
+    # program_transformations.py:207-215: loc = 1e-2 * randn, scale = softplus(-2); re-initialised per run
+    loc0 = 1e-2 * rng.standard_normal((R, D))
+    rho0 = np.full((R, D), -2.0)
+    al0 = np.zeros((R, D)) if target.learnable else None  # sigmoid(0) = 0.5, :507-510
+    out = engine.vi_run(mc, target.a, target.b, loc0, rho0, [float(l) for l in learning_rates],
+                        num_mc_samples=num_mc_samples, num_optimization_steps=num_optimization_steps,
+                        a_logit=al0, seed=seed, precision=precision)
+    best = None
+    for r, lr in enumerate(learning_rates):
+        timeline = out["elbo"][r]
+        this_elbo = float(np.mean(timeline[-32:]))                     # inference.py:121
+        if log_fn is not None:
+            for step in range(0, num_optimization_steps, 100):         # inference.py:107-108
+                log_fn("step {} elbo {}".format(step, timeline[step]))
+            log_fn("     finished optimization with elbo {} vs best ELBO {}".format(
+                this_elbo, None if best is None else best[0]))
+        if not np.isfinite(this_elbo):                                 # inference.py:127
+            continue
+        if best is None or best[0] < this_elbo:
+            best = (this_elbo, r, float(lr))
+    if best is None:
+        raise FloatingPointError("no learning rate produced a finite ELBO")
+    best_elbo, r, best_lr = best
+    scale = np.logaddexp(out["rho"][r].astype(np.float64), 0.0)          # softplus
+    params = collections.OrderedDict()
+    for (name, shape), lo, sc in zip(mc.sites, mc.split(out["loc"][r]), mc.split(scale)):
+        params[name + "_loc"] = np.asarray(lo, dtype=np.float32)
+        params[name + "_scale"] = np.asarray(sc, dtype=np.float32)
+    step_size_init = util.get_approximate_step_size(params, num_leapfrog_steps=1)  # inference.py:42-43
+    learned_reparam = None
+    if target.learnable:
+        a = 1.0 / (1.0 + np.exp(-out["a_logit"][r].astype(np.float64)))
+        learned_reparam = collections.OrderedDict(
+            (name + "_a", np.asarray(v, dtype=np.float32)) for (name, _), v in zip(mc.sites, mc.split(a)))
+    return (best_elbo, list(out["elbo"][r]), best_lr, step_size_init, params, learned_reparam)

@@ -139,8 +139,11 @@ int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_real* a, cons
                 const arp_hmc_buffers* buf, int mem, void* stream);
 
 /* replaces tfp.mcmc.effective_sample_size (inference.py:240,327):
- * samples [S,C,D] -> ess [C,D]. */
-int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* ess, int mem, void* stream);
+ * samples [S,C,D] -> ess [C,D].  Optional extra outputs (NULL to skip): per-series
+ * mean [C,D] and biased variance [C,D] -- the per-chain moments R-hat is built
+ * from (new capability; the reference has no R-hat). */
+int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* ess, arp_real* mean,
+            arp_real* var, int mem, void* stream);
 
 /* VI: replaces util.get_mean_field_elbo (util.py:232-268) + the Adam loops of
  * inference.find_best_learning_rate (inference.py:26-154): all `num_runs`
