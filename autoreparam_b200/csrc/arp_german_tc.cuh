@@ -1,19 +1,570 @@
-// tcgen05 engine for German credit (placeholder until the tensor-core kernel lands).
+// tcgen05 engine: persistent HMC kernel for german_credit_lognormalcentered with
+// the design-matrix contractions on the 5th-generation tensor cores.
+//
+//   eta = X beta   (reference models.py:903 einsum)  ->  GEMM1  H[chain, obs] = B[chain, f] X[obs, f]^T
+//   gbeta = X^T r  (autodiff of :903-904)            ->  GEMM2  G[chain, f]  = R[chain, obs] X[obs, f]
+//
+// One CTA owns 128 chains (= the 128 TMEM lanes).  X stays resident in shared
+// memory for the whole run as ONE canonical no-swizzle core-matrix image that
+// serves GEMM1 as a K-major B operand and GEMM2 as an MN-major B operand.  The
+// residual R = y - sigmoid(H) never leaves the SM: the epilogue warps read H from
+// TMEM (tcgen05.ld), compute R and write it back to TMEM (tcgen05.st) as the
+// A operand of GEMM2 (tcgen05.mma with A in TMEM).
+//
+// Precision: fp32 operands are split into an fp16 head and tail (x = x1 + x2,
+// 22 significant bits) and each contraction is three kind::f16 MMAs with fp32
+// accumulation (x1 b1 + x2 b1 + x1 b2) -- the split-precision scheme of 3xTF32,
+// done in fp16 because (a) both X parts then fit in shared memory (128 KiB) and
+// (b) the f16 MMA rate is twice the tf32 rate.  Error per product ~2^-22, which
+// holds the 1e-5 fp32 tolerance of the log-joint gradient (tests/test_gpu_tc.py).
+//
+// Warp roles (288 threads): warps 0-3 and 4-7 are two "halves" that both map
+// thread -> chain (TMEM lane = tid & 127); half h owns features [16h, 16h+16),
+// observation columns [64h, 64h+64) of every 128-observation chunk and every
+// other Philox block of the elementwise leapfrog updates.  Warp 8 issues every
+// tcgen05.mma / tcgen05.commit from one elected lane.
+//
+// Everything else (Philox momenta, two half-kicks per leapfrog step, Metropolis
+// accept, per-chain dual averaging, thinning, centred-sample store) follows
+// arp_hmc.cuh / SURVEY.md appendix D.
 #pragma once
 #include <atomic>
+#include <cuda_fp16.h>
 #include <string>
+#include <vector>
 #include "arp_host.cuh"
 #include "arp_hmc.cuh"
 
 namespace arp {
-struct GermanTc {
-  bool build(const float*, const float*, int, int, std::string*) { return true; }
-  bool ready() const { return false; }
+
+#define TC_CHAINS 128
+#define TC_NF 32          // padded feature count (K of GEMM1, N of GEMM2)
+#define TC_NOBS 1024      // padded observation count
+#define TC_CHUNK 128      // observations per GEMM1 tile
+#define TC_NCHUNK (TC_NOBS / TC_CHUNK)
+#define TC_THREADS 288
+// canonical no-swizzle image: block (g = row/8, c = col/8) is 8 rows x 16 B, contiguous 128 B
+#define TC_SF 128u        // bytes between feature chunks (8 features) of one row group
+#define TC_SG 512u        // bytes between row groups (8 rows): TC_NF/8 * 128
+#define TC_XIMG_BYTES (TC_NOBS / 8 * TC_SG)      // 65536 per part
+#define TC_AIMG_BYTES (TC_CHAINS / 8 * TC_SG)    // 8192 per part
+// TMEM columns
+#define TC_COL_H 0        // 2 x 128 fp32 accumulator columns (GEMM1 output, then R head in place)
+#define TC_COL_G 256      // 32 fp32 accumulator columns (GEMM2 output)
+#define TC_COL_R2 288     // 2 x 64 columns: packed fp16 tail of R
+#define TC_TMEM_COLS 512
+
+struct TcSmem {
+  static constexpr uint32_t X1 = 0;
+  static constexpr uint32_t X2 = X1 + TC_XIMG_BYTES;
+  static constexpr uint32_t A1 = X2 + TC_XIMG_BYTES;
+  static constexpr uint32_t A2 = A1 + TC_AIMG_BYTES;
+  static constexpr uint32_t Y = A2 + TC_AIMG_BYTES;              // float[1024]
+  static constexpr uint32_t XCH = Y + TC_NOBS * 4;               // float[4][2][128]
+  static constexpr uint32_t BAR = XCH + 4 * 2 * TC_CHAINS * 4;   // 6 mbarriers
+  static constexpr uint32_t TMEM_PTR = BAR + 8 * 8;
+  static constexpr uint32_t BYTES = TMEM_PTR + 16;
 };
-static inline bool german_tc_auto(long long) { return false; }
-static inline int german_tc_hmc(GermanTc&, const HmcArgs&, const real*, cudaStream_t, DevBuf*, DevBuf*, DevBuf*,
-                                std::atomic<long long>*, std::string* err) {
-  *err = "tcgen05 engine not built";
-  return 1;
+
+// ---------------------------------------------------------------- PTX wrappers ---
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+// instruction descriptors: f16 x f16 -> f32, M = 128
+#define TC_IDESC_G1 ((1u << 4) | ((uint32_t)(TC_CHUNK >> 3) << 17) | ((128u >> 4) << 24))               // B K-major,  N = 128
+#define TC_IDESC_G2 ((1u << 4) | (1u << 16) | ((uint32_t)(TC_NF >> 3) << 17) | ((128u >> 4) << 24))     // B MN-major, N = 32
+
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+
+#define TC_LD32(taddr, v)                                                                                  \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                   \
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                    \
+               "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                   \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) \
+               : "r"(taddr) : "memory")
+#define TC_LD16(taddr, v)                                                                                  \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                   \
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                            \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+               : "r"(taddr) : "memory")
+#define TC_ST16(taddr, v)                                                                                  \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                             \
+               "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                  \
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory")
+
+// fp32 pair -> packed fp16x2 head (element 0 in the low half) and the packed tail of the remainders
+__device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+struct TcParams {
+  const uint8_t* ximg;  // X1 image followed by X2 image
+  const float* ypad;    // [TC_NOBS]
+  int N, F;
+};
+
+// ------------------------------------------------------------------------ kernel ---
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_a = sbase + TcSmem::BAR, bar_h0 = bar_a + 8, bar_r0 = bar_a + 24, bar_g = bar_a + 40;
+  float* sy = reinterpret_cast<float*>(smem + TcSmem::Y);
+  float* xch = reinterpret_cast<float*>(smem + TcSmem::XCH);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + TcSmem::TMEM_PTR);
+
+  // ---- one-time set-up: X image and y into shared memory, barriers, TMEM
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(tp.ximg);
+    uint4* dst = reinterpret_cast<uint4*>(smem + TcSmem::X1);
+    for (int i = tid; i < 2 * TC_XIMG_BYTES / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < TC_NOBS; i += TC_THREADS) sy[i] = __ldg(tp.ypad + i);
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                 "r"((uint32_t)TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(bar_a, 256);
+    mbar_init(bar_h0, 1); mbar_init(bar_h0 + 8, 1);
+    mbar_init(bar_r0, 256); mbar_init(bar_r0 + 8, 256);
+    mbar_init(bar_g, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_s;
+  const int n_lf = p.T * p.L;  // leapfrog steps = gradient evaluations per chain
+
+  if (warp == 8) {
+    // =========================== MMA issuer ===========================
+    uint32_t pa = 0, pr[2] = {0, 0};
+    const uint32_t sX[2] = {sbase + TcSmem::X1, sbase + TcSmem::X2};
+    const uint32_t sA[2] = {sbase + TcSmem::A1, sbase + TcSmem::A2};
+    // the three split products (head x head, tail x head, head x tail)
+    const int pa_sel[3] = {0, 0, 1}, pb_sel[3] = {0, 1, 0};
+    auto issue_g1 = [&](int c) {
+      const uint32_t d = tmem + TC_COL_H + (uint32_t)(c & 1) * TC_CHUNK;
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int ks = 0; ks < TC_NF / 16; ++ks) {
+          const uint64_t ad = tc_desc(sA[pa_sel[q]] + ks * 2 * TC_SF, TC_SF, TC_SG);
+          const uint64_t bd = tc_desc(sX[pb_sel[q]] + (uint32_t)c * (TC_CHUNK / 8) * TC_SG + ks * 2 * TC_SF, TC_SF, TC_SG);
+          mma_ss(d, ad, bd, TC_IDESC_G1, (q | ks) ? 1u : 0u);
+        }
+    };
+    auto issue_g2 = [&](int c) {
+      const uint32_t b = (uint32_t)(c & 1);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            // A: 16 observations = 8 packed columns; head in place of H, tail in its own buffer
+            const uint32_t a_t = pa_sel[q] == 0 ? tmem + TC_COL_H + b * TC_CHUNK + 64 * h + 8 * kk
+                                                : tmem + TC_COL_R2 + b * 64 + 32 * h + 8 * kk;
+            const uint32_t og = (uint32_t)c * (TC_CHUNK / 8) + 8 * h + 2 * kk;  // first 8-observation group
+            // MN-major B: N = features (chunks of 8 at TC_SF), K = observations (groups of 8 at TC_SG)
+            const uint64_t bd = tc_desc(sX[pb_sel[q]] + og * TC_SG, TC_SG, TC_SF);
+            mma_ts(tmem + TC_COL_G, a_t, bd, TC_IDESC_G2, (c | q | h | kk) ? 1u : 0u);
+          }
+    };
+    for (int s = 0; s < n_lf; ++s) {
+      mbar_wait(bar_a, pa); pa ^= 1;
+      tc_fence_after();
+      if (lane == 0) {
+        issue_g1(0); tc_commit(bar_h0);
+        issue_g1(1); tc_commit(bar_h0 + 8);
+      }
+      for (int c = 0; c < TC_NCHUNK; ++c) {
+        const int b = c & 1;
+        mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
+        tc_fence_after();
+        if (lane == 0) {
+          issue_g2(c);
+          if (c + 2 < TC_NCHUNK) { issue_g1(c + 2); tc_commit(bar_h0 + 8 * b); }
+          if (c == TC_NCHUNK - 1) tc_commit(bar_g);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ====================== chain workers (2 per chain) ======================
+    const int h = tid >> 7;                 // half
+    const int r = tid & 127;                // chain within the CTA = TMEM lane
+    const int chain = blockIdx.x * TC_CHAINS + r;
+    const bool valid = chain < p.C;
+    const int D = p.D, F = tp.F;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const size_t co = (size_t)chain * ws.sc;
+    Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
+    Vec X{ws.x + co, ws.sd}, GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
+    Vec V{ws.v + co, ws.sd};
+    const float* __restrict__ eps0 = p.eps0;
+    float lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
+    int nacc = ws.nacc[chain];
+    const unsigned int gchain = p.chain_offset + (unsigned int)chain;
+    const int nb = (D + 3) >> 2;
+    uint32_t ph[2] = {0, 0}, pg = 0;
+    const float a0 = p.a[0], b0 = p.b[0];
+    uint8_t* a_row1 = smem + TcSmem::A1 + (r >> 3) * TC_SG + (r & 7) * 16;
+    uint8_t* a_row2 = smem + TcSmem::A2 + (r >> 3) * TC_SG + (r & 7) * 16;
+    const float NLOG2E = -1.4426950408889634f;
+
+    for (int t = 0; t < p.T; ++t) {
+      const int tg = p.t_begin + t;
+      // ---- momenta (Philox block j belongs to half j & 1); proposal starts at the current state
+      float ke0 = 0.f, ke1 = 0.f;
+      for (int j = h; j < nb; j += 2) {
+        float n4[4];
+        if (p.ext_momenta) {
+          const float* mom = p.ext_momenta + ((size_t)tg * p.C + (valid ? chain : 0)) * D;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) n4[q] = (4 * j + q < D) ? mom[4 * j + q] : 0.f;
+        } else {
+          philox_normal4(p.seed, gchain, (unsigned int)tg, (unsigned int)j, ARP_STREAM_MOMENTUM, n4);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int d = 4 * j + q;
+          if (d < D) {
+            V(d) = n4[q];
+            ke0 = fmaf(n4[q], n4[q], ke0);
+            X(d) = Z(d);
+            GX(d) = G(d);
+          }
+        }
+      }
+      float lpx = 0.f;
+      for (int l = 0; l < p.L; ++l) {
+        const bool last = (l == p.L - 1);
+        // ---- first half kick + drift
+        for (int j = h; j < nb; j += 2)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int d = 4 * j + q;
+            if (d < D) {
+              const float e = __ldg(eps0 + d) * mult;
+              const float v = V(d) + 0.5f * e * GX(d);
+              V(d) = v;
+              X(d) = X(d) + e * v;
+            }
+          }
+        epi_bar();
+        // ---- site forward: centred log-scales and coefficients of my 16 features -> A operand (head, tail)
+        float lp_top = 0.f;
+        const Site s0 = site_fwd(X(0), 0.f, ARP_LOG_10, a0, b0, lp_top);
+        if (h == 0) XCX(0) = s0.x;
+#pragma unroll
+        for (int fc = 0; fc < 2; ++fc) {
+          float be[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int f = 16 * h + 8 * fc + i;
+            be[i] = 0.f;
+            if (f < F) {
+              float dummy = 0.f;
+              const Site ss = site_fwd_unit(X(1 + f), s0.x, p.a[1 + f], dummy);
+              const Site sb = site_fwd(X(1 + F + f), 0.f, ss.x, p.a[1 + F + f], p.b[1 + F + f], dummy);
+              XCX(1 + f) = ss.x;
+              XCX(1 + F + f) = sb.x;
+              be[i] = sb.x;
+            }
+          }
+          uint4 hi, lo;
+          split_pack(be[0], be[1], hi.x, lo.x);
+          split_pack(be[2], be[3], hi.y, lo.y);
+          split_pack(be[4], be[5], hi.z, lo.z);
+          split_pack(be[6], be[7], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(a_row1 + (2 * h + fc) * TC_SF) = hi;
+          *reinterpret_cast<uint4*>(a_row2 + (2 * h + fc) * TC_SF) = lo;
+        }
+        fence_async_smem();
+        tc_fence_before();  // orders last step's tcgen05.ld of G before the issuer's next MMAs
+        mbar_arrive(bar_a);
+        // ---- likelihood epilogue: H -> R = y - sigmoid(H), 8 chunks of 128 observations
+        float lik = 0.f;
+        for (int c = 0; c < TC_NCHUNK; ++c) {
+          const int b = c & 1;
+          mbar_wait(bar_h0 + 8 * b, ph[b]); ph[b] ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint32_t hv[32];
+            TC_LD32(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 64 * h + 32 * sub, hv);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int n0 = c * TC_CHUNK + 64 * h + 32 * sub;
+            uint32_t r1[16], r2[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 y4 = *reinterpret_cast<const float4*>(sy + n0 + i);
+              const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+              float rr[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float eta = __uint_as_float(hv[i + q]);
+                const float sg = __fdividef(1.0f, 1.0f + exp2f(eta * NLOG2E));
+                rr[q] = yy[q] - sg;
+                if (last) {
+                  // y eta - softplus(eta), softplus = max(eta,0) - log(sigmoid(|eta|))
+                  const float m = fmaxf(sg, 1.0f - sg);
+                  const float term = yy[q] * eta - fmaxf(eta, 0.f) + __logf(m);
+                  lik += (n0 + i + q < tp.N) ? term : 0.f;
+                }
+              }
+              split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
+              split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
+            }
+            TC_ST16(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 64 * h + 16 * sub, r1);
+            TC_ST16(tmem + lane_off + TC_COL_R2 + b * 64 + 32 * h + 16 * sub, r2);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          mbar_arrive(bar_r0 + 8 * b);
+        }
+        // ---- gradient wrt beta from TMEM, reverse through the sites
+        mbar_wait(bar_g, pg); pg ^= 1;
+        tc_fence_after();
+        uint32_t gv[16];
+        TC_LD16(tmem + lane_off + TC_COL_G + 16 * h, gv);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float acc0 = 0.f, lps = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int f = 16 * h + i;
+          if (f < F) {
+            const float af = p.a[1 + f], ab_ = p.a[1 + F + f], bb_ = p.b[1 + F + f];
+            const Site ss = site_fwd_unit(X(1 + f), s0.x, af, lps);
+            const Site sb = site_fwd(X(1 + F + f), 0.f, ss.x, ab_, bb_, lps);
+            float zb, mb, lb, ab;
+            site_rev(sb, __uint_as_float(gv[i]), 0.f, ab_, bb_, zb, mb, lb, ab);
+            GX(1 + F + f) = zb;
+            float zb2, mb2, lb2, ab2;
+            site_rev(ss, lb, s0.x, af, 1.f, zb2, mb2, lb2, ab2);
+            GX(1 + f) = zb2;
+            acc0 += mb2;
+          }
+        }
+        xch[(0 * 2 + h) * TC_CHAINS + r] = acc0;
+        xch[(1 * 2 + h) * TC_CHAINS + r] = lik + lps;
+        epi_bar();
+        const float acc0_t = xch[(0 * 2 + 0) * TC_CHAINS + r] + xch[(0 * 2 + 1) * TC_CHAINS + r];
+        lpx = xch[(1 * 2 + 0) * TC_CHAINS + r] + xch[(1 * 2 + 1) * TC_CHAINS + r] + lp_top;
+        if (h == 0) {
+          float zb, mb, lb, ab;
+          site_rev(s0, acc0_t, 0.f, a0, b0, zb, mb, lb, ab);
+          GX(0) = zb;
+        }
+        epi_bar();
+        // ---- second half kick
+        for (int j = h; j < nb; j += 2)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int d = 4 * j + q;
+            if (d < D) {
+              const float e = __ldg(eps0 + d) * mult;
+              const float v = V(d) + 0.5f * e * GX(d);
+              V(d) = v;
+              if (last) ke1 = fmaf(v, v, ke1);
+            }
+          }
+      }
+      // ---- Metropolis-Hastings (both halves compute the same decision)
+      xch[(2 * 2 + h) * TC_CHAINS + r] = ke0;
+      xch[(3 * 2 + h) * TC_CHAINS + r] = ke1;
+      epi_bar();
+      ke0 = xch[(2 * 2 + 0) * TC_CHAINS + r] + xch[(2 * 2 + 1) * TC_CHAINS + r];
+      ke1 = xch[(3 * 2 + 0) * TC_CHAINS + r] + xch[(3 * 2 + 1) * TC_CHAINS + r];
+      float log_alpha = lpx - lp_cur + 0.5f * ke0 - 0.5f * ke1;
+      if (!(log_alpha == log_alpha) || log_alpha == -INFINITY) log_alpha = -INFINITY;
+      float log_u;
+      if (p.ext_log_u) log_u = p.ext_log_u[(size_t)tg * p.C + (valid ? chain : 0)];
+      else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
+      const bool acc = log_u < log_alpha;
+      if (acc) {
+        for (int j = h; j < nb; j += 2)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int d = 4 * j + q;
+            if (d < D) { Z(d) = X(d); G(d) = GX(d); XC(d) = XCX(d); }
+          }
+        lp_cur = lpx;
+        ++nacc;
+      }
+      const int t1 = tg + 1;
+      if (t1 <= p.num_adapt) {
+        const float ft = (float)t1;
+        Hc += p.target_accept - expf(log_alpha < 0.f ? log_alpha : 0.f);
+        const float log_step = ARP_LOG_10 - Hc * sqrtf(ft) / ((ft + 10.f) * 0.05f);
+        const float eta = powf(ft, -0.75f);
+        lavg = eta * log_step + (1.f - eta) * lavg;
+        mult = (t1 < p.num_adapt) ? expf(log_step) : expf(lavg);
+      }
+      const int since = tg - p.num_burnin;
+      if (since >= 0 && (since % p.stride) == 0 && valid) {
+        const int s = since / p.stride;
+        if (s < p.S) {
+          const size_t o = ((size_t)s * p.C + chain) * D;
+          for (int j = h; j < nb; j += 2)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int d = 4 * j + q;
+              if (d < D) {
+                if (p.samples) p.samples[o + d] = XC(d);
+                if (p.samples_orig) p.samples_orig[o + d] = Z(d);
+              }
+            }
+          if (p.is_accepted && h == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
+        }
+      }
+      epi_bar();
+    }
+    if (h == 0) {
+      ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------- host ---
+struct GermanTc {
+  DevBuf ximg, ypad;
+  int N = 0, F = 0;
+  bool ok = false;
+
+  // X [N, F] fp32 row-major -> fp16 head/tail canonical images (zero padded to 1024 x 32)
+  bool build(const float* X, const float* y, int n, int f, std::string* err) {
+    ok = false;
+    if (n > TC_NOBS || f > TC_NF) return true;  // not an error: the SIMT engine handles it
+    std::vector<__half> img((size_t)2 * TC_XIMG_BYTES / 2, __float2half(0.f));
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < f; ++j) {
+        const float x = X[(size_t)i * f + j];
+        if (!(fabsf(x) < 60000.f)) return true;  // outside fp16 range: SIMT engine only
+        const __half h1 = __float2half_rn(x);
+        const __half h2 = __float2half_rn(x - __half2float(h1));
+        const size_t off = ((size_t)(i / 8) * TC_SG + (size_t)(j / 8) * TC_SF + (size_t)(i % 8) * 16) / 2 + (j % 8);
+        img[off] = h1;
+        img[TC_XIMG_BYTES / 2 + off] = h2;
+      }
+    std::vector<float> yp(TC_NOBS, 0.f);
+    for (int i = 0; i < n; ++i) yp[i] = y[i];
+    cudaError_t e = upload(ximg, img);
+    if (e == cudaSuccess) e = upload(ypad, yp);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return false; }
+    N = n; F = f; ok = true;
+    return true;
+  }
+  bool ready() const { return ok; }
+};
+
+static inline bool german_tc_auto(long long C) { return C >= 2 * TC_CHAINS; }
+
+__global__ void k_gather_ws_tc(const real* ws, int sd, int sc, int C, int D, real* out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)C * D) return;
+  const int c = (int)(i / D), d = (int)(i % D);
+  out[i] = ws[(size_t)d * sd + (size_t)c * sc];
+}
+
+// Runs the whole HMC job on the tcgen05 engine.  wsbuf / scal / nacc keep the
+// workspace alive for the caller (final state, step multipliers, accept counts).
+static inline int german_tc_hmc(GermanTc& tc, const DevModel& dm, const HmcArgs& p, const real* z0, cudaStream_t st,
+                                bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
+                                std::atomic<long long>* launches, std::string* err) {
+#define TC_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(_e); return 1; } } while (0)
+  const long long C = p.C;
+  const long long Cpad = (C + TC_CHAINS - 1) / TC_CHAINS * TC_CHAINS;
+  const long long Dpad = (p.D + 7) / 8 * 8;
+  const size_t vec = (size_t)Cpad * Dpad;
+  TC_CUDA(wsbuf->alloc(7 * vec * sizeof(real)));
+  TC_CUDA(cudaMemsetAsync(wsbuf->p, 0, 7 * vec * sizeof(real), st));
+  TC_CUDA(scal->alloc(4 * Cpad * sizeof(real)));
+  TC_CUDA(nacc->alloc(Cpad * sizeof(int)));
+  HmcWs ws{};
+  real* base = wsbuf->as<real>();
+  ws.z = base; ws.g = base + vec; ws.xc = base + 2 * vec; ws.x = base + 3 * vec;
+  ws.gx = base + 4 * vec; ws.xcx = base + 5 * vec; ws.v = base + 6 * vec;
+  real* sb = scal->as<real>();
+  ws.mult = sb; ws.lp = sb + Cpad; ws.H = sb + 2 * Cpad; ws.lavg = sb + 3 * Cpad;
+  ws.nacc = nacc->as<int>();
+  ws.sd = (int)Cpad; ws.sc = 1;  // [d][chain]: one thread per chain, coalesced
+  const dim3 grid((unsigned)(Cpad / TC_CHAINS));
+  // bootstrap (log-prob, gradient, centred values of the initial state) on the SIMT kernel
+  k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 32><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
+  launches->fetch_add(1);
+  TC_CUDA(cudaGetLastError());
+  TcParams tp{tc.ximg.as<uint8_t>(), tc.ypad.as<float>(), tc.N, tc.F};
+  TC_CUDA(cudaFuncSetAttribute(k_german_tc_hmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem::BYTES));
+  k_german_tc_hmc<<<grid, TC_THREADS, TcSmem::BYTES, st>>>(tp, ws, p);
+  launches->fetch_add(1);
+  TC_CUDA(cudaGetLastError());
+  if (want_final) {
+    TC_CUDA(dfz->alloc((size_t)C * p.D * sizeof(real)));
+    const long long n = C * p.D;
+    k_gather_ws_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.z, ws.sd, ws.sc, (int)C, p.D, dfz->as<real>());
+    launches->fetch_add(1);
+    TC_CUDA(cudaGetLastError());
+  }
+#undef TC_CUDA
+  return 0;
+}
+
 }  // namespace arp

@@ -334,7 +334,8 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
 
 #ifndef ARP_FP64
   if (use_tc) {
-    int rc = german_tc_hmc(m->tc, p, z0, st, &dfz, &scal, &nacc, &g_launches, &g_last_error);
+    int rc = german_tc_hmc(m->tc, m->dev, p, z0, st, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc, &g_launches,
+                           &g_last_error);
     if (rc) return rc;
     final_z_dev = dfz.as<real>();
     out_mult_dev = scal.as<real>();

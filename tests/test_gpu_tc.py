@@ -1,0 +1,102 @@
+"""GPU parity of the tcgen05 German-credit engine (split-fp16 MMA, fp32 accumulate)
+against the fp64 oracle and against the SIMT fp32 engine."""
+import numpy as np
+import pytest
+
+from autoreparam_b200 import engine
+from oracle import oracle as O
+from tests import common
+
+pytestmark = pytest.mark.gpu
+MODEL = "german_credit_lognormalcentered"
+
+
+def _case(method, C, seed):
+    mc = common.model_config("german_synth")
+    raw = common.raw_data("german_synth")
+    D = mc.num_coords
+    a, b = common.ab_for(method, D)
+    z0 = common.random_states("german_synth", D, C, seed=seed, scale=0.3).astype(np.float32).astype(np.float64)
+    return mc, raw, D, a, b, z0
+
+
+@pytest.mark.parametrize("method", ["CP", "NCP", "VIP_a", "VIP_ab"])
+def test_tc_single_leapfrog_gradient(method):
+    """One transition of one leapfrog step with zero momenta and a tiny step:
+    the proposal equals z0 + eps^2/2 * grad, which exposes the tensor-core
+    gradient itself: 1e-5 relative to the fp64 oracle gradient."""
+    C = 9
+    mc, raw, D, a, b, z0 = _case(method, C, seed=31)
+    _, g_ref = O.log_joint_and_grad(MODEL, raw, z0, a, b)
+    eps = 2.0 ** -6
+    eps0 = np.full(D, eps)
+    mom = np.zeros((1, C, D))
+    lu = np.full((1, C), -1e30)   # always accept
+    out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=1, num_results=1, num_burnin_steps=0,
+                         num_adaptation_steps=0, ext_momenta=mom, ext_log_u=lu, want_orig=True,
+                         engine=engine.ENGINE_TCGEN05)
+    assert out["is_accepted"].all()
+    g_tc = (out["samples_orig"][0].astype(np.float64) - z0) / (0.5 * eps * eps)
+    # z0 + eps^2/2 g is rounded to fp32: recover g only to ~ulp(z)/(eps^2/2); compare with that allowance
+    err = np.abs(g_tc - g_ref).max(axis=1)
+    allow = 1e-5 * np.maximum(np.abs(g_ref).max(axis=1), 1.0) + 2.0 ** -23 * np.abs(z0).max() / (0.5 * eps * eps)
+    assert (err < allow).all(), (err, allow)
+
+
+@pytest.mark.parametrize("method", ["NCP", "VIP_a"])
+def test_tc_fixed_momenta_trajectory(method):
+    C, L, S, burn, adapt = 6, 3, 3, 2, 4
+    mc, raw, D, a, b, z0 = _case(method, C, seed=32)
+    T = O.num_transitions(S, burn)
+    rng = np.random.default_rng(8)
+    mom = rng.standard_normal((T, C, D)).astype(np.float32).astype(np.float64)
+    lu = np.log(rng.uniform(size=(T, C))).astype(np.float32).astype(np.float64)
+    eps0 = (np.full(D, 0.01) * rng.uniform(0.5, 1.5, D)).astype(np.float32).astype(np.float64)
+    ref = O.hmc_chain(MODEL, raw, z0, eps0, L, S, burn, adapt, a, b, momenta=mom, log_u=lu)
+    out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn,
+                         num_adaptation_steps=adapt, ext_momenta=mom, ext_log_u=lu, want_orig=True,
+                         engine=engine.ENGINE_TCGEN05)
+    assert (out["is_accepted"].astype(bool) == ref["is_accepted"]).all()
+    assert ref["is_accepted"].mean() > 0
+    err = common.rel_err(out["samples"].reshape(S * C, D), ref["samples_centered"].reshape(S * C, D)).max()
+    # 8 transitions x 3 leapfrog steps amplify the per-evaluation round-off (which the test above pins at 1e-5)
+    assert err < 2e-3, err
+    assert common.rel_err(out["step_mult"], ref["step_mult"]).max() < 1e-3
+
+
+def test_tc_matches_simt_engine_many_chains():
+    """Several CTAs incl. a ragged tail, internal Philox momenta: the two engines
+    draw identical random numbers, so short runs agree to fp32 round-off."""
+    C, L, S, burn, adapt = 128 * 2 + 37, 4, 2, 2, 3
+    mc, raw, D, a, b, z0 = _case("NCP", C, seed=33)
+    eps0 = np.full(D, 0.02)
+    kw = dict(num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn, num_adaptation_steps=adapt, seed=99,
+              chain_offset=5)
+    o1 = engine.hmc_run(mc, z0, eps0, a, b, engine=engine.ENGINE_SIMT, **kw)
+    o2 = engine.hmc_run(mc, z0, eps0, a, b, engine=engine.ENGINE_TCGEN05, **kw)
+    same = o1["is_accepted"] == o2["is_accepted"]
+    assert same.mean() > 0.995, same.mean()
+    ok = same.all(axis=0)
+    err = common.rel_err(o2["samples"][:, ok].reshape(-1, D), o1["samples"][:, ok].reshape(-1, D))
+    # after the first transition the adapted step is 10 x eps0: a few chains amplify round-off strongly
+    assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 1e-2, (np.median(err), np.quantile(err, 0.99))
+    assert (o1["accept_count"][ok] == o2["accept_count"][ok]).all()
+
+
+def test_tc_posterior_agrees_with_simt():
+    """Posterior means / sds from the two engines agree within Monte-Carlo error."""
+    C = 512
+    mc, raw, D, a, b, z0 = _case("NCP", C, seed=34)
+    eps0 = np.full(D, 0.05)
+    kw = dict(num_leapfrog_steps=4, num_results=150, num_burnin_steps=400, num_adaptation_steps=300)
+    o1 = engine.hmc_run(mc, z0 * 0.3, eps0, a, b, engine=engine.ENGINE_SIMT, seed=1, **kw)
+    o2 = engine.hmc_run(mc, z0 * 0.3, eps0, a, b, engine=engine.ENGINE_TCGEN05, seed=2, **kw)
+    for o in (o1, o2):
+        assert 0.5 < o["is_accepted"].mean() < 0.98
+    x1, x2 = o1["samples"].astype(np.float64), o2["samples"].astype(np.float64)
+    m1, m2 = x1.mean(axis=(0, 1)), x2.mean(axis=(0, 1))
+    s1, s2 = x1.std(axis=(0, 1)), x2.std(axis=(0, 1))
+    # chain means are independent across chains: sd of the grand mean <= posterior sd / sqrt(C)
+    z = np.abs(m1 - m2) / (np.sqrt(s1 ** 2 + s2 ** 2) / np.sqrt(C))
+    assert z.max() < 6.0, z.max()
+    assert np.median(np.abs(s1 / s2 - 1)) < 0.05 and np.abs(s1 / s2 - 1).max() < 0.25  # slow-mixing log-scales
