@@ -54,6 +54,8 @@ namespace arp {
 #define TC_COL_R2 288     // 2 x 64 columns: packed fp16 tail of R
 #define TC_TMEM_COLS 512
 
+#define TC_NLOC 33        // coordinates a worker thread owns: overall_log_scale (replicated) + 16 log-scales + 16 betas
+
 struct TcSmem {
   static constexpr uint32_t X1 = 0;
   static constexpr uint32_t X2 = X1 + TC_XIMG_BYTES;
@@ -61,10 +63,13 @@ struct TcSmem {
   static constexpr uint32_t A2 = A1 + TC_AIMG_BYTES;
   static constexpr uint32_t Y = A2 + TC_AIMG_BYTES;              // float[1024]
   static constexpr uint32_t XCH = Y + TC_NOBS * 4;               // float[4][2][128]
-  static constexpr uint32_t BAR = XCH + 4 * 2 * TC_CHAINS * 4;   // 6 mbarriers
+  static constexpr uint32_t XS = XCH + 4 * 2 * TC_CHAINS * 4;    // float[TC_NLOC][256]: thread-private proposal x
+  static constexpr uint32_t PAR = XS + TC_NLOC * 256 * 4;        // float[3][2*TC_NF+4]: a, b, eps0 per coordinate
+  static constexpr uint32_t BAR = PAR + 3 * (2 * TC_NF + 4) * 4; // 6 mbarriers
   static constexpr uint32_t TMEM_PTR = BAR + 8 * 8;
   static constexpr uint32_t BYTES = TMEM_PTR + 16;
 };
+static_assert(TcSmem::BYTES <= 232448, "shared memory budget");
 
 // ---------------------------------------------------------------- PTX wrappers ---
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,6 +149,22 @@ __device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hi, uin
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct TcParams {
   const uint8_t* ximg;  // X1 image followed by X2 image
   const float* ypad;    // [TC_NOBS]
@@ -167,6 +188,12 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
     uint4* dst = reinterpret_cast<uint4*>(smem + TcSmem::X1);
     for (int i = tid; i < 2 * TC_XIMG_BYTES / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
     for (int i = tid; i < TC_NOBS; i += TC_THREADS) sy[i] = __ldg(tp.ypad + i);
+    float* par = reinterpret_cast<float*>(smem + TcSmem::PAR);
+    for (int i = tid; i < p.D; i += TC_THREADS) {
+      par[i] = p.a[i];
+      par[(2 * TC_NF + 4) + i] = p.b[i];
+      par[2 * (2 * TC_NF + 4) + i] = p.eps0[i];
+    }
   }
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
@@ -243,85 +270,85 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
     }
   } else {
     // ====================== chain workers (2 per chain) ======================
+    // Worker (chain r, half h) owns features f = 16h + k (k < 16, f < F): local coordinate 1 + k is the
+    // log-scale d = 1 + f, local 17 + k is the coefficient d = 1 + F + f; local 0 (overall_log_scale, d = 0)
+    // is replicated in both halves.  Momentum lives in registers, the proposal x in a private smem column.
     const int h = tid >> 7;                 // half
     const int r = tid & 127;                // chain within the CTA = TMEM lane
     const int chain = blockIdx.x * TC_CHAINS + r;
     const bool valid = chain < p.C;
     const int D = p.D, F = tp.F;
+    const int nf = max(0, min(16, F - 16 * h));   // features owned
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const size_t co = (size_t)chain * ws.sc;
     Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
-    Vec X{ws.x + co, ws.sd}, GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
-    Vec V{ws.v + co, ws.sd};
-    const float* __restrict__ eps0 = p.eps0;
+    Vec GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
+    float* xs = reinterpret_cast<float*>(smem + TcSmem::XS) + tid;           // xs[i * 256]
+    const float* pa_s = reinterpret_cast<const float*>(smem + TcSmem::PAR);  // a[d]
+    const float* pb_s = pa_s + (2 * TC_NF + 4);                              // b[d]
+    const float* pe_s = pb_s + (2 * TC_NF + 4);                              // eps0[d]
     float lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
     int nacc = ws.nacc[chain];
     const unsigned int gchain = p.chain_offset + (unsigned int)chain;
-    const int nb = (D + 3) >> 2;
     uint32_t ph[2] = {0, 0}, pg = 0;
-    const float a0 = p.a[0], b0 = p.b[0];
+    const float a0 = pa_s[0], b0 = pb_s[0];
     uint8_t* a_row1 = smem + TcSmem::A1 + (r >> 3) * TC_SG + (r & 7) * 16;
     uint8_t* a_row2 = smem + TcSmem::A2 + (r >> 3) * TC_SG + (r & 7) * 16;
     const float NLOG2E = -1.4426950408889634f;
+    // global coordinate of local coordinate i
+    auto dof = [&](int i) { return i == 0 ? 0 : (i <= 16 ? 16 * h + i : F + 16 * h + i - 16); };
+    auto owned = [&](int i) { return i == 0 || (i <= 16 ? (i - 1) < nf : (i - 17) < nf); };
 
     for (int t = 0; t < p.T; ++t) {
       const int tg = p.t_begin + t;
-      // ---- momenta (Philox block j belongs to half j & 1); proposal starts at the current state
-      float ke0 = 0.f, ke1 = 0.f;
-      for (int j = h; j < nb; j += 2) {
+      // ---- momenta for my coordinates; first half kick + drift from the current state
+      float v[TC_NLOC];
+      float ke0 = 0.f, ke1 = 0.f;   // coordinate 0 is counted by half 0 only
+      {
         float n4[4];
-        if (p.ext_momenta) {
-          const float* mom = p.ext_momenta + ((size_t)tg * p.C + (valid ? chain : 0)) * D;
+        int jcur = -1;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) n4[q] = (4 * j + q < D) ? mom[4 * j + q] : 0.f;
-        } else {
-          philox_normal4(p.seed, gchain, (unsigned int)tg, (unsigned int)j, ARP_STREAM_MOMENTUM, n4);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int d = 4 * j + q;
-          if (d < D) {
-            V(d) = n4[q];
-            ke0 = fmaf(n4[q], n4[q], ke0);
-            X(d) = Z(d);
-            GX(d) = G(d);
+        for (int i = 0; i < TC_NLOC; ++i) {
+          v[i] = 0.f;
+          if (owned(i)) {
+            const int d = dof(i);
+            if (p.ext_momenta) {
+              v[i] = p.ext_momenta[((size_t)tg * p.C + (valid ? chain : 0)) * D + d];
+            } else {
+              if ((d >> 2) != jcur) {
+                jcur = d >> 2;
+                philox_normal4(p.seed, gchain, (unsigned int)tg, (unsigned int)jcur, ARP_STREAM_MOMENTUM, n4);
+              }
+              v[i] = (d & 3) == 0 ? n4[0] : ((d & 3) == 1 ? n4[1] : ((d & 3) == 2 ? n4[2] : n4[3]));
+            }
+            if (i > 0 || h == 0) ke0 = fmaf(v[i], v[i], ke0);
+            const float e = pe_s[d] * mult;
+            v[i] = v[i] + 0.5f * e * G(d);
+            xs[i * 256] = Z(d) + e * v[i];
           }
         }
       }
       float lpx = 0.f;
       for (int l = 0; l < p.L; ++l) {
         const bool last = (l == p.L - 1);
-        // ---- first half kick + drift
-        for (int j = h; j < nb; j += 2)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int d = 4 * j + q;
-            if (d < D) {
-              const float e = __ldg(eps0 + d) * mult;
-              const float v = V(d) + 0.5f * e * GX(d);
-              V(d) = v;
-              X(d) = X(d) + e * v;
-            }
-          }
-        epi_bar();
-        // ---- site forward: centred log-scales and coefficients of my 16 features -> A operand (head, tail)
+        // ---- site forward: centred log-scales and coefficients of my features -> A operand (head, tail)
         float lp_top = 0.f;
-        const Site s0 = site_fwd(X(0), 0.f, ARP_LOG_10, a0, b0, lp_top);
-        if (h == 0) XCX(0) = s0.x;
+        const Site s0 = site_fwd(xs[0], 0.f, ARP_LOG_10, a0, b0, lp_top);
+        if (last && h == 0) XCX(0) = s0.x;
 #pragma unroll
         for (int fc = 0; fc < 2; ++fc) {
           float be[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int f = 16 * h + 8 * fc + i;
-            be[i] = 0.f;
-            if (f < F) {
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const int k = 8 * fc + k8;
+            be[k8] = 0.f;
+            if (k < nf) {
+              const int f = 16 * h + k;
               float dummy = 0.f;
-              const Site ss = site_fwd_unit(X(1 + f), s0.x, p.a[1 + f], dummy);
-              const Site sb = site_fwd(X(1 + F + f), 0.f, ss.x, p.a[1 + F + f], p.b[1 + F + f], dummy);
-              XCX(1 + f) = ss.x;
-              XCX(1 + F + f) = sb.x;
-              be[i] = sb.x;
+              const Site ss = site_fwd_unit(xs[(1 + k) * 256], s0.x, pa_s[1 + f], dummy);
+              const Site sb = site_fwd(xs[(17 + k) * 256], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
+              if (last) { XCX(1 + f) = ss.x; XCX(1 + F + f) = sb.x; }
+              be[k8] = sb.x;
             }
           }
           uint4 hi, lo;
@@ -341,11 +368,12 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
           const int b = c & 1;
           mbar_wait(bar_h0 + 8 * b, ph[b]); ph[b] ^= 1;
           tc_fence_after();
+          uint32_t hv[2][32];
+          TC_LD32(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 64 * h, hv[0]);
+          TC_LD32(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 64 * h + 32, hv[1]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
-            uint32_t hv[32];
-            TC_LD32(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 64 * h + 32 * sub, hv);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int n0 = c * TC_CHUNK + 64 * h + 32 * sub;
             uint32_t r1[16], r2[16];
 #pragma unroll
@@ -355,13 +383,13 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
               float rr[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const float eta = __uint_as_float(hv[i + q]);
-                const float sg = __fdividef(1.0f, 1.0f + exp2f(eta * NLOG2E));
+                const float eta = __uint_as_float(hv[sub][i + q]);
+                const float sg = rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
                 rr[q] = yy[q] - sg;
                 if (last) {
-                  // y eta - softplus(eta), softplus = max(eta,0) - log(sigmoid(|eta|))
+                  // y eta - softplus(eta), softplus(eta) = max(eta,0) - log(sigmoid(|eta|))
                   const float m = fmaxf(sg, 1.0f - sg);
-                  const float term = yy[q] * eta - fmaxf(eta, 0.f) + __logf(m);
+                  const float term = fmaf(lg2_approx(m), 0.69314718055994531f, yy[q] * eta - fmaxf(eta, 0.f));
                   lik += (n0 + i + q < tp.N) ? term : 0.f;
                 }
               }
@@ -375,7 +403,7 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
           tc_fence_before();
           mbar_arrive(bar_r0 + 8 * b);
         }
-        // ---- gradient wrt beta from TMEM, reverse through the sites
+        // ---- gradient wrt beta from TMEM; reverse through my sites, kicks and drift fused in
         mbar_wait(bar_g, pg); pg ^= 1;
         tc_fence_after();
         uint32_t gv[16];
@@ -383,19 +411,33 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float acc0 = 0.f, lps = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int f = 16 * h + i;
-          if (f < F) {
-            const float af = p.a[1 + f], ab_ = p.a[1 + F + f], bb_ = p.b[1 + F + f];
-            const Site ss = site_fwd_unit(X(1 + f), s0.x, af, lps);
-            const Site sb = site_fwd(X(1 + F + f), 0.f, ss.x, ab_, bb_, lps);
-            float zb, mb, lb, ab;
-            site_rev(sb, __uint_as_float(gv[i]), 0.f, ab_, bb_, zb, mb, lb, ab);
-            GX(1 + F + f) = zb;
-            float zb2, mb2, lb2, ab2;
-            site_rev(ss, lb, s0.x, af, 1.f, zb2, mb2, lb2, ab2);
-            GX(1 + f) = zb2;
+        for (int k = 0; k < 16; ++k) {
+          if (k < nf) {
+            const int f = 16 * h + k;
+            const float af = pa_s[1 + f], ab_ = pa_s[1 + F + f], bb_ = pb_s[1 + F + f];
+            const float xs_s = xs[(1 + k) * 256], xs_b = xs[(17 + k) * 256];
+            const Site ss = site_fwd_unit(xs_s, s0.x, af, lps);
+            const Site sb = site_fwd(xs_b, 0.f, ss.x, ab_, bb_, lps);
+            float gb, mb, lb, ab;
+            site_rev(sb, __uint_as_float(gv[k]), 0.f, ab_, bb_, gb, mb, lb, ab);
+            float gs, mb2, lb2, ab2;
+            site_rev(ss, lb, s0.x, af, 1.f, gs, mb2, lb2, ab2);
             acc0 += mb2;
+            // second half kick of this step, then (unless last) first half kick + drift of the next
+            const float es = pe_s[1 + f] * mult, eb = pe_s[1 + F + f] * mult;
+            v[1 + k] = v[1 + k] + 0.5f * es * gs;
+            v[17 + k] = v[17 + k] + 0.5f * eb * gb;
+            if (last) {
+              ke1 = fmaf(v[1 + k], v[1 + k], ke1);
+              ke1 = fmaf(v[17 + k], v[17 + k], ke1);
+              GX(1 + f) = gs;
+              GX(1 + F + f) = gb;
+            } else {
+              v[1 + k] = v[1 + k] + 0.5f * es * gs;
+              v[17 + k] = v[17 + k] + 0.5f * eb * gb;
+              xs[(1 + k) * 256] = xs_s + es * v[1 + k];
+              xs[(17 + k) * 256] = xs_b + eb * v[17 + k];
+            }
           }
         }
         xch[(0 * 2 + h) * TC_CHAINS + r] = acc0;
@@ -403,24 +445,19 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
         epi_bar();
         const float acc0_t = xch[(0 * 2 + 0) * TC_CHAINS + r] + xch[(0 * 2 + 1) * TC_CHAINS + r];
         lpx = xch[(1 * 2 + 0) * TC_CHAINS + r] + xch[(1 * 2 + 1) * TC_CHAINS + r] + lp_top;
-        if (h == 0) {
-          float zb, mb, lb, ab;
-          site_rev(s0, acc0_t, 0.f, a0, b0, zb, mb, lb, ab);
-          GX(0) = zb;
-        }
-        epi_bar();
-        // ---- second half kick
-        for (int j = h; j < nb; j += 2)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int d = 4 * j + q;
-            if (d < D) {
-              const float e = __ldg(eps0 + d) * mult;
-              const float v = V(d) + 0.5f * e * GX(d);
-              V(d) = v;
-              if (last) ke1 = fmaf(v, v, ke1);
-            }
+        {
+          float g0, mb, lb, ab;
+          site_rev(s0, acc0_t, 0.f, a0, b0, g0, mb, lb, ab);
+          const float e = pe_s[0] * mult;
+          v[0] = v[0] + 0.5f * e * g0;
+          if (last) {
+            if (h == 0) { ke1 = fmaf(v[0], v[0], ke1); GX(0) = g0; }
+          } else {
+            v[0] = v[0] + 0.5f * e * g0;
+            xs[0] = xs[0] + e * v[0];
           }
+        }
+        epi_bar();  // xch is rewritten by the next step
       }
       // ---- Metropolis-Hastings (both halves compute the same decision)
       xch[(2 * 2 + h) * TC_CHAINS + r] = ke0;
@@ -435,11 +472,11 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
       else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
       const bool acc = log_u < log_alpha;
       if (acc) {
-        for (int j = h; j < nb; j += 2)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int d = 4 * j + q;
-            if (d < D) { Z(d) = X(d); G(d) = GX(d); XC(d) = XCX(d); }
+        for (int i = 0; i < TC_NLOC; ++i)
+          if (owned(i) && (i > 0 || h == 0)) {
+            const int d = dof(i);
+            Z(d) = xs[i * 256]; G(d) = GX(d); XC(d) = XCX(d);
           }
         lp_cur = lpx;
         ++nacc;
@@ -458,14 +495,12 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
         const int s = since / p.stride;
         if (s < p.S) {
           const size_t o = ((size_t)s * p.C + chain) * D;
-          for (int j = h; j < nb; j += 2)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int d = 4 * j + q;
-              if (d < D) {
-                if (p.samples) p.samples[o + d] = XC(d);
-                if (p.samples_orig) p.samples_orig[o + d] = Z(d);
-              }
+          for (int i = 0; i < TC_NLOC; ++i)
+            if (owned(i) && (i > 0 || h == 0)) {
+              const int d = dof(i);
+              if (p.samples) p.samples[o + d] = XC(d);
+              if (p.samples_orig) p.samples_orig[o + d] = Z(d);
             }
           if (p.is_accepted && h == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
         }
