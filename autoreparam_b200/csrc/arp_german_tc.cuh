@@ -18,11 +18,13 @@
 // (b) the f16 MMA rate is twice the tf32 rate.  Error per product ~2^-22, which
 // holds the 1e-5 fp32 tolerance of the log-joint gradient (tests/test_gpu_tc.py).
 //
-// Warp roles (288 threads): warps 0-3 and 4-7 are two "halves" that both map
-// thread -> chain (TMEM lane = tid & 127); half h owns features [16h, 16h+16),
-// observation columns [64h, 64h+64) of every 128-observation chunk and every
-// other Philox block of the elementwise leapfrog updates.  Warp 8 issues every
-// tcgen05.mma / tcgen05.commit from one elected lane.
+// Warp roles (544 threads): 16 worker warps in four "quarters" that all map
+// thread -> chain (TMEM lane = tid & 127): quarter w owns features [8w, 8w+8)
+// (their log-scale and coefficient coordinates: momentum in registers, proposal
+// in a private shared-memory column) and observation columns [32w, 32w+32) of
+// every 128-observation chunk; four warps per SM sub-partition hide the MUFU /
+// TMEM latencies of each other.  Warp 16 issues every tcgen05.mma /
+// tcgen05.commit from one elected lane.
 //
 // Everything else (Philox momenta, two half-kicks per leapfrog step, Metropolis
 // accept, per-chain dual averaging, thinning, centred-sample store) follows
@@ -42,7 +44,10 @@ namespace arp {
 #define TC_NOBS 1024      // padded observation count
 #define TC_CHUNK 128      // observations per GEMM1 tile
 #define TC_NCHUNK (TC_NOBS / TC_CHUNK)
-#define TC_THREADS 288
+#define TC_NQ 4            // worker threads per chain
+#define TC_WORKERS (TC_NQ * TC_CHAINS)   // 512
+#define TC_THREADS (TC_WORKERS + 32)     // + the MMA issuer warp
+#define TC_MMA_WARP (TC_WORKERS / 32)
 // canonical no-swizzle image: block (g = row/8, c = col/8) is 8 rows x 16 B, contiguous 128 B
 #define TC_SF 128u        // bytes between feature chunks (8 features) of one row group
 #define TC_SG 512u        // bytes between row groups (8 rows): TC_NF/8 * 128
@@ -54,7 +59,7 @@ namespace arp {
 #define TC_COL_R2 288     // 2 x 64 columns: packed fp16 tail of R
 #define TC_TMEM_COLS 512
 
-#define TC_NLOC 33        // coordinates a worker thread owns: overall_log_scale (replicated) + 16 log-scales + 16 betas
+#define TC_NLOC 17        // coordinates a worker thread owns: overall_log_scale (replicated) + 8 log-scales + 8 betas
 
 struct TcSmem {
   static constexpr uint32_t X1 = 0;
@@ -62,9 +67,9 @@ struct TcSmem {
   static constexpr uint32_t A1 = X2 + TC_XIMG_BYTES;
   static constexpr uint32_t A2 = A1 + TC_AIMG_BYTES;
   static constexpr uint32_t Y = A2 + TC_AIMG_BYTES;              // float[1024]
-  static constexpr uint32_t XCH = Y + TC_NOBS * 4;               // float[4][2][128]
-  static constexpr uint32_t XS = XCH + 4 * 2 * TC_CHAINS * 4;    // float[TC_NLOC][256]: thread-private proposal x
-  static constexpr uint32_t PAR = XS + TC_NLOC * 256 * 4;        // float[3][2*TC_NF+4]: a, b, eps0 per coordinate
+  static constexpr uint32_t XCH = Y + TC_NOBS * 4;               // float[4][TC_NQ][128]
+  static constexpr uint32_t XS = XCH + 4 * TC_NQ * TC_CHAINS * 4; // float[TC_NLOC][512]: thread-private proposal x
+  static constexpr uint32_t PAR = XS + TC_NLOC * TC_WORKERS * 4;        // float[3][2*TC_NF+4]: a, b, eps0 per coordinate
   static constexpr uint32_t BAR = PAR + 3 * (2 * TC_NF + 4) * 4; // 6 mbarriers
   static constexpr uint32_t TMEM_PTR = BAR + 8 * 8;
   static constexpr uint32_t BYTES = TMEM_PTR + 16;
@@ -95,7 +100,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -133,6 +138,10 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                            \
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+               : "r"(taddr) : "memory")
+#define TC_LD8(taddr, v)                                                                                   \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                     \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
                : "r"(taddr) : "memory")
 #define TC_ST16(taddr, v)                                                                                  \
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                             \
@@ -195,15 +204,15 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
       par[2 * (2 * TC_NF + 4) + i] = p.eps0[i];
     }
   }
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
                  "r"((uint32_t)TC_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(bar_a, 256);
+    mbar_init(bar_a, TC_WORKERS);
     mbar_init(bar_h0, 1); mbar_init(bar_h0 + 8, 1);
-    mbar_init(bar_r0, 256); mbar_init(bar_r0 + 8, 256);
+    mbar_init(bar_r0, TC_WORKERS); mbar_init(bar_r0 + 8, TC_WORKERS);
     mbar_init(bar_g, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -214,7 +223,7 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
   const uint32_t tmem = *tmem_ptr_s;
   const int n_lf = p.T * p.L;  // leapfrog steps = gradient evaluations per chain
 
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     // =========================== MMA issuer ===========================
     uint32_t pa = 0, pr[2] = {0, 0};
     const uint32_t sX[2] = {sbase + TcSmem::X1, sbase + TcSmem::X2};
@@ -237,16 +246,16 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
 #pragma unroll
       for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int w = 0; w < TC_NQ; ++w)
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
+          for (int kk = 0; kk < 2; ++kk) {
             // A: 16 observations = 8 packed columns; head in place of H, tail in its own buffer
-            const uint32_t a_t = pa_sel[q] == 0 ? tmem + TC_COL_H + b * TC_CHUNK + 64 * h + 8 * kk
-                                                : tmem + TC_COL_R2 + b * 64 + 32 * h + 8 * kk;
-            const uint32_t og = (uint32_t)c * (TC_CHUNK / 8) + 8 * h + 2 * kk;  // first 8-observation group
+            const uint32_t a_t = pa_sel[q] == 0 ? tmem + TC_COL_H + b * TC_CHUNK + 32 * w + 8 * kk
+                                                : tmem + TC_COL_R2 + b * 64 + 16 * w + 8 * kk;
+            const uint32_t og = (uint32_t)c * (TC_CHUNK / 8) + 4 * w + 2 * kk;  // first 8-observation group
             // MN-major B: N = features (chunks of 8 at TC_SF), K = observations (groups of 8 at TC_SG)
             const uint64_t bd = tc_desc(sX[pb_sel[q]] + og * TC_SG, TC_SG, TC_SF);
-            mma_ts(tmem + TC_COL_G, a_t, bd, TC_IDESC_G2, (c | q | h | kk) ? 1u : 0u);
+            mma_ts(tmem + TC_COL_G, a_t, bd, TC_IDESC_G2, (c | q | w | kk) ? 1u : 0u);
           }
     };
     for (int s = 0; s < n_lf; ++s) {
@@ -269,21 +278,22 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
       __syncwarp();
     }
   } else {
-    // ====================== chain workers (2 per chain) ======================
-    // Worker (chain r, half h) owns features f = 16h + k (k < 16, f < F): local coordinate 1 + k is the
-    // log-scale d = 1 + f, local 17 + k is the coefficient d = 1 + F + f; local 0 (overall_log_scale, d = 0)
-    // is replicated in both halves.  Momentum lives in registers, the proposal x in a private smem column.
-    const int h = tid >> 7;                 // half
+    // ====================== chain workers (4 per chain) ======================
+    // Worker (chain r, quarter w) owns features f = 8w + k (k < 8, f < F): local coordinate 1 + k is the
+    // log-scale d = 1 + f, local 9 + k is the coefficient d = 1 + F + f; local 0 (overall_log_scale, d = 0)
+    // is replicated in all quarters.  It also owns observation columns [32w, 32w + 32) of every chunk.
+    // Momentum lives in registers, the proposal x in a private shared-memory column.
+    const int w = tid >> 7;                 // quarter
     const int r = tid & 127;                // chain within the CTA = TMEM lane
     const int chain = blockIdx.x * TC_CHAINS + r;
     const bool valid = chain < p.C;
     const int D = p.D, F = tp.F;
-    const int nf = max(0, min(16, F - 16 * h));   // features owned
+    const int nf = max(0, min(8, F - 8 * w));   // features owned
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const size_t co = (size_t)chain * ws.sc;
     Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
     Vec GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
-    float* xs = reinterpret_cast<float*>(smem + TcSmem::XS) + tid;           // xs[i * 256]
+    float* xs = reinterpret_cast<float*>(smem + TcSmem::XS) + tid;           // xs[i * TC_WORKERS]
     const float* pa_s = reinterpret_cast<const float*>(smem + TcSmem::PAR);  // a[d]
     const float* pb_s = pa_s + (2 * TC_NF + 4);                              // b[d]
     const float* pe_s = pb_s + (2 * TC_NF + 4);                              // eps0[d]
@@ -292,63 +302,72 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
     const unsigned int gchain = p.chain_offset + (unsigned int)chain;
     uint32_t ph[2] = {0, 0}, pg = 0;
     const float a0 = pa_s[0], b0 = pb_s[0];
-    uint8_t* a_row1 = smem + TcSmem::A1 + (r >> 3) * TC_SG + (r & 7) * 16;
-    uint8_t* a_row2 = smem + TcSmem::A2 + (r >> 3) * TC_SG + (r & 7) * 16;
+    uint8_t* a_row1 = smem + TcSmem::A1 + (r >> 3) * TC_SG + (r & 7) * 16 + w * TC_SF;
+    uint8_t* a_row2 = smem + TcSmem::A2 + (r >> 3) * TC_SG + (r & 7) * 16 + w * TC_SF;
     const float NLOG2E = -1.4426950408889634f;
-    // global coordinate of local coordinate i
-    auto dof = [&](int i) { return i == 0 ? 0 : (i <= 16 ? 16 * h + i : F + 16 * h + i - 16); };
-    auto owned = [&](int i) { return i == 0 || (i <= 16 ? (i - 1) < nf : (i - 17) < nf); };
+    // global coordinate of local coordinate i, and whether this worker really owns it
+    auto dof = [&](int i) { return i == 0 ? 0 : (i <= 8 ? 8 * w + i : F + 8 * w + i - 8); };
+    auto owned = [&](int i) { return i == 0 || (i <= 8 ? (i - 1) < nf : (i - 9) < nf); };
+    auto xch_at = [&](int slot, int q) -> float& { return xch[(slot * TC_NQ + q) * TC_CHAINS + r]; };
 
     for (int t = 0; t < p.T; ++t) {
       const int tg = p.t_begin + t;
-      // ---- momenta for my coordinates; first half kick + drift from the current state
-      float v[TC_NLOC];
-      float ke0 = 0.f, ke1 = 0.f;   // coordinate 0 is counted by half 0 only
-      {
-        float n4[4];
-        int jcur = -1;
+      // ---- momenta: stage the normals of my coordinates in my xs column, then kick + drift
+      if (p.ext_momenta) {
+        const float* mom = p.ext_momenta + ((size_t)tg * p.C + (valid ? chain : 0)) * D;
 #pragma unroll
-        for (int i = 0; i < TC_NLOC; ++i) {
-          v[i] = 0.f;
-          if (owned(i)) {
-            const int d = dof(i);
-            if (p.ext_momenta) {
-              v[i] = p.ext_momenta[((size_t)tg * p.C + (valid ? chain : 0)) * D + d];
-            } else {
-              if ((d >> 2) != jcur) {
-                jcur = d >> 2;
-                philox_normal4(p.seed, gchain, (unsigned int)tg, (unsigned int)jcur, ARP_STREAM_MOMENTUM, n4);
-              }
-              v[i] = (d & 3) == 0 ? n4[0] : ((d & 3) == 1 ? n4[1] : ((d & 3) == 2 ? n4[2] : n4[3]));
+        for (int i = 0; i < TC_NLOC; ++i)
+          if (owned(i)) xs[i * TC_WORKERS] = mom[dof(i)];
+      } else {
+        // Philox block j holds coordinates 4j .. 4j+3; my ranges are d = 0, [1+8w, 1+8w+nf), [1+F+8w, ..+nf)
+        for (int seg = 0; seg < 3; ++seg) {
+          const int d_lo = seg == 0 ? 0 : (seg == 1 ? 1 + 8 * w : 1 + F + 8 * w);
+          const int d_hi = seg == 0 ? 1 : d_lo + nf;
+          const int i_lo = seg == 0 ? 0 : (seg == 1 ? 1 : 9);
+          for (int j = d_lo >> 2; 4 * j < d_hi; ++j) {
+            float n4[4];
+            philox_normal4(p.seed, gchain, (unsigned int)tg, (unsigned int)j, ARP_STREAM_MOMENTUM, n4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int d = 4 * j + q;
+              if (d >= d_lo && d < d_hi) xs[(i_lo + d - d_lo) * TC_WORKERS] = n4[q];
             }
-            if (i > 0 || h == 0) ke0 = fmaf(v[i], v[i], ke0);
-            const float e = pe_s[d] * mult;
-            v[i] = v[i] + 0.5f * e * G(d);
-            xs[i * 256] = Z(d) + e * v[i];
           }
+        }
+      }
+      float v[TC_NLOC];
+      float ke0 = 0.f, ke1 = 0.f;   // coordinate 0 is counted by quarter 0 only
+#pragma unroll
+      for (int i = 0; i < TC_NLOC; ++i) {
+        v[i] = 0.f;
+        if (owned(i)) {
+          const int d = dof(i);
+          v[i] = xs[i * TC_WORKERS];
+          if (i > 0 || w == 0) ke0 = fmaf(v[i], v[i], ke0);
+          const float e = pe_s[d] * mult;
+          v[i] = v[i] + 0.5f * e * G(d);
+          xs[i * TC_WORKERS] = Z(d) + e * v[i];
         }
       }
       float lpx = 0.f;
       for (int l = 0; l < p.L; ++l) {
         const bool last = (l == p.L - 1);
-        // ---- site forward: centred log-scales and coefficients of my features -> A operand (head, tail)
+        // ---- site forward: centred log-scales and coefficients of my 8 features -> A operand (head, tail)
         float lp_top = 0.f;
         const Site s0 = site_fwd(xs[0], 0.f, ARP_LOG_10, a0, b0, lp_top);
-        if (last && h == 0) XCX(0) = s0.x;
-#pragma unroll
-        for (int fc = 0; fc < 2; ++fc) {
+        if (last && w == 0) XCX(0) = s0.x;
+        {
           float be[8];
 #pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const int k = 8 * fc + k8;
-            be[k8] = 0.f;
+          for (int k = 0; k < 8; ++k) {
+            be[k] = 0.f;
             if (k < nf) {
-              const int f = 16 * h + k;
+              const int f = 8 * w + k;
               float dummy = 0.f;
-              const Site ss = site_fwd_unit(xs[(1 + k) * 256], s0.x, pa_s[1 + f], dummy);
-              const Site sb = site_fwd(xs[(17 + k) * 256], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
+              const Site ss = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy);
+              const Site sb = site_fwd(xs[(9 + k) * TC_WORKERS], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
               if (last) { XCX(1 + f) = ss.x; XCX(1 + F + f) = sb.x; }
-              be[k8] = sb.x;
+              be[k] = sb.x;
             }
           }
           uint4 hi, lo;
@@ -356,49 +375,45 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
           split_pack(be[2], be[3], hi.y, lo.y);
           split_pack(be[4], be[5], hi.z, lo.z);
           split_pack(be[6], be[7], hi.w, lo.w);
-          *reinterpret_cast<uint4*>(a_row1 + (2 * h + fc) * TC_SF) = hi;
-          *reinterpret_cast<uint4*>(a_row2 + (2 * h + fc) * TC_SF) = lo;
+          *reinterpret_cast<uint4*>(a_row1) = hi;
+          *reinterpret_cast<uint4*>(a_row2) = lo;
         }
         fence_async_smem();
         tc_fence_before();  // orders last step's tcgen05.ld of G before the issuer's next MMAs
         mbar_arrive(bar_a);
-        // ---- likelihood epilogue: H -> R = y - sigmoid(H), 8 chunks of 128 observations
+        // ---- likelihood epilogue: H -> R = y - sigmoid(H), 8 chunks of 128 observations, 32 columns each
         float lik = 0.f;
         for (int c = 0; c < TC_NCHUNK; ++c) {
           const int b = c & 1;
           mbar_wait(bar_h0 + 8 * b, ph[b]); ph[b] ^= 1;
           tc_fence_after();
-          uint32_t hv[2][32];
-          TC_LD32(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 64 * h, hv[0]);
-          TC_LD32(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 64 * h + 32, hv[1]);
+          uint32_t hv[32];
+          TC_LD32(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 32 * w, hv);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int n0 = c * TC_CHUNK + 32 * w;
+          uint32_t r1[16], r2[16];
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int n0 = c * TC_CHUNK + 64 * h + 32 * sub;
-            uint32_t r1[16], r2[16];
+          for (int i = 0; i < 32; i += 4) {
+            const float4 y4 = *reinterpret_cast<const float4*>(sy + n0 + i);
+            const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+            float rr[4];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 y4 = *reinterpret_cast<const float4*>(sy + n0 + i);
-              const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
-              float rr[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float eta = __uint_as_float(hv[sub][i + q]);
-                const float sg = rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
-                rr[q] = yy[q] - sg;
-                if (last) {
-                  // y eta - softplus(eta), softplus(eta) = max(eta,0) - log(sigmoid(|eta|))
-                  const float m = fmaxf(sg, 1.0f - sg);
-                  const float term = fmaf(lg2_approx(m), 0.69314718055994531f, yy[q] * eta - fmaxf(eta, 0.f));
-                  lik += (n0 + i + q < tp.N) ? term : 0.f;
-                }
+            for (int q = 0; q < 4; ++q) {
+              const float eta = __uint_as_float(hv[i + q]);
+              const float sg = rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
+              rr[q] = yy[q] - sg;
+              if (last) {
+                // y eta - softplus(eta), softplus(eta) = max(eta,0) - log(sigmoid(|eta|))
+                const float m = fmaxf(sg, 1.0f - sg);
+                const float term = fmaf(lg2_approx(m), 0.69314718055994531f, yy[q] * eta - fmaxf(eta, 0.f));
+                lik += (n0 + i + q < tp.N) ? term : 0.f;
               }
-              split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
-              split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
             }
-            TC_ST16(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 64 * h + 16 * sub, r1);
-            TC_ST16(tmem + lane_off + TC_COL_R2 + b * 64 + 32 * h + 16 * sub, r2);
+            split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
+            split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
           }
+          TC_ST16(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 32 * w, r1);
+          TC_ST16(tmem + lane_off + TC_COL_R2 + b * 64 + 16 * w, r2);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           mbar_arrive(bar_r0 + 8 * b);
@@ -406,16 +421,16 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
         // ---- gradient wrt beta from TMEM; reverse through my sites, kicks and drift fused in
         mbar_wait(bar_g, pg); pg ^= 1;
         tc_fence_after();
-        uint32_t gv[16];
-        TC_LD16(tmem + lane_off + TC_COL_G + 16 * h, gv);
+        uint32_t gv[8];
+        TC_LD8(tmem + lane_off + TC_COL_G + 8 * w, gv);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float acc0 = 0.f, lps = 0.f;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < 8; ++k) {
           if (k < nf) {
-            const int f = 16 * h + k;
+            const int f = 8 * w + k;
             const float af = pa_s[1 + f], ab_ = pa_s[1 + F + f], bb_ = pb_s[1 + F + f];
-            const float xs_s = xs[(1 + k) * 256], xs_b = xs[(17 + k) * 256];
+            const float xs_s = xs[(1 + k) * TC_WORKERS], xs_b = xs[(9 + k) * TC_WORKERS];
             const Site ss = site_fwd_unit(xs_s, s0.x, af, lps);
             const Site sb = site_fwd(xs_b, 0.f, ss.x, ab_, bb_, lps);
             float gb, mb, lb, ab;
@@ -426,32 +441,32 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
             // second half kick of this step, then (unless last) first half kick + drift of the next
             const float es = pe_s[1 + f] * mult, eb = pe_s[1 + F + f] * mult;
             v[1 + k] = v[1 + k] + 0.5f * es * gs;
-            v[17 + k] = v[17 + k] + 0.5f * eb * gb;
+            v[9 + k] = v[9 + k] + 0.5f * eb * gb;
             if (last) {
               ke1 = fmaf(v[1 + k], v[1 + k], ke1);
-              ke1 = fmaf(v[17 + k], v[17 + k], ke1);
+              ke1 = fmaf(v[9 + k], v[9 + k], ke1);
               GX(1 + f) = gs;
               GX(1 + F + f) = gb;
             } else {
               v[1 + k] = v[1 + k] + 0.5f * es * gs;
-              v[17 + k] = v[17 + k] + 0.5f * eb * gb;
-              xs[(1 + k) * 256] = xs_s + es * v[1 + k];
-              xs[(17 + k) * 256] = xs_b + eb * v[17 + k];
+              v[9 + k] = v[9 + k] + 0.5f * eb * gb;
+              xs[(1 + k) * TC_WORKERS] = xs_s + es * v[1 + k];
+              xs[(9 + k) * TC_WORKERS] = xs_b + eb * v[9 + k];
             }
           }
         }
-        xch[(0 * 2 + h) * TC_CHAINS + r] = acc0;
-        xch[(1 * 2 + h) * TC_CHAINS + r] = lik + lps;
+        xch_at(0, w) = acc0;
+        xch_at(1, w) = lik + lps;
         epi_bar();
-        const float acc0_t = xch[(0 * 2 + 0) * TC_CHAINS + r] + xch[(0 * 2 + 1) * TC_CHAINS + r];
-        lpx = xch[(1 * 2 + 0) * TC_CHAINS + r] + xch[(1 * 2 + 1) * TC_CHAINS + r] + lp_top;
+        const float acc0_t = (xch_at(0, 0) + xch_at(0, 1)) + (xch_at(0, 2) + xch_at(0, 3));
+        lpx = (xch_at(1, 0) + xch_at(1, 1)) + (xch_at(1, 2) + xch_at(1, 3)) + lp_top;
         {
           float g0, mb, lb, ab;
           site_rev(s0, acc0_t, 0.f, a0, b0, g0, mb, lb, ab);
           const float e = pe_s[0] * mult;
           v[0] = v[0] + 0.5f * e * g0;
           if (last) {
-            if (h == 0) { ke1 = fmaf(v[0], v[0], ke1); GX(0) = g0; }
+            if (w == 0) { ke1 = fmaf(v[0], v[0], ke1); GX(0) = g0; }
           } else {
             v[0] = v[0] + 0.5f * e * g0;
             xs[0] = xs[0] + e * v[0];
@@ -459,12 +474,12 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
         }
         epi_bar();  // xch is rewritten by the next step
       }
-      // ---- Metropolis-Hastings (both halves compute the same decision)
-      xch[(2 * 2 + h) * TC_CHAINS + r] = ke0;
-      xch[(3 * 2 + h) * TC_CHAINS + r] = ke1;
+      // ---- Metropolis-Hastings (all quarters compute the same decision)
+      xch_at(2, w) = ke0;
+      xch_at(3, w) = ke1;
       epi_bar();
-      ke0 = xch[(2 * 2 + 0) * TC_CHAINS + r] + xch[(2 * 2 + 1) * TC_CHAINS + r];
-      ke1 = xch[(3 * 2 + 0) * TC_CHAINS + r] + xch[(3 * 2 + 1) * TC_CHAINS + r];
+      ke0 = (xch_at(2, 0) + xch_at(2, 1)) + (xch_at(2, 2) + xch_at(2, 3));
+      ke1 = (xch_at(3, 0) + xch_at(3, 1)) + (xch_at(3, 2) + xch_at(3, 3));
       float log_alpha = lpx - lp_cur + 0.5f * ke0 - 0.5f * ke1;
       if (!(log_alpha == log_alpha) || log_alpha == -INFINITY) log_alpha = -INFINITY;
       float log_u;
@@ -474,9 +489,9 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
       if (acc) {
 #pragma unroll
         for (int i = 0; i < TC_NLOC; ++i)
-          if (owned(i) && (i > 0 || h == 0)) {
+          if (owned(i) && (i > 0 || w == 0)) {
             const int d = dof(i);
-            Z(d) = xs[i * 256]; G(d) = GX(d); XC(d) = XCX(d);
+            Z(d) = xs[i * TC_WORKERS]; G(d) = GX(d); XC(d) = XCX(d);
           }
         lp_cur = lpx;
         ++nacc;
@@ -497,23 +512,23 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
           const size_t o = ((size_t)s * p.C + chain) * D;
 #pragma unroll
           for (int i = 0; i < TC_NLOC; ++i)
-            if (owned(i) && (i > 0 || h == 0)) {
+            if (owned(i) && (i > 0 || w == 0)) {
               const int d = dof(i);
               if (p.samples) p.samples[o + d] = XC(d);
               if (p.samples_orig) p.samples_orig[o + d] = Z(d);
             }
-          if (p.is_accepted && h == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
+          if (p.is_accepted && w == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
         }
       }
       epi_bar();
     }
-    if (h == 0) {
+    if (w == 0) {
       ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS) : "memory");
   }
 }
