@@ -465,8 +465,9 @@ __device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
   const real sa = s_sa.x, sm = s_sm.x, be = s_be.x;
   const real sig_a = r_softplus(sa), sig_m = r_softplus(sm);
   const real lsa = r_log(sig_a), lsm = r_log(sig_m);
-  const real inv_obs = (real)(1.0 / 0.12);
-  const real log_obs = (real)-2.1202635362000910;  // log(0.12)
+  const real obs_sd = (real)0.12f;  // the reference's scale=0.12 is a float32 graph constant
+  const real inv_obs = (real)1 / obs_sd;
+  const real log_obs = r_log(obs_sd);
   // forward scan
   real al_prev = 0, mu_prev = 0;
   for (int t = 0; t < T; ++t) {

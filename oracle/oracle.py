@@ -250,7 +250,8 @@ def _m_time_series(tr, d):
         alpha.append(tr.site("alpha%d" % t, alpha[t - 1] + mu[t - 1], sp(sa)))
         mu.append(tr.site("mu%d" % t, mu[t - 1], sp(sm)))
     beta = tr.site("beta", 0.0, 1.0)
-    tr.add(normal_lp(y, torch.stack(alpha) + beta * x, torch.as_tensor(0.12, dtype=dt)).sum())
+    # scale=0.12 enters the TF graph as a float32 constant
+    tr.add(normal_lp(y, torch.stack(alpha) + beta * x, torch.as_tensor(float(np.float32(0.12)), dtype=dt)).sum())
 
 
 def site_table(model, d):

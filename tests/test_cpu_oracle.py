@@ -1,0 +1,148 @@
+"""CPU: the oracle is pinned against (i) golden vectors produced by running the
+reference's own models.py / program_transformations.py (tests/golden/
+make_reference_golden.py), (ii) the survey's scipy known-answer table, (iii) the
+structural properties of the reference's models_test.py, (iv) Philox known answers."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import common
+
+GOLD = os.path.join(common.GOLDEN, "reference_logjoint.npz")
+RULES = ["CP", "NCP", "VIP_a", "VIP_ab", "dVIP"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with np.load(GOLD) as f:
+        return {k: f[k] for k in f.files}
+
+
+@pytest.mark.parametrize("rule", RULES)
+@pytest.mark.parametrize("model", common.MODELS)
+def test_oracle_matches_reference_model_code(gold, model, rule):
+    key = "%s/%s" % (model, rule)
+    if key + "/lp" not in gold:
+        assert model == "german_credit_gammascale" and rule != "CP"
+        assert any(n.startswith(key) and "IndexError" in n for n in gold["notes"])
+        pytest.skip("the reference itself raises IndexError for gammascale under %s (ncp/recenter index "
+                    "rv_args[1] of a TransformedDistribution built with a keyword bijector)" % rule)
+    raw = common.raw_data(model, "PA")
+    Z, a, b = gold[key + "/z"], gold[key + "/a"], gold[key + "/b"]
+    lp = np.array([float(O.log_joint(model, raw, z, a, b)) for z in Z])
+    np.testing.assert_allclose(lp, gold[key + "/lp"], rtol=1e-11, atol=1e-9)
+    cen = O.to_centered(model, raw, Z, a, b)
+    np.testing.assert_allclose(cen, gold[key + "/centered"], rtol=1e-11, atol=1e-11)
+    if rule == "NCP":
+        back = O.to_noncentered(model, raw, cen)
+        np.testing.assert_allclose(back, gold[key + "/noncentered"], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(back, Z, rtol=1e-8, atol=1e-8)
+
+
+def test_tied_pparams_quirk_is_b_equal_one(gold):
+    """with --tied_pparams the graphs that are optimised / sampled use b = 1."""
+    raw = common.raw_data("8schools")
+    z = gold["8schools/cVIP_tied_as_written/z"][0]
+    lp_ref = gold["8schools/cVIP_tied_as_written/lp"][0]
+    assert not any(k.endswith("_b") for k in gold["8schools/cVIP_tied_as_written/keys"])
+    assert abs(float(O.log_joint("8schools", raw, z, 0.5, 1.0)) - lp_ref) < 1e-10
+    assert abs(float(O.log_joint("8schools", raw, z, 0.5, 0.5)) - lp_ref) > 1e-3   # the paper-intent rule differs
+
+
+KAT = [((1, 1), -48.1979957021, (0.7, -0.3, -1.0, 1.0)),
+       ((0, 0), -41.4014799581, (3.5, -1.5, 3.276870, 3.723130)),
+       ((0.3, 1), -44.7287094594, (0.7, -0.3, -0.51, 1.49)),
+       ((0.3, 0.3), -44.6815219408, (2.159619, -0.925551, 1.297526, 2.343827))]
+
+
+@pytest.mark.parametrize("ab,lp_ref,cen_ref", KAT)
+def test_survey_known_answers(ab, lp_ref, cen_ref):
+    raw = common.raw_data("8schools")
+    z = np.concatenate([[0.7, -0.3], np.linspace(-1, 1, 8)])
+    tr = O.trace("8schools", raw, z, ab[0], ab[1])
+    assert abs(float(tr.lp) - lp_ref) < 5e-10
+    c = tr.centered
+    got = (float(c["mu"]), float(c["log_tau"]), float(c["theta"][0]), float(c["theta"][7]))
+    np.testing.assert_allclose(got, cen_ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("model", common.MODELS)
+def test_models_test_properties(model):
+    """reference models_test.py:38-60: identity at a=b=1, determinism, round trip."""
+    raw = common.raw_data(model, "MN")
+    D = O.num_coords(model, raw)
+    X = common.random_states(model, D, 2, seed=4)
+    np.testing.assert_allclose(O.to_centered(model, raw, X, 1.0, 1.0), X, rtol=0, atol=1e-13)
+    z1, z2 = O.to_noncentered(model, raw, X), O.to_noncentered(model, raw, X)
+    np.testing.assert_array_equal(z1, z2)
+    np.testing.assert_allclose(O.to_centered(model, raw, z1, 0.0, 0.0), X, rtol=1e-9, atol=1e-9)
+    a, b = common.ab_for("VIP_ab", D)
+    zp = O.to_noncentered(model, raw, X, a, b)
+    np.testing.assert_allclose(O.to_centered(model, raw, zp, a, b), X, rtol=1e-9, atol=1e-9)
+
+
+def test_gradients_match_finite_differences():
+    for model in ("8schools", "electric", "time_series"):
+        raw = common.raw_data(model)
+        D = O.num_coords(model, raw)
+        a, b = common.ab_for("VIP_ab", D)
+        z = common.random_states(model, D, 1, seed=2)[0]
+        _, g = O.log_joint_and_grad(model, raw, z[None], a, b)
+        for d in np.random.default_rng(0).choice(D, 5, replace=False):
+            h = 1e-6 * max(1.0, abs(z[d]))
+            zp, zm = z.copy(), z.copy()
+            zp[d] += h; zm[d] -= h
+            fd = (float(O.log_joint(model, raw, zp, a, b)) - float(O.log_joint(model, raw, zm, a, b))) / (2 * h)
+            assert abs(fd - g[0, d]) < 1e-5 * max(1.0, abs(fd)), (model, d)
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        got = O.philox4x32(np.array(ctr, dtype=np.uint32)[None], key)[0]
+        assert tuple(int(x) for x in got) == out
+    n = O.philox_normals(123, np.arange(2000), 7, O.STREAM_MOMENTUM, 12)
+    assert abs(n.mean()) < 0.03 and abs(n.std() - 1) < 0.03
+    assert np.array_equal(n[5:9], O.philox_normals(123, np.arange(5, 9), 7, O.STREAM_MOMENTUM, 12))
+
+
+def test_ess_oracle_on_ar1():
+    """AR(1) with coefficient phi has ESS/S -> (1-phi)/(1+phi)."""
+    rng = np.random.default_rng(0)
+    S, phi = 20000, 0.6
+    x = np.zeros((S, 8)); e = rng.standard_normal((S, 8))
+    for t in range(1, S):
+        x[t] = phi * x[t - 1] + e[t]
+    ess = O.effective_sample_size(x)
+    assert np.abs(ess / S / ((1 - phi) / (1 + phi)) - 1).max() < 0.15
+    mean, sem = O.get_min_ess([ess[:, None]], 8)
+    assert abs(mean - ess.mean()) < 1e-9 and sem >= 0
+
+
+def test_sample_chain_transition_count():
+    assert O.num_transitions(50000, 10000) == 1 + 10000 + 2 * 49999   # SURVEY 0.4 / BASELINE.md
+
+
+def test_oracle_hmc_samples_8schools_posterior():
+    """End-to-end sanity of the TFP-order sampler restatement: CP and NCP chains agree on the
+    posterior of mu within Monte-Carlo error (they target the same centred posterior)."""
+    raw = common.raw_data("8schools")
+    D = 10
+    out = {}
+    for method, eps in (("CP", 0.25), ("NCP", 0.35)):
+        a, b = common.ab_for(method, D)
+        rng = np.random.default_rng(3)
+        z0 = rng.standard_normal((12, D)) * 0.5
+        r = O.hmc_chain("8schools", raw, z0, np.full(D, eps), 5, 150, 150, 120, a, b, seed=11,
+                        dtype=__import__("torch").float64)
+        assert 0.4 < r["is_accepted"].mean() < 0.99
+        out[method] = r["samples_centered"][:, :, 0]
+    # CP mixes poorly in the funnel (the point of the paper), so it only gets a loose bound here
+    assert abs(out["CP"].mean() - out["NCP"].mean()) < 3.5
+    assert 3.0 < out["NCP"].mean() < 6.0   # posterior mean of mu for eight schools is about 4.4
