@@ -54,7 +54,8 @@ _libs = {}
 
 
 def lib_path(precision="f32"):
-    return os.path.join(_HERE, "libarp_%s.so" % precision)
+    # ARP_LIB_F32 / ARP_LIB_F64 override the path (kernel A/B experiments); default is the in-tree build
+    return os.environ.get("ARP_LIB_%s" % precision.upper(), os.path.join(_HERE, "libarp_%s.so" % precision))
 
 
 def load(precision="f32"):

@@ -39,6 +39,12 @@
 
 namespace arp {
 
+#ifndef TC_FAST_SITE
+#define TC_FAST_SITE 1    // MUFU-based exp / log / sincos in the site math and the Box-Muller transform
+#endif
+#ifndef TC_NEWTON_MIX
+#define TC_NEWTON_MIX 0   // 1: odd likelihood elements take their reciprocal on the FMA pipe (measured 3.6 % slower: issue-bound)
+#endif
 #define TC_CHAINS 128
 #define TC_NF 32          // padded feature count (K of GEMM1, N of GEMM2)
 #define TC_NOBS 1024      // padded observation count
@@ -174,6 +180,48 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// exp via one MUFU.EX2 (relative error ~2^-21 for |x| < 16); used for the site scales
+__device__ __forceinline__ float exp_fast(float x) { return ex2_approx(x * 1.4426950408889634f); }
+// reciprocal of d in [1, 2^60] on the FMA pipe: bit-trick seed + 3 Newton steps (error ~5e-8);
+// takes MUFU pressure off the epilogue, where the XU pipe is the binding resource
+__device__ __forceinline__ float rcp_newton(float d) {
+  float r = __int_as_float(0x7EF311C3 - __float_as_int(d));
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  return r;
+}
+// site rule with fast exponentials (same algebra as arp_common.cuh: site_fwd)
+__device__ __forceinline__ Site site_fwd_fast(float z, float mu, float ls, float a, float b, float& lp) {
+#if !TC_FAST_SITE
+  return site_fwd(z, mu, ls, a, b, lp);
+#endif
+  Site s;
+  float sb_inv;
+  if (b == 1.f) { sb_inv = exp_fast(-ls); s.r = 1.f; }
+  else if (b == 0.f) { sb_inv = 1.f; s.r = exp_fast(ls); }
+  else { sb_inv = exp_fast(-b * ls); s.r = exp_fast((1.f - b) * ls); }
+  s.dz = z - a * mu;
+  const float u = s.dz * sb_inv;
+  s.usb = u * sb_inv;
+  s.x = mu + s.r * s.dz;
+  lp += -0.5f * u * u - b * ls - ARP_HALF_LOG_2PI;
+  return s;
+}
+// 4 standard normals from one Philox block, MUFU log / sincos (the XU pipe idles outside the epilogue)
+__device__ __forceinline__ void philox_normal4_fast(uint64_t seed, uint32_t chain, uint32_t step, uint32_t j, float out[4]) {
+#if !TC_FAST_SITE
+  philox_normal4(seed, chain, step, j, ARP_STREAM_MOMENTUM, out);
+  return;
+#endif
+  const uint4 r = philox4x32_10(make_uint4(chain, step, j, ARP_STREAM_MOMENTUM), (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float rad0 = sqrtf(-2.0f * __logf(u01(r.x))), rad1 = sqrtf(-2.0f * __logf(u01(r.z)));
+  float s0, c0, s1, c1;   // sin/cos(2 pi u) = -sin/cos(2 pi (u - 1/2)), argument in (-pi, pi)
+  __sincosf(6.283185307179586f * (u01(r.y) - 0.5f), &s0, &c0);
+  __sincosf(6.283185307179586f * (u01(r.w) - 0.5f), &s1, &c1);
+  out[0] = -rad0 * c0; out[1] = -rad0 * s0; out[2] = -rad1 * c1; out[3] = -rad1 * s1;
+}
+
 struct TcParams {
   const uint8_t* ximg;  // X1 image followed by X2 image
   const float* ypad;    // [TC_NOBS]
@@ -258,25 +306,25 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
             mma_ts(tmem + TC_COL_G, a_t, bd, TC_IDESC_G2, (c | q | w | kk) ? 1u : 0u);
           }
     };
-    for (int s = 0; s < n_lf; ++s) {
-      mbar_wait(bar_a, pa); pa ^= 1;
-      tc_fence_after();
-      if (lane == 0) {
+    // ONE lane runs the whole issue loop (waits included).  If the other 31 lanes ran ahead into the next
+    // mbarrier.try_wait they could suspend the warp while lane 0 still has MMAs to issue.
+    if (lane == 0) {
+      for (int s = 0; s < n_lf; ++s) {
+        mbar_wait(bar_a, pa); pa ^= 1;
+        tc_fence_after();
         issue_g1(0); tc_commit(bar_h0);
         issue_g1(1); tc_commit(bar_h0 + 8);
-      }
-      for (int c = 0; c < TC_NCHUNK; ++c) {
-        const int b = c & 1;
-        mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
-        tc_fence_after();
-        if (lane == 0) {
+        for (int c = 0; c < TC_NCHUNK; ++c) {
+          const int b = c & 1;
+          mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
+          tc_fence_after();
           issue_g2(c);
           if (c + 2 < TC_NCHUNK) { issue_g1(c + 2); tc_commit(bar_h0 + 8 * b); }
           if (c == TC_NCHUNK - 1) tc_commit(bar_g);
         }
       }
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ====================== chain workers (4 per chain) ======================
     // Worker (chain r, quarter w) owns features f = 8w + k (k < 8, f < F): local coordinate 1 + k is the
@@ -292,7 +340,6 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const size_t co = (size_t)chain * ws.sc;
     Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
-    Vec GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
     float* xs = reinterpret_cast<float*>(smem + TcSmem::XS) + tid;           // xs[i * TC_WORKERS]
     const float* pa_s = reinterpret_cast<const float*>(smem + TcSmem::PAR);  // a[d]
     const float* pb_s = pa_s + (2 * TC_NF + 4);                              // b[d]
@@ -326,7 +373,7 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
           const int i_lo = seg == 0 ? 0 : (seg == 1 ? 1 : 9);
           for (int j = d_lo >> 2; 4 * j < d_hi; ++j) {
             float n4[4];
-            philox_normal4(p.seed, gchain, (unsigned int)tg, (unsigned int)j, ARP_STREAM_MOMENTUM, n4);
+            philox_normal4_fast(p.seed, gchain, (unsigned int)tg, (unsigned int)j, n4);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int d = 4 * j + q;
@@ -350,12 +397,14 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
         }
       }
       float lpx = 0.f;
+      float glast[TC_NLOC], xclast[TC_NLOC];
+#pragma unroll
+      for (int i = 0; i < TC_NLOC; ++i) { glast[i] = 0.f; xclast[i] = 0.f; }
       for (int l = 0; l < p.L; ++l) {
         const bool last = (l == p.L - 1);
         // ---- site forward: centred log-scales and coefficients of my 8 features -> A operand (head, tail)
         float lp_top = 0.f;
-        const Site s0 = site_fwd(xs[0], 0.f, ARP_LOG_10, a0, b0, lp_top);
-        if (last && w == 0) XCX(0) = s0.x;
+        const Site s0 = site_fwd_fast(xs[0], 0.f, ARP_LOG_10, a0, b0, lp_top);
         {
           float be[8];
 #pragma unroll
@@ -365,8 +414,7 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
               const int f = 8 * w + k;
               float dummy = 0.f;
               const Site ss = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy);
-              const Site sb = site_fwd(xs[(9 + k) * TC_WORKERS], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
-              if (last) { XCX(1 + f) = ss.x; XCX(1 + F + f) = sb.x; }
+              const Site sb = site_fwd_fast(xs[(9 + k) * TC_WORKERS], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
               be[k] = sb.x;
             }
           }
@@ -400,7 +448,13 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float eta = __uint_as_float(hv[i + q]);
+              // odd elements: reciprocal on the FMA pipe (Newton) instead of MUFU.RCP
+#if TC_NEWTON_MIX
+              const float sg = (q & 1) ? rcp_newton(1.0f + ex2_approx(fminf(eta * NLOG2E, 60.f)))
+                                       : rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
+#else
               const float sg = rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
+#endif
               rr[q] = yy[q] - sg;
               if (last) {
                 // y eta - softplus(eta), softplus(eta) = max(eta,0) - log(sigmoid(|eta|))
@@ -432,7 +486,7 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
             const float af = pa_s[1 + f], ab_ = pa_s[1 + F + f], bb_ = pb_s[1 + F + f];
             const float xs_s = xs[(1 + k) * TC_WORKERS], xs_b = xs[(9 + k) * TC_WORKERS];
             const Site ss = site_fwd_unit(xs_s, s0.x, af, lps);
-            const Site sb = site_fwd(xs_b, 0.f, ss.x, ab_, bb_, lps);
+            const Site sb = site_fwd_fast(xs_b, 0.f, ss.x, ab_, bb_, lps);
             float gb, mb, lb, ab;
             site_rev(sb, __uint_as_float(gv[k]), 0.f, ab_, bb_, gb, mb, lb, ab);
             float gs, mb2, lb2, ab2;
@@ -445,8 +499,8 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
             if (last) {
               ke1 = fmaf(v[1 + k], v[1 + k], ke1);
               ke1 = fmaf(v[9 + k], v[9 + k], ke1);
-              GX(1 + f) = gs;
-              GX(1 + F + f) = gb;
+              glast[1 + k] = gs; glast[9 + k] = gb;       // proposal gradient and centred values stay in
+              xclast[1 + k] = ss.x; xclast[9 + k] = sb.x;  // registers until the accept decision
             } else {
               v[1 + k] = v[1 + k] + 0.5f * es * gs;
               v[9 + k] = v[9 + k] + 0.5f * eb * gb;
@@ -466,7 +520,8 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
           const float e = pe_s[0] * mult;
           v[0] = v[0] + 0.5f * e * g0;
           if (last) {
-            if (w == 0) { ke1 = fmaf(v[0], v[0], ke1); GX(0) = g0; }
+            if (w == 0) ke1 = fmaf(v[0], v[0], ke1);
+            glast[0] = g0; xclast[0] = s0.x;
           } else {
             v[0] = v[0] + 0.5f * e * g0;
             xs[0] = xs[0] + e * v[0];
@@ -491,7 +546,7 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
         for (int i = 0; i < TC_NLOC; ++i)
           if (owned(i) && (i > 0 || w == 0)) {
             const int d = dof(i);
-            Z(d) = xs[i * TC_WORKERS]; G(d) = GX(d); XC(d) = XCX(d);
+            Z(d) = xs[i * TC_WORKERS]; G(d) = glast[i]; XC(d) = xclast[i];
           }
         lp_cur = lpx;
         ++nacc;
