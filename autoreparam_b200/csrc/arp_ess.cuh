@@ -11,8 +11,11 @@
 // those by direct summation, ARP_ESS_W lags per pass, and stops at the first
 // negative one: O(S*K) instead of O(S log S) + a [2S] complex buffer per series.
 //
-// One thread per series; consecutive threads own consecutive (c, d) so every
-// load samples[t][i] is coalesced.  The mean is accumulated in double; the lag
+// One thread per series.  The input is first transposed [S][C][D] -> [S][D][C]
+// (k_ess_transpose) so that the 32 lanes of a warp own the SAME coordinate of 32
+// consecutive chains: their autocorrelation lengths are similar, so the
+// data-dependent number of passes barely diverges inside a warp, and every load
+// xT[t][d][c] is coalesced.  The mean is accumulated in double; the lag
 // products in `real` with one partial sum per 32-sample block folded into a
 // double total (fp32 build: error ~1e-6 of the lag-0 term, far below the
 // Monte-Carlo error of an ESS estimate; fp64 build: exact to round-off).
@@ -23,52 +26,88 @@ namespace arp {
 
 #define ARP_ESS_BLOCK 128
 #define ARP_ESS_W 32
+#define ARP_ESS_FOLD 8   // blocks of ARP_ESS_W samples accumulated in `real` before folding into double
 
+// [S][n] -> [n][S] (series-major), 32 x 32 tiles through shared memory.  With the series
+// contiguous, a thread walks 4*S bytes of one page instead of striding 4*n bytes (3.3 MB in the
+// bench) per sample, which thrashed the TLB (ncu: 12 % issue-active, long_scoreboard 12.6).
+__global__ void k_ess_transpose(const real* __restrict__ x, int S, long long n, real* __restrict__ xt) {
+  __shared__ real tile[32][33];
+  const long long i0 = (long long)blockIdx.x * 32;
+  for (int t0 = blockIdx.y * 32; t0 < S; t0 += gridDim.y * 32) {
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int t = t0 + r;
+      const long long i = i0 + threadIdx.x;
+      if (t < S && i < n) tile[r][threadIdx.x] = x[(size_t)t * n + i];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const long long i = i0 + r;
+      const int t = t0 + threadIdx.x;
+      if (t < S && i < n) xt[(size_t)i * S + t] = tile[threadIdx.x][r];
+    }
+    __syncthreads();
+  }
+}
+
+// x is [n][S] with n = C*D series in [c][d] order.  Thread j owns series (d = j / C, c = j % C) so the
+// lanes of a warp own the same coordinate of 32 consecutive chains (similar autocorrelation lengths).
 __global__ void __launch_bounds__(ARP_ESS_BLOCK)
-k_ess(const real* __restrict__ x, int S, long long n, real* __restrict__ ess, real* __restrict__ mean_out,
-      real* __restrict__ var_out) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const real* xs = x + i;
+k_ess(const real* __restrict__ x, int S, int C, int D, real* __restrict__ ess_cd, real* __restrict__ mean_cd,
+      real* __restrict__ var_cd) {
+  const long long ntot = (long long)C * D;
+  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j >= ntot) return;
+  const long long i = (j % C) * D + j / C;   // series / output index [c][d]
+  real* ess = ess_cd + i;
+  real* mean_out = mean_cd ? mean_cd + i : nullptr;
+  real* var_out = var_cd ? var_cd + i : nullptr;
+  const size_t n = 1;                         // stride between consecutive samples of a series
+  const real* xs = x + (size_t)i * S;
   double mean = 0;
   for (int t = 0; t < S; ++t) mean += (double)xs[(size_t)t * n];
   mean /= S;
-  if (mean_out) mean_out[i] = (real)mean;
+  if (mean_out) *mean_out = (real)mean;
+  // centring in `real` with a two-term mean (hi + lo) keeps the conversions off the XU pipe
+  const real mean_hi = (real)mean, mean_lo = (real)(mean - (double)mean_hi);
 
   double sum = 0;       // sum_k (S-k)/S rho_k over the kept lags
   double acov0 = 0;
   bool done = false;
   for (int k0 = 0; k0 < S && !done; k0 += ARP_ESS_W) {
     double acc[ARP_ESS_W];
-    real ring[ARP_ESS_W];
+    real ring[ARP_ESS_W], part[ARP_ESS_W];
 #pragma unroll
-    for (int w = 0; w < ARP_ESS_W; ++w) { acc[w] = 0; ring[w] = 0; }
-    real part[ARP_ESS_W];
+    for (int w = 0; w < ARP_ESS_W; ++w) { acc[w] = 0; ring[w] = 0; part[w] = 0; }
     const int ns = S - k0;  // pairs (s + k0, s - w), s = 0 .. ns-1
+    int fold = 0;
     for (int s0 = 0; s0 < ns; s0 += ARP_ESS_W) {
-#pragma unroll
-      for (int w = 0; w < ARP_ESS_W; ++w) part[w] = 0;
 #pragma unroll
       for (int u = 0; u < ARP_ESS_W; ++u) {
         const int s = s0 + u;
         real past = 0, pres = 0;
         if (s < ns) {
-          past = (real)((double)xs[(size_t)s * n] - mean);
-          pres = (k0 == 0) ? past : (real)((double)xs[(size_t)(s + k0) * n] - mean);
+          past = (xs[(size_t)s * n] - mean_hi) - mean_lo;
+          pres = (k0 == 0) ? past : (xs[(size_t)(s + k0) * n] - mean_hi) - mean_lo;
         }
         ring[u] = past;
 #pragma unroll
         for (int w = 0; w < ARP_ESS_W; ++w)
           part[w] = fma(pres, ring[(u - w + ARP_ESS_W) % ARP_ESS_W], part[w]);
       }
+      if (++fold == ARP_ESS_FOLD) {   // fold the `real` partial sums into the double totals
+        fold = 0;
 #pragma unroll
-      for (int w = 0; w < ARP_ESS_W; ++w) acc[w] += (double)part[w];
+        for (int w = 0; w < ARP_ESS_W; ++w) { acc[w] += (double)part[w]; part[w] = 0; }
+      }
     }
+#pragma unroll
+    for (int w = 0; w < ARP_ESS_W; ++w) acc[w] += (double)part[w];
     if (k0 == 0) {
       acov0 = acc[0] / S;
-      if (var_out) var_out[i] = (real)acov0;
+      if (var_out) *var_out = (real)acov0;
       if (!(acov0 > 0.0)) {  // constant (or non-finite) series: TFP yields NaN
-        ess[i] = (real)NAN;
+        *ess = (real)NAN;
         return;
       }
     }
@@ -78,11 +117,11 @@ k_ess(const real* __restrict__ x, int S, long long n, real* __restrict__ ess, re
       if (!done && k < S) {
         const double rho = (acc[w] / (double)(S - k)) / acov0;
         if (rho < 0.0) done = true;           // filter_threshold = 0: this lag and all later ones are zeroed
-        else sum += (double)(S - k) / S * rho;  // NaN (constant series) propagates, as in TFP
+        else sum += (double)(S - k) / S * rho;
       }
     }
   }
-  ess[i] = (real)((double)S / (-1.0 + 2.0 * sum));
+  *ess = (real)((double)S / (-1.0 + 2.0 * sum));
 }
 
 }  // namespace arp

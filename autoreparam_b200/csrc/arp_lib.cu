@@ -410,8 +410,16 @@ extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D,
     in = din.as<real>(); out = dout.as<real>();
     omean = mean ? out + n : nullptr; ovar = var ? out + 2 * n : nullptr;
   }
-  k_ess<<<(unsigned)((n + ARP_ESS_BLOCK - 1) / ARP_ESS_BLOCK), ARP_ESS_BLOCK, 0, st>>>(in, (int)S, (long long)n, out, omean, ovar);
+  DevBuf dxt;
+  ARP_CUDA(dxt.alloc((size_t)S * n * sizeof(real)));
+  {
+    const dim3 tb(32, 8), tg((unsigned)((n + 31) / 32), (unsigned)std::min<long long>((S + 31) / 32, 64));
+    k_ess_transpose<<<tg, tb, 0, st>>>(in, (int)S, (long long)n, dxt.as<real>());
+    ARP_LAUNCH_CHECK();
+  }
+  k_ess<<<(unsigned)((n + ARP_ESS_BLOCK - 1) / ARP_ESS_BLOCK), ARP_ESS_BLOCK, 0, st>>>(dxt.as<real>(), (int)S, (int)C, (int)D, out, omean, ovar);
   ARP_LAUNCH_CHECK();
+  ARP_CUDA(cudaStreamSynchronize(st));  // the transposed copy is freed on return
   if (mem == ARP_MEM_HOST) {
     ARP_CUDA(cudaMemcpyAsync(ess, out, n * sizeof(real), cudaMemcpyDeviceToHost, st));
     if (mean) ARP_CUDA(cudaMemcpyAsync(mean, omean, n * sizeof(real), cudaMemcpyDeviceToHost, st));

@@ -24,6 +24,18 @@ class HmcResult(collections.namedtuple(
     (None unless chains were requested); rhat [D] per coordinate."""
 
 
+_PINNED = {}
+
+
+def _pinned_like(t):
+    """Reusable pinned host staging buffer for a device tensor (allocated once per shape / dtype)."""
+    import torch
+    key = (tuple(t.shape), t.dtype)
+    if key not in _PINNED:
+        _PINNED[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    return _PINNED[key]
+
+
 def _flat_step_sizes(model_config, step_size_init):
     """initial_step_size is a list per site in trace order (main.py:283-284)."""
     if isinstance(step_size_init, np.ndarray) and step_size_init.shape == (model_config.num_coords,):
@@ -56,23 +68,29 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
     tdt = torch.float32 if precision == "f32" else torch.float64
     dev = torch.device(device)
     # host -> device from pinned memory
-    z_pin = torch.from_numpy(np.ascontiguousarray(z0, dtype=np.float32 if precision == "f32" else np.float64)).pin_memory()
+    z_np = np.ascontiguousarray(z0, dtype=np.float32 if precision == "f32" else np.float64)
+    z_pin = _pinned_like(torch.from_numpy(z_np))
+    z_pin.copy_(torch.from_numpy(z_np))
     z_dev = z_pin.to(dev, non_blocking=True)
     out = engine.hmc_run(mc, z_dev, eps0, target.a, target.b, num_leapfrog_steps=num_leapfrog_steps,
                          num_results=num_samples, num_burnin_steps=num_burnin_steps,
                          num_adaptation_steps=num_adaptation_steps, seed=seed, chain_offset=chain_offset,
                          want_final=False, engine=engine_kind, precision=precision)
     ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
-    # device -> host: only what the caller consumes
-    ess_flat = ess_dev.cpu().numpy()
-    is_acc = out["is_accepted"].cpu().numpy().astype(bool)
-    mean_h, var_h = mean_dev.cpu().numpy(), var_dev.cpu().numpy()
+    # device -> host through pinned buffers, one synchronisation: only what the caller consumes
+    host = [_pinned_like(t) for t in (ess_dev, out["is_accepted"], mean_dev, var_dev, out["step_mult"],
+                                      out["accept_count"])]
+    for h, t in zip(host, (ess_dev, out["is_accepted"], mean_dev, var_dev, out["step_mult"], out["accept_count"])):
+        h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    ess_flat, is_acc_u8, mean_h, var_h, step_mult, accept_count = [h.numpy().copy() for h in host]
+    is_acc = is_acc_u8.view(np.bool_)
     samples = None
     if num_chains_to_save > 0:
         samples = mc.split(out["samples"][:, :num_chains_to_save].cpu().numpy())
     res = HmcResult(ess=mc.split(ess_flat), is_accepted=is_acc, samples=samples,
                     rhat=util.rhat_from_moments(mean_h, var_h, num_samples) if C > 1 else None,
-                    step_mult=out["step_mult"].cpu().numpy(), accept_count=out["accept_count"].cpu().numpy(),
+                    step_mult=step_mult, accept_count=accept_count,
                     num_transitions=out["num_transitions"], ess_flat=ess_flat)
     if keep_on_device:
         return res, out
