@@ -27,10 +27,10 @@ class HmcResult(collections.namedtuple(
 _PINNED = {}
 
 
-def _pinned_like(t):
-    """Reusable pinned host staging buffer for a device tensor (allocated once per shape / dtype)."""
+def _pinned_like(t, tag=0):
+    """Reusable pinned host staging buffer for a device tensor (allocated once per tag / shape / dtype)."""
     import torch
-    key = (tuple(t.shape), t.dtype)
+    key = (tag, tuple(t.shape), t.dtype)
     if key not in _PINNED:
         _PINNED[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     return _PINNED[key]
@@ -69,7 +69,7 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
     dev = torch.device(device)
     # host -> device from pinned memory
     z_np = np.ascontiguousarray(z0, dtype=np.float32 if precision == "f32" else np.float64)
-    z_pin = _pinned_like(torch.from_numpy(z_np))
+    z_pin = _pinned_like(torch.from_numpy(z_np), "z0")
     z_pin.copy_(torch.from_numpy(z_np))
     z_dev = z_pin.to(dev, non_blocking=True)
     out = engine.hmc_run(mc, z_dev, eps0, target.a, target.b, num_leapfrog_steps=num_leapfrog_steps,
@@ -78,8 +78,8 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
                          want_final=False, engine=engine_kind, precision=precision)
     ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
     # device -> host through pinned buffers, one synchronisation: only what the caller consumes
-    host = [_pinned_like(t) for t in (ess_dev, out["is_accepted"], mean_dev, var_dev, out["step_mult"],
-                                      out["accept_count"])]
+    host = [_pinned_like(t, tag) for tag, t in enumerate((ess_dev, out["is_accepted"], mean_dev, var_dev,
+                                                          out["step_mult"], out["accept_count"]))]
     for h, t in zip(host, (ess_dev, out["is_accepted"], mean_dev, var_dev, out["step_mult"], out["accept_count"])):
         h.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
