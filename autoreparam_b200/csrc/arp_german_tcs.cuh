@@ -1,0 +1,517 @@
+// tcgen05 engine, STREAMING variant: same algorithm as arp_german_tc.cuh, but the design matrix is
+// not resident in shared memory.  X (fp16 head + tail, plus y) is cut into 128-observation chunk
+// images that a producer warp ring-buffers from L2 into shared memory with bulk asynchronous copies
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP); each chunk image feeds GEMM1 (K-major B) and,
+// one epilogue later, GEMM2 (MN-major B) before its stage is released by tcgen05.commit.  This lifts
+// the limits of the resident kernel: up to 64 features with full tails (the reference's real German
+// credit data is 1000 x 62) and any number of observations.  L2 -> SM traffic is one chunk image per
+// 128 observations per gradient evaluation of 128 chains (~1 % of L2 bandwidth at the measured rate).
+//
+// Roles (576 threads): warps 0-15 workers (4 per chain, as in the resident kernel), warp 16 MMA issuer
+// (one lane), warp 17 producer (one lane).  For NF = 64 a worker owns 16 features, so the momentum moves
+// from registers to the [d][chain] global workspace (coalesced, L2 resident).
+#pragma once
+#include "arp_german_tc.cuh"
+
+namespace arp {
+
+#define TCS_NSTAGE 3
+#define TCS_THREADS (TC_WORKERS + 64)
+#define TCS_MMA_WARP (TC_WORKERS / 32)
+#define TCS_PROD_WARP (TC_WORKERS / 32 + 1)
+
+template <int NF>
+struct Tcs {
+  static constexpr uint32_t NFC = NF / 8;                 // feature chunks of 8
+  static constexpr uint32_t SF = 128;                     // bytes between feature chunks
+  static constexpr uint32_t SG = NFC * 128;               // bytes between 8-row groups
+  static constexpr uint32_t XCHUNK = (TC_CHUNK / 8) * SG; // one part of one 128-observation chunk
+  static constexpr uint32_t STAGE = 2 * XCHUNK + TC_CHUNK * 4;   // head | tail | y
+  static constexpr uint32_t AIMG = (TC_CHAINS / 8) * SG;
+  static constexpr int FPW = NF / TC_NQ;                  // features per worker
+  static constexpr int NLOC = 1 + 2 * FPW;
+  // shared memory
+  static constexpr uint32_t RING = 0;
+  static constexpr uint32_t A1 = RING + TCS_NSTAGE * STAGE;
+  static constexpr uint32_t A2 = A1 + AIMG;
+  static constexpr uint32_t XCH = A2 + AIMG;                        // float[4][TC_NQ][128]
+  static constexpr uint32_t XS = XCH + 4 * TC_NQ * TC_CHAINS * 4;   // float[NLOC][512]
+  static constexpr uint32_t PAR = XS + NLOC * TC_WORKERS * 4;       // float[3][2 NF + 4]
+  static constexpr uint32_t BAR = PAR + 3 * (2 * NF + 4) * 4;       // 6 + 2 * NSTAGE mbarriers
+  static constexpr uint32_t TMEM_PTR = BAR + 16 * 8;
+  static constexpr uint32_t BYTES = TMEM_PTR + 16;
+  // TMEM columns
+  static constexpr uint32_t COL_H = 0, COL_G = 256, COL_R2 = 320;
+  static constexpr uint32_t IDESC_G1 = (1u << 4) | ((uint32_t)(TC_CHUNK >> 3) << 17) | ((128u >> 4) << 24);
+  static constexpr uint32_t IDESC_G2 = (1u << 4) | (1u << 16) | ((uint32_t)(NF >> 3) << 17) | ((128u >> 4) << 24);
+  static_assert(BYTES <= 232448, "shared memory budget");
+};
+
+struct TcsParams {
+  const uint8_t* img;  // nchunk stage images
+  int N, F, nchunk;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int NF>
+__global__ void __launch_bounds__(TCS_THREADS, 1)
+k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
+  using K = Tcs<NF>;
+  constexpr int FPW = K::FPW, NLOC = K::NLOC;
+  constexpr bool V_IN_REGS = (NF <= 32);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_a = sbase + K::BAR, bar_h0 = bar_a + 8, bar_r0 = bar_a + 24, bar_g = bar_a + 40;
+  const uint32_t bar_xf = bar_a + 48, bar_xe = bar_xf + 8 * TCS_NSTAGE;
+  float* xch = reinterpret_cast<float*>(smem + K::XCH);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + K::TMEM_PTR);
+  {
+    float* par = reinterpret_cast<float*>(smem + K::PAR);
+    for (int i = tid; i < p.D; i += TCS_THREADS) {
+      par[i] = p.a[i];
+      par[(2 * NF + 4) + i] = p.b[i];
+      par[2 * (2 * NF + 4) + i] = p.eps0[i];
+    }
+  }
+  if (warp == TCS_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
+                 "r"((uint32_t)TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(bar_a, TC_WORKERS);
+    mbar_init(bar_h0, 1); mbar_init(bar_h0 + 8, 1);
+    mbar_init(bar_r0, TC_WORKERS); mbar_init(bar_r0 + 8, TC_WORKERS);
+    mbar_init(bar_g, 1);
+    for (int s = 0; s < TCS_NSTAGE; ++s) { mbar_init(bar_xf + 8 * s, 1); mbar_init(bar_xe + 8 * s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_s;
+  const int n_lf = p.T * p.L;
+  const int NCH = tp.nchunk;
+
+  if (warp == TCS_PROD_WARP) {
+    // =========================== producer: chunk images L2 -> smem ring ===========================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int s = 0; s < n_lf; ++s)
+        for (int c = 0; c < NCH; ++c, ++cnt) {
+          const uint32_t st = cnt % TCS_NSTAGE, use = cnt / TCS_NSTAGE;
+          if (use > 0) mbar_wait(bar_xe + 8 * st, (use - 1) & 1);
+          mbar_expect_tx(bar_xf + 8 * st, K::STAGE);
+          bulk_g2s(sbase + K::RING + st * K::STAGE, tp.img + (size_t)c * K::STAGE, K::STAGE, bar_xf + 8 * st);
+        }
+    }
+    __syncwarp();
+  } else if (warp == TCS_MMA_WARP) {
+    // =========================== MMA issuer (one lane runs the whole loop) ===========================
+    if (lane == 0) {
+      uint32_t pa = 0, pr[2] = {0, 0};
+      const uint32_t sA[2] = {sbase + K::A1, sbase + K::A2};
+      const int pa_sel[3] = {0, 0, 1}, pb_sel[3] = {0, 1, 0};
+      uint32_t cnt = 0;  // global chunk counter of the next GEMM1 to issue
+      auto stage_of = [&](uint32_t k) { return sbase + K::RING + (k % TCS_NSTAGE) * K::STAGE; };
+      auto issue_g1 = [&](int c, uint32_t k) {
+        mbar_wait(bar_xf + 8 * (k % TCS_NSTAGE), (k / TCS_NSTAGE) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem + K::COL_H + (uint32_t)(c & 1) * TC_CHUNK;
+        const uint32_t xs = stage_of(k);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int ks = 0; ks < NF / 16; ++ks) {
+            const uint64_t ad = tc_desc(sA[pa_sel[q]] + ks * 2 * K::SF, K::SF, K::SG);
+            const uint64_t bd = tc_desc(xs + pb_sel[q] * K::XCHUNK + ks * 2 * K::SF, K::SF, K::SG);
+            mma_ss(d, ad, bd, K::IDESC_G1, (q | ks) ? 1u : 0u);
+          }
+      };
+      auto issue_g2 = [&](int c, uint32_t k) {
+        const uint32_t b = (uint32_t)(c & 1);
+        const uint32_t xs = stage_of(k);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int w = 0; w < TC_NQ; ++w)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint32_t a_t = pa_sel[q] == 0 ? tmem + K::COL_H + b * TC_CHUNK + 32 * w + 8 * kk
+                                                  : tmem + K::COL_R2 + b * 64 + 16 * w + 8 * kk;
+              const uint32_t og = 4 * w + 2 * kk;  // 8-observation group inside the chunk
+              const uint64_t bd = tc_desc(xs + pb_sel[q] * K::XCHUNK + og * K::SG, K::SG, K::SF);
+              mma_ts(tmem + K::COL_G, a_t, bd, K::IDESC_G2, (c | q | w | kk) ? 1u : 0u);
+            }
+      };
+      for (int s = 0; s < n_lf; ++s) {
+        const uint32_t k0 = cnt;  // global index of chunk 0 of this step
+        mbar_wait(bar_a, pa); pa ^= 1;
+        tc_fence_after();
+        issue_g1(0, k0); tc_commit(bar_h0);
+        if (NCH > 1) { issue_g1(1, k0 + 1); tc_commit(bar_h0 + 8); }
+        for (int c = 0; c < NCH; ++c) {
+          const int b = c & 1;
+          mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
+          tc_fence_after();
+          issue_g2(c, k0 + c);
+          tc_commit(bar_xe + 8 * ((k0 + c) % TCS_NSTAGE));   // stage free once GEMM2(c) has read it
+          if (c + 2 < NCH) { issue_g1(c + 2, k0 + c + 2); tc_commit(bar_h0 + 8 * b); }
+          if (c == NCH - 1) tc_commit(bar_g);
+        }
+        cnt += NCH;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ====================== chain workers (4 per chain) ======================
+    const int w = tid >> 7, r = tid & 127;
+    const int chain = blockIdx.x * TC_CHAINS + r;
+    const bool valid = chain < p.C;
+    const int D = p.D, F = tp.F;
+    const int nf = max(0, min(FPW, F - FPW * w));
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const size_t co = (size_t)chain * ws.sc;
+    Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd}, VG{ws.v + co, ws.sd};
+    float* xs = reinterpret_cast<float*>(smem + K::XS) + tid;
+    const float* pa_s = reinterpret_cast<const float*>(smem + K::PAR);
+    const float* pb_s = pa_s + (2 * NF + 4);
+    const float* pe_s = pb_s + (2 * NF + 4);
+    float lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
+    int nacc = ws.nacc[chain];
+    const unsigned int gchain = p.chain_offset + (unsigned int)chain;
+    uint32_t ph[2] = {0, 0}, pg = 0, kcnt = 0;
+    const float a0 = pa_s[0], b0 = pb_s[0];
+    uint8_t* a_row1 = smem + K::A1 + (r >> 3) * K::SG + (r & 7) * 16 + w * (FPW / 8) * K::SF;
+    uint8_t* a_row2 = smem + K::A2 + (r >> 3) * K::SG + (r & 7) * 16 + w * (FPW / 8) * K::SF;
+    const float NLOG2E = -1.4426950408889634f;
+    auto dof = [&](int i) { return i == 0 ? 0 : (i <= FPW ? FPW * w + i : F + FPW * w + i - FPW); };
+    auto owned = [&](int i) { return i == 0 || (i <= FPW ? (i - 1) < nf : (i - 1 - FPW) < nf); };
+    auto xch_at = [&](int slot, int q) -> float& { return xch[(slot * TC_NQ + q) * TC_CHAINS + r]; };
+    // momentum: registers (NF = 32) or the global workspace (NF = 64); coordinate 0 is replicated in every
+    // quarter, so its momentum always stays in a private register
+    float vreg[V_IN_REGS ? NLOC : 1];
+    float v0r = 0.f;
+    auto vget = [&](int i) -> float {
+      if (i == 0) return v0r;
+      if constexpr (V_IN_REGS) return vreg[i]; else return VG(dof(i));
+    };
+    auto vset = [&](int i, float x) {
+      if (i == 0) { v0r = x; return; }
+      if constexpr (V_IN_REGS) vreg[i] = x; else VG(dof(i)) = x;
+    };
+
+    for (int t = 0; t < p.T; ++t) {
+      const int tg = p.t_begin + t;
+      if (p.ext_momenta) {
+        const float* mom = p.ext_momenta + ((size_t)tg * p.C + (valid ? chain : 0)) * D;
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i)
+          if (owned(i)) xs[i * TC_WORKERS] = mom[dof(i)];
+      } else {
+        for (int seg = 0; seg < 3; ++seg) {
+          const int d_lo = seg == 0 ? 0 : (seg == 1 ? 1 + FPW * w : 1 + F + FPW * w);
+          const int d_hi = seg == 0 ? 1 : d_lo + nf;
+          const int i_lo = seg == 0 ? 0 : (seg == 1 ? 1 : 1 + FPW);
+          for (int j = d_lo >> 2; 4 * j < d_hi; ++j) {
+            float n4[4];
+            philox_normal4_fast(p.seed, gchain, (unsigned int)tg, (unsigned int)j, n4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int d = 4 * j + q;
+              if (d >= d_lo && d < d_hi) xs[(i_lo + d - d_lo) * TC_WORKERS] = n4[q];
+            }
+          }
+        }
+      }
+      float ke0 = 0.f, ke1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NLOC; ++i) {
+        if (owned(i)) {
+          const int d = dof(i);
+          float vi = xs[i * TC_WORKERS];
+          if (i > 0 || w == 0) ke0 = fmaf(vi, vi, ke0);
+          const float e = pe_s[d] * mult;
+          vi = vi + 0.5f * e * G(d);
+          vset(i, vi);
+          xs[i * TC_WORKERS] = Z(d) + e * vi;
+        }
+      }
+      float lpx = 0.f;
+      for (int l = 0; l < p.L; ++l) {
+        const bool last = (l == p.L - 1);
+        float lp_top = 0.f;
+        const Site s0 = site_fwd_fast(xs[0], 0.f, ARP_LOG_10, a0, b0, lp_top);
+#pragma unroll
+        for (int fc = 0; fc < FPW / 8; ++fc) {
+          float be[8];
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const int k = 8 * fc + k8;
+            be[k8] = 0.f;
+            if (k < nf) {
+              const int f = FPW * w + k;
+              float dummy = 0.f;
+              const Site ss = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy);
+              const Site sb = site_fwd_fast(xs[(1 + FPW + k) * TC_WORKERS], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
+              be[k8] = sb.x;
+            }
+          }
+          uint4 hi, lo;
+          split_pack(be[0], be[1], hi.x, lo.x);
+          split_pack(be[2], be[3], hi.y, lo.y);
+          split_pack(be[4], be[5], hi.z, lo.z);
+          split_pack(be[6], be[7], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(a_row1 + fc * K::SF) = hi;
+          *reinterpret_cast<uint4*>(a_row2 + fc * K::SF) = lo;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_a);
+        float lik = 0.f;
+        for (int c = 0; c < NCH; ++c, ++kcnt) {
+          const int b = c & 1;
+          mbar_wait(bar_h0 + 8 * b, ph[b]); ph[b] ^= 1;
+          tc_fence_after();
+          uint32_t hv[32];
+          TC_LD32(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, hv);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const float* sy = reinterpret_cast<const float*>(smem + K::RING + (kcnt % TCS_NSTAGE) * K::STAGE + 2 * K::XCHUNK);
+          const int n0 = c * TC_CHUNK + 32 * w;
+          uint32_t r1[16], r2[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 y4 = *reinterpret_cast<const float4*>(sy + 32 * w + i);
+            const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
+            float rr[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float eta = __uint_as_float(hv[i + q]);
+              const float sg = rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
+              rr[q] = yy[q] - sg;
+              if (last) {
+                const float m = fmaxf(sg, 1.0f - sg);
+                const float term = fmaf(lg2_approx(m), 0.69314718055994531f, yy[q] * eta - fmaxf(eta, 0.f));
+                lik += (n0 + i + q < tp.N) ? term : 0.f;
+              }
+            }
+            split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
+            split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
+          }
+          TC_ST16(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, r1);
+          TC_ST16(tmem + lane_off + K::COL_R2 + b * 64 + 16 * w, r2);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          mbar_arrive(bar_r0 + 8 * b);
+        }
+        mbar_wait(bar_g, pg); pg ^= 1;
+        tc_fence_after();
+        uint32_t gv[FPW];
+        if constexpr (FPW == 8) { TC_LD8(tmem + lane_off + K::COL_G + 8 * w, gv); }
+        else { TC_LD16(tmem + lane_off + K::COL_G + 16 * w, gv); }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float acc0 = 0.f, lps = 0.f;
+#pragma unroll
+        for (int k = 0; k < FPW; ++k) {
+          if (k < nf) {
+            const int f = FPW * w + k;
+            const float af = pa_s[1 + f], ab_ = pa_s[1 + F + f], bb_ = pb_s[1 + F + f];
+            const float xs_s = xs[(1 + k) * TC_WORKERS], xs_b = xs[(1 + FPW + k) * TC_WORKERS];
+            const Site ss = site_fwd_unit(xs_s, s0.x, af, lps);
+            const Site sb = site_fwd_fast(xs_b, 0.f, ss.x, ab_, bb_, lps);
+            float gb, mb, lb, ab;
+            site_rev(sb, __uint_as_float(gv[k]), 0.f, ab_, bb_, gb, mb, lb, ab);
+            float gs, mb2, lb2, ab2;
+            site_rev(ss, lb, s0.x, af, 1.f, gs, mb2, lb2, ab2);
+            acc0 += mb2;
+            const float es = pe_s[1 + f] * mult, eb = pe_s[1 + F + f] * mult;
+            float vs = vget(1 + k) + 0.5f * es * gs;
+            float vb = vget(1 + FPW + k) + 0.5f * eb * gb;
+            if (last) {
+              ke1 = fmaf(vs, vs, ke1);
+              ke1 = fmaf(vb, vb, ke1);
+              // proposal gradient / centred values: parked in the global proposal slots until the accept decision
+              ws.gx[co + (size_t)(1 + f) * ws.sd] = gs; ws.gx[co + (size_t)(1 + F + f) * ws.sd] = gb;
+              ws.xcx[co + (size_t)(1 + f) * ws.sd] = ss.x; ws.xcx[co + (size_t)(1 + F + f) * ws.sd] = sb.x;
+            } else {
+              vs = vs + 0.5f * es * gs;
+              vb = vb + 0.5f * eb * gb;
+              xs[(1 + k) * TC_WORKERS] = xs_s + es * vs;
+              xs[(1 + FPW + k) * TC_WORKERS] = xs_b + eb * vb;
+            }
+            vset(1 + k, vs);
+            vset(1 + FPW + k, vb);
+          }
+        }
+        xch_at(0, w) = acc0;
+        xch_at(1, w) = lik + lps;
+        epi_bar();
+        const float acc0_t = (xch_at(0, 0) + xch_at(0, 1)) + (xch_at(0, 2) + xch_at(0, 3));
+        lpx = (xch_at(1, 0) + xch_at(1, 1)) + (xch_at(1, 2) + xch_at(1, 3)) + lp_top;
+        {
+          float g0, mb, lb, ab;
+          site_rev(s0, acc0_t, 0.f, a0, b0, g0, mb, lb, ab);
+          const float e = pe_s[0] * mult;
+          float v0 = v0r + 0.5f * e * g0;
+          if (last) {
+            if (w == 0) { ke1 = fmaf(v0, v0, ke1); ws.gx[co] = g0; ws.xcx[co] = s0.x; }
+          } else {
+            v0 = v0 + 0.5f * e * g0;
+            xs[0] = xs[0] + e * v0;
+          }
+          v0r = v0;
+        }
+        epi_bar();
+      }
+      xch_at(2, w) = ke0;
+      xch_at(3, w) = ke1;
+      epi_bar();
+      ke0 = (xch_at(2, 0) + xch_at(2, 1)) + (xch_at(2, 2) + xch_at(2, 3));
+      ke1 = (xch_at(3, 0) + xch_at(3, 1)) + (xch_at(3, 2) + xch_at(3, 3));
+      float log_alpha = lpx - lp_cur + 0.5f * ke0 - 0.5f * ke1;
+      if (!(log_alpha == log_alpha) || log_alpha == -INFINITY) log_alpha = -INFINITY;
+      float log_u;
+      if (p.ext_log_u) log_u = p.ext_log_u[(size_t)tg * p.C + (valid ? chain : 0)];
+      else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
+      const bool acc = log_u < log_alpha;
+      if (acc) {
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i)
+          if (owned(i) && (i > 0 || w == 0)) {
+            const int d = dof(i);
+            Z(d) = xs[i * TC_WORKERS];
+            G(d) = ws.gx[co + (size_t)d * ws.sd];
+            XC(d) = ws.xcx[co + (size_t)d * ws.sd];
+          }
+        lp_cur = lpx;
+        ++nacc;
+      }
+      const int t1 = tg + 1;
+      if (t1 <= p.num_adapt) {
+        const float ft = (float)t1;
+        Hc += p.target_accept - expf(log_alpha < 0.f ? log_alpha : 0.f);
+        const float log_step = ARP_LOG_10 - Hc * sqrtf(ft) / ((ft + 10.f) * 0.05f);
+        const float eta = powf(ft, -0.75f);
+        lavg = eta * log_step + (1.f - eta) * lavg;
+        mult = (t1 < p.num_adapt) ? expf(log_step) : expf(lavg);
+      }
+      const int since = tg - p.num_burnin;
+      if (since >= 0 && (since % p.stride) == 0 && valid) {
+        const int s = since / p.stride;
+        if (s < p.S) {
+          const size_t o = ((size_t)s * p.C + chain) * D;
+#pragma unroll
+          for (int i = 0; i < NLOC; ++i)
+            if (owned(i) && (i > 0 || w == 0)) {
+              const int d = dof(i);
+              if (p.samples) p.samples[o + d] = XC(d);
+              if (p.samples_orig) p.samples_orig[o + d] = Z(d);
+            }
+          if (p.is_accepted && w == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
+        }
+      }
+      epi_bar();
+    }
+    if (w == 0) {
+      ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TCS_MMA_WARP) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------- host ---
+struct GermanTcs {
+  DevBuf img;
+  int N = 0, F = 0, nf_pad = 0, nchunk = 0;
+  bool ok = false;
+
+  // X [N, F] fp32 row-major, y [N] -> per-chunk stage images (head | tail | y), zero padded
+  bool build(const float* X, const float* y, int n, int f, std::string* err) {
+    ok = false;
+    if (f > 64) return true;   // SIMT engine only
+    nf_pad = f <= 32 ? 32 : 64;
+    nchunk = (n + TC_CHUNK - 1) / TC_CHUNK;
+    const uint32_t SG = (uint32_t)(nf_pad / 8) * 128, XCHUNK = (TC_CHUNK / 8) * SG, STAGE = 2 * XCHUNK + TC_CHUNK * 4;
+    std::vector<uint8_t> buf((size_t)nchunk * STAGE, 0);
+    for (int i = 0; i < n; ++i) {
+      const int c = i / TC_CHUNK, rloc = i % TC_CHUNK;
+      uint8_t* st = buf.data() + (size_t)c * STAGE;
+      for (int j = 0; j < f; ++j) {
+        const float x = X[(size_t)i * f + j];
+        if (!(fabsf(x) < 60000.f)) return true;  // outside fp16 range: SIMT engine only
+        const __half h1 = __float2half_rn(x);
+        const __half h2 = __float2half_rn(x - __half2float(h1));
+        const size_t off = (size_t)(rloc / 8) * SG + (size_t)(j / 8) * 128 + (size_t)(rloc % 8) * 16 + (size_t)(j % 8) * 2;
+        memcpy(st + off, &h1, 2);
+        memcpy(st + XCHUNK + off, &h2, 2);
+      }
+      memcpy(st + 2 * XCHUNK + (size_t)rloc * 4, &y[i], 4);
+    }
+    cudaError_t e = upload(img, buf);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return false; }
+    N = n; F = f; ok = true;
+    return true;
+  }
+  bool ready() const { return ok; }
+};
+
+static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt, const HmcArgs& p, const real* z0,
+                                 cudaStream_t st, bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
+                                 std::atomic<long long>* launches, std::string* err) {
+#define TCS_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(_e); return 1; } } while (0)
+  const long long C = p.C;
+  const long long Cpad = (C + TC_CHAINS - 1) / TC_CHAINS * TC_CHAINS;
+  const long long Dpad = (p.D + 7) / 8 * 8;
+  const size_t vec = (size_t)Cpad * Dpad;
+  TCS_CUDA(wsbuf->alloc(7 * vec * sizeof(real)));
+  TCS_CUDA(cudaMemsetAsync(wsbuf->p, 0, 7 * vec * sizeof(real), st));
+  TCS_CUDA(scal->alloc(4 * Cpad * sizeof(real)));
+  TCS_CUDA(nacc->alloc(Cpad * sizeof(int)));
+  HmcWs ws{};
+  real* base = wsbuf->as<real>();
+  ws.z = base; ws.g = base + vec; ws.xc = base + 2 * vec; ws.x = base + 3 * vec;
+  ws.gx = base + 4 * vec; ws.xcx = base + 5 * vec; ws.v = base + 6 * vec;
+  real* sb = scal->as<real>();
+  ws.mult = sb; ws.lp = sb + Cpad; ws.H = sb + 2 * Cpad; ws.lavg = sb + 3 * Cpad;
+  ws.nacc = nacc->as<int>();
+  ws.sd = (int)Cpad; ws.sc = 1;
+  const dim3 grid((unsigned)(Cpad / TC_CHAINS));
+  if (fp_simt == 32) k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 32><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
+  else k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 64><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
+  launches->fetch_add(1);
+  TCS_CUDA(cudaGetLastError());
+  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk};
+  if (tc.nf_pad == 32) {
+    TCS_CUDA(cudaFuncSetAttribute(k_german_tcs_hmc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tcs<32>::BYTES));
+    k_german_tcs_hmc<32><<<grid, TCS_THREADS, Tcs<32>::BYTES, st>>>(tp, ws, p);
+  } else {
+    TCS_CUDA(cudaFuncSetAttribute(k_german_tcs_hmc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tcs<64>::BYTES));
+    k_german_tcs_hmc<64><<<grid, TCS_THREADS, Tcs<64>::BYTES, st>>>(tp, ws, p);
+  }
+  launches->fetch_add(1);
+  TCS_CUDA(cudaGetLastError());
+  if (want_final) {
+    TCS_CUDA(dfz->alloc((size_t)C * p.D * sizeof(real)));
+    const long long n = C * p.D;
+    k_gather_ws_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.z, ws.sd, ws.sc, (int)C, p.D, dfz->as<real>());
+    launches->fetch_add(1);
+    TCS_CUDA(cudaGetLastError());
+  }
+#undef TCS_CUDA
+  return 0;
+}
+
+}  // namespace arp

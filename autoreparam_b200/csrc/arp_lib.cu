@@ -18,6 +18,7 @@
 #include "arp_vi.cuh"
 #ifndef ARP_FP64
 #include "arp_german_tc.cuh"
+#include "arp_german_tcs.cuh"
 #endif
 
 using namespace arp;
@@ -55,7 +56,8 @@ struct arp_model {
   DevBuf X, y, x1, x2, w, u, offs, gidx, pidx;
   int fp = 32;  // german: register-resident padded feature count of the SIMT engine
 #ifndef ARP_FP64
-  GermanTc tc;  // german: operands of the tcgen05 engine
+  GermanTc tc;    // german: operands of the tcgen05 engine (X resident in shared memory: F <= 32, N <= 1024)
+  GermanTcs tcs;  // german: operands of the streaming tcgen05 engine (F <= 64, any N)
 #endif
 };
 
@@ -94,6 +96,7 @@ extern "C" int arp_model_create(const char* model_name, const arp_model_data* d,
     if (dm.kind == MODEL_GERMAN_LOGNORMAL) {
       std::string err;
       if (!m->tc.build(d->X, d->y, dm.N, dm.F, &err)) return bail("tcgen05 operand build: " + err);
+      if (!m->tcs.build(d->X, d->y, dm.N, dm.F, &err)) return bail("tcgen05 streaming operand build: " + err);
     }
 #endif
   } else if (name == "radon" || name == "radon_stddvs") {
@@ -290,9 +293,14 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
   const bool host = mem == ARP_MEM_HOST;
 
 #ifndef ARP_FP64
-  const bool tc_ok = m->dev.kind == MODEL_GERMAN_LOGNORMAL && m->tc.ready();
-  if (cfg->engine == 2 && !tc_ok) return fail("arp_hmc_run: tcgen05 engine is only available for german_credit_lognormalcentered");
-  const bool use_tc = tc_ok && (cfg->engine == 2 || (cfg->engine == 0 && german_tc_auto(C)));
+  const bool tc_res = m->dev.kind == MODEL_GERMAN_LOGNORMAL && m->tc.ready();   // resident-X kernel
+  const bool tc_str = m->dev.kind == MODEL_GERMAN_LOGNORMAL && m->tcs.ready();  // streaming kernel
+  const bool tc_ok = tc_res || tc_str;
+  if ((cfg->engine == 2 || cfg->engine == 3) && !tc_ok)
+    return fail("arp_hmc_run: the tcgen05 engine needs german_credit_lognormalcentered with at most 64 features");
+  if (cfg->engine == 3 && !tc_str) return fail("arp_hmc_run: streaming tcgen05 engine not available for this model");
+  const bool use_tc = tc_ok && (cfg->engine == 2 || cfg->engine == 3 || (cfg->engine == 0 && german_tc_auto(C)));
+  const bool use_stream = use_tc && (cfg->engine == 3 || !tc_res);
 #else
   if (cfg->engine == 2) return fail("arp_hmc_run: the fp64 check build has no tcgen05 engine");
   const bool use_tc = false;
@@ -334,8 +342,11 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
 
 #ifndef ARP_FP64
   if (use_tc) {
-    int rc = german_tc_hmc(m->tc, m->dev, p, z0, st, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc, &g_launches,
-                           &g_last_error);
+    int rc = use_stream
+                 ? german_tcs_hmc(m->tcs, m->dev, m->fp, p, z0, st, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc,
+                                  &g_launches, &g_last_error)
+                 : german_tc_hmc(m->tc, m->dev, p, z0, st, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc, &g_launches,
+                                 &g_last_error);
     if (rc) return rc;
     final_z_dev = dfz.as<real>();
     out_mult_dev = scal.as<real>();

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib
 
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_STREAM = 0, 1, 2, 3
 
 
 def _is_torch(x):

@@ -100,3 +100,69 @@ def test_tc_posterior_agrees_with_simt():
     z = np.abs(m1 - m2) / (np.sqrt(s1 ** 2 + s2 ** 2) / np.sqrt(C))
     assert z.max() < 6.0, z.max()
     assert np.median(np.abs(s1 / s2 - 1)) < 0.05 and np.abs(s1 / s2 - 1).max() < 0.25  # slow-mixing log-scales
+
+
+# --------------------------------------------------------------------------------------------
+# streaming variant (X chunk images ring-buffered from L2): synthetic 1000 x 25 (NF = 32) and the
+# reference's real 1000 x 62 German credit data (NF = 64, momentum in the global workspace)
+# --------------------------------------------------------------------------------------------
+def _case_model(model, method, C, seed):
+    mc = common.model_config(model)
+    raw = common.raw_data(model)
+    D = mc.num_coords
+    a, b = common.ab_for(method, D)
+    z0 = common.random_states(model, D, C, seed=seed, scale=0.3).astype(np.float32).astype(np.float64)
+    return mc, raw, D, a, b, z0
+
+
+@pytest.mark.parametrize("model", ["german_synth", MODEL])
+@pytest.mark.parametrize("method", ["CP", "NCP", "VIP_ab"])
+def test_tcs_single_leapfrog_gradient(model, method):
+    C = 9
+    mc, raw, D, a, b, z0 = _case_model(model, method, C, seed=41)
+    _, g_ref = O.log_joint_and_grad(MODEL, raw, z0, a, b)
+    eps = 2.0 ** -6
+    out = engine.hmc_run(mc, z0, np.full(D, eps), a, b, num_leapfrog_steps=1, num_results=1, num_burnin_steps=0,
+                         num_adaptation_steps=0, ext_momenta=np.zeros((1, C, D)), ext_log_u=np.full((1, C), -1e30),
+                         want_orig=True, engine=engine.ENGINE_TCGEN05_STREAM)
+    assert out["is_accepted"].all()
+    g_tc = (out["samples_orig"][0].astype(np.float64) - z0) / (0.5 * eps * eps)
+    err = np.abs(g_tc - g_ref).max(axis=1)
+    allow = 1e-5 * np.maximum(np.abs(g_ref).max(axis=1), 1.0) + 2.0 ** -23 * np.abs(z0).max() / (0.5 * eps * eps)
+    assert (err < allow).all(), (err, allow)
+
+
+@pytest.mark.parametrize("model", ["german_synth", MODEL])
+def test_tcs_fixed_momenta_trajectory(model):
+    C, L, S, burn, adapt = 6, 3, 3, 2, 4
+    mc, raw, D, a, b, z0 = _case_model(model, "VIP_a", C, seed=42)
+    T = O.num_transitions(S, burn)
+    rng = np.random.default_rng(9)
+    mom = rng.standard_normal((T, C, D)).astype(np.float32).astype(np.float64)
+    lu = np.log(rng.uniform(size=(T, C))).astype(np.float32).astype(np.float64)
+    eps0 = (np.full(D, 0.01) * rng.uniform(0.5, 1.5, D)).astype(np.float32).astype(np.float64)
+    ref = O.hmc_chain(MODEL, raw, z0, eps0, L, S, burn, adapt, a, b, momenta=mom, log_u=lu)
+    out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn,
+                         num_adaptation_steps=adapt, ext_momenta=mom, ext_log_u=lu, want_orig=True,
+                         engine=engine.ENGINE_TCGEN05_STREAM)
+    assert (out["is_accepted"].astype(bool) == ref["is_accepted"]).all()
+    assert ref["is_accepted"].mean() > 0
+    err = common.rel_err(out["samples"].reshape(S * C, D), ref["samples_centered"].reshape(S * C, D)).max()
+    assert err < 2e-3, err
+    assert common.rel_err(out["final_z"], ref["z"]).max() < 2e-3
+
+
+@pytest.mark.parametrize("model", ["german_synth", MODEL])
+def test_tcs_matches_simt_engine_many_chains(model):
+    C, L, S, burn, adapt = 128 * 2 + 37, 4, 2, 2, 3
+    mc, raw, D, a, b, z0 = _case_model(model, "NCP", C, seed=43)
+    eps0 = np.full(D, 0.01)
+    kw = dict(num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn, num_adaptation_steps=adapt, seed=77,
+              chain_offset=11)
+    o1 = engine.hmc_run(mc, z0, eps0, a, b, engine=engine.ENGINE_SIMT, **kw)
+    o2 = engine.hmc_run(mc, z0, eps0, a, b, engine=engine.ENGINE_TCGEN05_STREAM, **kw)
+    same = o1["is_accepted"] == o2["is_accepted"]
+    assert same.mean() > 0.99, same.mean()
+    ok = same.all(axis=0)
+    err = common.rel_err(o2["samples"][:, ok].reshape(-1, D), o1["samples"][:, ok].reshape(-1, D))
+    assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 1e-2, (np.median(err), np.quantile(err, 0.99))
