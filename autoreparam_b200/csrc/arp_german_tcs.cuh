@@ -263,7 +263,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               float dummy = 0.f;
               const Site ss = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy);
               const Site sb = site_fwd_fast(xs[(1 + FPW + k) * TC_WORKERS], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
-              be[k8] = sb.x;
+              be[k8] = sb.x * NLOG2E;   // GEMM1 then yields -log2(e) * eta: one FMUL less per likelihood element
             }
           }
           uint4 hi, lo;
@@ -295,10 +295,12 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             float rr[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float eta = __uint_as_float(hv[i + q]);
-              const float sg = rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
+              const float hq = __uint_as_float(hv[i + q]);      // = -log2(e) * eta
+              const float sg = rcp_approx(1.0f + ex2_approx(hq));
               rr[q] = yy[q] - sg;
               if (last) {
+                // y eta - softplus(eta), softplus(eta) = max(eta,0) - log(sigmoid(|eta|))
+                const float eta = hq * -0.69314718055994531f;
                 const float m = fmaxf(sg, 1.0f - sg);
                 const float term = fmaf(lg2_approx(m), 0.69314718055994531f, yy[q] * eta - fmaxf(eta, 0.f));
                 lik += (n0 + i + q < tp.N) ? term : 0.f;
