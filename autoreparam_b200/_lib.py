@@ -35,6 +35,19 @@ class HmcBuffers(C.Structure):
                 ("final_z", C.c_void_p), ("step_mult", C.c_void_p), ("accept_count", C.c_void_p)]
 
 
+class IlvConfig(C.Structure):
+    _fields_ = [("num_leapfrog_steps_a", C.c_int32), ("num_leapfrog_steps_b", C.c_int32), ("num_results", C.c_int32),
+                ("num_burnin_steps", C.c_int32), ("num_adaptation_steps", C.c_int32),
+                ("num_steps_between_results", C.c_int32), ("seed", C.c_uint64), ("chain_offset", C.c_int64),
+                ("target_accept_prob", C.c_double), ("adaptation_rate", C.c_double), ("lanes_per_chain", C.c_int32)]
+
+
+class IlvBuffers(C.Structure):
+    _fields_ = [("x0", C.c_void_p), ("eps0_a", C.c_void_p), ("eps0_b", C.c_void_p), ("ext_momenta", C.c_void_p),
+                ("ext_log_u", C.c_void_p), ("samples", C.c_void_p), ("is_accepted_a", C.c_void_p),
+                ("is_accepted_b", C.c_void_p), ("step_mult_a", C.c_void_p), ("step_mult_b", C.c_void_p)]
+
+
 class ViConfig(C.Structure):
     _fields_ = [("num_mc_samples", C.c_int32), ("num_optimization_steps", C.c_int32), ("num_runs", C.c_int32),
                 ("learning_rates", C.c_double * ARP_VI_MAX_RUNS), ("seed", C.c_uint64), ("learn_a", C.c_int32)]
@@ -47,7 +60,7 @@ class ViBuffers(C.Structure):
 
 # every symbol include/autoreparam_b200.h declares
 EXPORTS = ["arp_model_create", "arp_model_destroy", "arp_model_num_coords", "arp_log_joint_grad",
-           "arp_hmc_num_transitions", "arp_hmc_run", "arp_ess", "arp_vi_run", "arp_kernel_launch_count",
+           "arp_hmc_num_transitions", "arp_hmc_run", "arp_hmc_interleaved_run", "arp_ess", "arp_vi_run", "arp_kernel_launch_count",
            "arp_last_error", "arp_precision"]
 
 _libs = {}
@@ -81,6 +94,8 @@ def load(precision="f32"):
     lib.arp_hmc_num_transitions.restype = i64
     lib.arp_hmc_run.argtypes = [vp, C.POINTER(HmcConfig), vp, vp, i64, C.POINTER(HmcBuffers), i32, vp]
     lib.arp_hmc_run.restype = i32
+    lib.arp_hmc_interleaved_run.argtypes = [vp, C.POINTER(IlvConfig), vp, vp, vp, vp, i64, C.POINTER(IlvBuffers), i32, vp]
+    lib.arp_hmc_interleaved_run.restype = i32
     lib.arp_ess.argtypes = [vp, i64, i64, i64, vp, vp, vp, i32, vp]
     lib.arp_ess.restype = i32
     lib.arp_vi_run.argtypes = [vp, C.POINTER(ViConfig), vp, vp, C.POINTER(ViBuffers), i32, vp]

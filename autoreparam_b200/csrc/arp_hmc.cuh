@@ -198,4 +198,135 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Interleaved CP / NCP sampler (--method=i): reference interleaved.py:113-155 + inference.py:258-329.
+// The chain state is kept in the centred space.  One transition = for rule r in (A, B): map the centred
+// state to rule r's coordinates (to_rule), re-bootstrap (log-prob, gradient) there -- one extra gradient
+// evaluation, as Interleaved.one_step does with bootstrap_results -- take one HMC step of L_r leapfrog
+// steps, adapt that rule's step size with [TFP 0.7] SimpleStepSizeAdaptation (x (1 + rate) if the
+// acceptance probability exceeds the target, / (1 + rate) otherwise, while step < num_adaptation_steps),
+// and map back to the centred space (free: vg returns the centred values).  2 L + 2 gradient evaluations.
+struct IlvArgs {
+  const real* a2;            // rule B parameters (rule A = p.a, p.b)
+  const real* b2;
+  const real* eps0_2;        // [D] base step sizes of rule B (rule A = p.eps0)
+  int L2;
+  real rate;                 // adaptation_rate (0.05)
+  unsigned char* is_accepted2;   // [S, C] accepts of the rule-B sub-step (rule A -> p.is_accepted)
+  real* mult2;               // [Cpad] rule-B step multiplier
+  int* nacc2;
+};
+
+template <int KIND, int LPC, int FP>
+__global__ void __launch_bounds__(ARP_BLOCK)
+k_hmc_interleaved(DevModel m, HmcWs ws, HmcArgs p, IlvArgs q, const real* x0) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = gtid / LPC;
+  const int sub = gtid % LPC;
+  const bool valid = chain < p.C;
+  const int D = p.D;
+  const size_t co = (size_t)chain * ws.sc;
+  Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
+  Vec X{ws.x + co, ws.sd}, GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
+  Vec V{ws.v + co, ws.sd};
+  // the initial state is given in the centred space (initial_states_cp, inference.py:265)
+  for (int d = sub; d < D; d += LPC) XC(d) = valid ? x0[(size_t)chain * D + d] : (real)0;
+  __syncwarp();
+  real mult[2] = {1, 1};
+  int nacc[2] = {0, 0};
+  const unsigned int gchain = p.chain_offset + (unsigned int)chain;
+
+  for (int t = 0; t < p.T; ++t) {
+    const int tg = p.t_begin + t;
+    bool acc_r[2] = {false, false};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const real* a = r == 0 ? p.a : q.a2;
+      const real* b = r == 0 ? p.b : q.b2;
+      const real* eps0 = r == 0 ? p.eps0 : q.eps0_2;
+      const int L = r == 0 ? p.L : q.L2;
+      const unsigned int sid = 2u * (unsigned int)tg + (unsigned int)r;   // RNG / injected-stream index
+      // ---- centred -> rule coordinates, re-bootstrap
+      to_rule<KIND, LPC>(m, a, b, XC, Z, sub);
+      __syncwarp();
+      real lp_cur = vg<KIND, LPC, false, FP>(m, a, b, Z, G, XC, Vec{nullptr, 1}, sub, true);
+      __syncwarp();
+      // ---- one HMC step (same op order as k_hmc_run)
+      real ke0 = 0;
+      if (p.ext_momenta) {
+        const real* mom = p.ext_momenta + ((size_t)sid * p.C + (valid ? chain : 0)) * D;
+        for (int d = sub; d < D; d += LPC) { const real v = mom[d]; V(d) = v; ke0 = fma(v, v, ke0); }
+      } else {
+        const int nb = (D + 3) >> 2;
+        for (int j = sub; j < nb; j += LPC) {
+          real n4[4];
+          philox_normal4(p.seed, gchain, sid, (unsigned int)j, ARP_STREAM_MOMENTUM, n4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int d = 4 * j + k;
+            if (d < D) { V(d) = n4[k]; ke0 = fma(n4[k], n4[k], ke0); }
+          }
+        }
+        __syncwarp();
+      }
+      ke0 = group_sum<LPC>(ke0);
+      for (int d = sub; d < D; d += LPC) { X(d) = Z(d); GX(d) = G(d); }
+      real lpx = 0, ke1 = 0;
+      for (int l = 0; l < L; ++l) {
+        for (int d = sub; d < D; d += LPC) {
+          const real e = ldg(eps0 + d) * mult[r];
+          const real v = V(d) + (real)0.5 * e * GX(d);
+          V(d) = v;
+          X(d) = X(d) + e * v;
+        }
+        __syncwarp();
+        const bool last = (l == L - 1);
+        lpx = vg<KIND, LPC, false, FP>(m, a, b, X, GX, XCX, Vec{nullptr, 1}, sub, last);
+        __syncwarp();
+        for (int d = sub; d < D; d += LPC) {
+          const real e = ldg(eps0 + d) * mult[r];
+          const real v = V(d) + (real)0.5 * e * GX(d);
+          V(d) = v;
+          if (last) ke1 = fma(v, v, ke1);
+        }
+      }
+      ke1 = group_sum<LPC>(ke1);
+      real log_alpha = lpx - lp_cur + (real)0.5 * ke0 - (real)0.5 * ke1;
+      if (!(log_alpha == log_alpha) || log_alpha == -INFINITY) log_alpha = -INFINITY;
+      real log_u;
+      if (p.ext_log_u) log_u = p.ext_log_u[(size_t)sid * p.C + (valid ? chain : 0)];
+      else log_u = philox_log_uniform(p.seed, gchain, sid);
+      const bool acc = log_u < log_alpha;
+      acc_r[r] = acc;
+      if (acc) {
+        for (int d = sub; d < D; d += LPC) XC(d) = XCX(d);   // only the centred state is carried over
+        ++nacc[r];
+      }
+      if (tg < p.num_adapt) {
+        const real one_plus = (real)1 + q.rate;
+        const real pacc = r_exp(log_alpha < (real)0 ? log_alpha : (real)0);
+        mult[r] = pacc > p.target_accept ? mult[r] * one_plus : mult[r] / one_plus;
+      }
+      __syncwarp();
+    }
+    const int since = tg - p.num_burnin;
+    if (since >= 0 && (since % p.stride) == 0 && valid) {
+      const int s = since / p.stride;
+      if (s < p.S) {
+        const size_t o = ((size_t)s * p.C + chain) * D;
+        if (p.samples) for (int d = sub; d < D; d += LPC) p.samples[o + d] = XC(d);
+        if (sub == 0) {
+          if (p.is_accepted) p.is_accepted[(size_t)s * p.C + chain] = acc_r[0] ? 1 : 0;
+          if (q.is_accepted2) q.is_accepted2[(size_t)s * p.C + chain] = acc_r[1] ? 1 : 0;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (sub == 0) {
+    ws.mult[chain] = mult[0]; q.mult2[chain] = mult[1];
+    ws.nacc[chain] = nacc[0]; q.nacc2[chain] = nacc[1];
+  }
+}
+
 }  // namespace arp

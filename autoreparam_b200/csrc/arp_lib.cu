@@ -406,6 +406,84 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
   return 0;
 }
 
+// ---------------------------------------------------------------- interleaved ---
+extern "C" int arp_hmc_interleaved_run(arp_model* m, const arp_ilv_config* cfg, const arp_real* a_a, const arp_real* b_a,
+                                       const arp_real* a_b, const arp_real* b_b, int64_t C, const arp_ilv_buffers* buf,
+                                       int mem, void* stream) {
+  if (!m || !cfg || !a_a || !b_a || !a_b || !b_b || !buf || C <= 0) return fail("arp_hmc_interleaved_run: bad argument");
+  if (!buf->x0 || !buf->eps0_a || !buf->eps0_b) return fail("arp_hmc_interleaved_run: x0, eps0_a and eps0_b are required");
+  if (cfg->num_leapfrog_steps_a < 1 || cfg->num_leapfrog_steps_b < 1 || cfg->num_results < 1 ||
+      cfg->num_burnin_steps < 0 || cfg->num_steps_between_results < 0)
+    return fail("arp_hmc_interleaved_run: bad configuration");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->dev.D;
+  const long long S = cfg->num_results;
+  const long long T = 1 + (long long)cfg->num_burnin_steps + (1 + (long long)cfg->num_steps_between_results) * (S - 1);
+  const bool host = mem == ARP_MEM_HOST;
+  DevBuf da, db, da2, db2, dx0, de1, de2, dmom, dlu, dsamp, dacc1, dacc2;
+  if (stage_in(da, a_a, D * sizeof(real), ARP_MEM_HOST, st) || stage_in(db, b_a, D * sizeof(real), ARP_MEM_HOST, st) ||
+      stage_in(da2, a_b, D * sizeof(real), ARP_MEM_HOST, st) || stage_in(db2, b_b, D * sizeof(real), ARP_MEM_HOST, st))
+    return 1;
+  const real *x0 = buf->x0, *e1 = buf->eps0_a, *e2 = buf->eps0_b, *mom = buf->ext_momenta, *lu = buf->ext_log_u;
+  real* samples = buf->samples;
+  unsigned char *acc1 = buf->is_accepted_a, *acc2 = buf->is_accepted_b;
+  if (host) {
+    if (stage_in(dx0, x0, (size_t)C * D * sizeof(real), mem, st)) return 1;
+    if (stage_in(de1, e1, D * sizeof(real), mem, st) || stage_in(de2, e2, D * sizeof(real), mem, st)) return 1;
+    x0 = dx0.as<real>(); e1 = de1.as<real>(); e2 = de2.as<real>();
+    if (mom) { if (stage_in(dmom, mom, (size_t)2 * T * C * D * sizeof(real), mem, st)) return 1; mom = dmom.as<real>(); }
+    if (lu) { if (stage_in(dlu, lu, (size_t)2 * T * C * sizeof(real), mem, st)) return 1; lu = dlu.as<real>(); }
+    if (samples) { ARP_CUDA(dsamp.alloc((size_t)S * C * D * sizeof(real))); samples = dsamp.as<real>(); }
+    if (acc1) { ARP_CUDA(dacc1.alloc((size_t)S * C)); acc1 = dacc1.as<unsigned char>(); }
+    if (acc2) { ARP_CUDA(dacc2.alloc((size_t)S * C)); acc2 = dacc2.as<unsigned char>(); }
+  }
+  HmcArgs p{};
+  p.C = (int)C; p.D = D; p.L = cfg->num_leapfrog_steps_a; p.T = (int)T; p.t_begin = 0;
+  p.num_adapt = cfg->num_adaptation_steps; p.num_burnin = cfg->num_burnin_steps;
+  p.stride = 1 + cfg->num_steps_between_results; p.S = (int)S;
+  p.seed = cfg->seed; p.chain_offset = (unsigned int)cfg->chain_offset;
+  p.target_accept = (real)(cfg->target_accept_prob > 0 ? cfg->target_accept_prob : 0.75);
+  p.eps0 = e1; p.a = da.as<real>(); p.b = db.as<real>();
+  p.ext_momenta = mom; p.ext_log_u = lu; p.samples = samples; p.samples_orig = nullptr; p.is_accepted = acc1;
+  const int lpc = pick_lpc(m, C, cfg->lanes_per_chain);
+  const int cpb = ARP_BLOCK / lpc;
+  const long long Cpad = round_up(C, cpb), Dpad = round_up(D, 8);
+  const size_t vec = (size_t)Cpad * Dpad;
+  DevBuf wsbuf, scal, nacc;
+  ARP_CUDA(wsbuf.alloc(7 * vec * sizeof(real)));
+  ARP_CUDA(cudaMemsetAsync(wsbuf.p, 0, 7 * vec * sizeof(real), st));
+  ARP_CUDA(scal.alloc(2 * Cpad * sizeof(real)));
+  ARP_CUDA(nacc.alloc(2 * Cpad * sizeof(int)));
+  HmcWs ws{};
+  real* base = wsbuf.as<real>();
+  ws.z = base; ws.g = base + vec; ws.xc = base + 2 * vec; ws.x = base + 3 * vec;
+  ws.gx = base + 4 * vec; ws.xcx = base + 5 * vec; ws.v = base + 6 * vec;
+  ws.mult = scal.as<real>(); ws.nacc = nacc.as<int>();
+  ws.lp = ws.H = ws.lavg = nullptr;
+  if (lpc == 1) { ws.sd = (int)Cpad; ws.sc = 1; } else { ws.sd = 1; ws.sc = (int)Dpad; }
+  IlvArgs q{};
+  q.a2 = da2.as<real>(); q.b2 = db2.as<real>(); q.eps0_2 = e2; q.L2 = cfg->num_leapfrog_steps_b;
+  q.rate = (real)(cfg->adaptation_rate > 0 ? cfg->adaptation_rate : 0.05);
+  q.is_accepted2 = acc2; q.mult2 = scal.as<real>() + Cpad; q.nacc2 = nacc.as<int>() + Cpad;
+  const dim3 grid((unsigned)(Cpad / cpb)), block(ARP_BLOCK);
+  const DevModel dm = m->dev;
+  const int fp = m->fp;
+#define BODY(KIND, LPC, FP) k_hmc_interleaved<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p, q, x0);
+  ARP_DISPATCH(dm.kind, lpc, fp, BODY)
+#undef BODY
+  ARP_LAUNCH_CHECK();
+  const cudaMemcpyKind kd = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (host) {
+    if (buf->samples) ARP_CUDA(cudaMemcpyAsync(buf->samples, samples, (size_t)S * C * D * sizeof(real), kd, st));
+    if (buf->is_accepted_a) ARP_CUDA(cudaMemcpyAsync(buf->is_accepted_a, acc1, (size_t)S * C, kd, st));
+    if (buf->is_accepted_b) ARP_CUDA(cudaMemcpyAsync(buf->is_accepted_b, acc2, (size_t)S * C, kd, st));
+  }
+  if (buf->step_mult_a) ARP_CUDA(cudaMemcpyAsync(buf->step_mult_a, ws.mult, C * sizeof(real), kd, st));
+  if (buf->step_mult_b) ARP_CUDA(cudaMemcpyAsync(buf->step_mult_b, q.mult2, C * sizeof(real), kd, st));
+  ARP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ------------------------------------------------------------------------ ESS ---
 extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* ess, arp_real* mean,
                        arp_real* var, int mem, void* stream) {

@@ -522,6 +522,76 @@ __device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
   return lp;
 }
 
+// ------------------------------------------------- centred -> rule (a, b) ---
+// Inverse of the site rule: given the CENTRED values x of every coordinate, the state coordinate under
+// rule (a, b) is  z = a mu + (x - mu) sigma^(b-1)  with (mu, sigma) evaluated at the centred values of the
+// parents.  a = b = 0 is the reference's make_to_noncentered (models.py:84-102), general (a, b) its
+// build_make_to_partially_noncentered (models.py:105-128).  Used by the interleaved CP/NCP sampler.
+__device__ __forceinline__ real site_inv(real x, real mu, real ls, real a, real b) {
+  if (a == (real)1 && b == (real)1) return x;   // CP: the state IS the centred value (exactly)
+  return a * mu + (x - mu) * r_exp((b - (real)1) * ls);
+}
+
+template <int KIND, int LPC>
+__device__ void to_rule(const DevModel& m, const real* a, const real* b, Vec x, Vec z, int sub) {
+  if (KIND == MODEL_8SCHOOLS) {
+    const real mu = x(0), lt = x(1);
+    if (sub == 0) { z(0) = site_inv(mu, 0, ARP_LOG_5, a[0], b[0]); z(1) = site_inv(lt, 0, ARP_LOG_5, a[1], b[1]); }
+    for (int i = sub; i < 8; i += LPC) z(2 + i) = site_inv(x(2 + i), mu, lt, a[2 + i], b[2 + i]);
+  } else if (KIND == MODEL_GERMAN_LOGNORMAL || KIND == MODEL_GERMAN_GAMMA) {
+    const int F = m.F;
+    const real s0 = x(0);
+    if (sub == 0) z(0) = site_inv(s0, 0, ARP_LOG_10, a[0], b[0]);
+    for (int f = sub; f < F; f += LPC) {
+      const real sf = x(1 + f);
+      real ls;
+      if (KIND == MODEL_GERMAN_GAMMA) { z(1 + f) = sf; ls = s0 + sf; }
+      else { z(1 + f) = site_inv(sf, s0, 0, a[1 + f], b[1 + f]); ls = sf; }
+      z(1 + F + f) = site_inv(x(1 + F + f), 0, ls, a[1 + F + f], b[1 + F + f]);
+    }
+  } else if (KIND == MODEL_RADON || KIND == MODEL_RADON_STDDVS) {
+    const int J = m.J;
+    const real mua = x(0), b1 = x(1);
+    if (sub == 0) { z(0) = x(0); z(1) = x(1); z(2) = x(2); }   // mu = 0, sigma = 1
+    for (int j = sub; j < J; j += LPC) {
+      z(3 + j) = site_inv(x(3 + j), mua + ldg(m.u + j) * b1, 0, a[3 + j], b[3 + j]);
+      if (KIND == MODEL_RADON_STDDVS) z(3 + J + j) = x(3 + J + j);
+    }
+  } else if (KIND == MODEL_ELECTION) {
+    const int K = m.K;
+    const real mua = x(0), lsa = x(1);
+    if (sub == 0) {
+      z(0) = site_inv(mua, 0, ARP_LOG_100, a[0], b[0]);
+      z(1) = site_inv(lsa, 0, ARP_LOG_10, a[1], b[1]);
+      z(2 + K) = site_inv(x(2 + K), 0, ARP_LOG_100, a[2 + K], b[2 + K]);
+      z(3 + K) = site_inv(x(3 + K), 0, ARP_LOG_100, a[3 + K], b[3 + K]);
+    }
+    for (int k = sub; k < K; k += LPC) z(2 + k) = site_inv(x(2 + k), mua, lsa, a[2 + k], b[2 + k]);
+  } else if (KIND == MODEL_ELECTRIC) {
+    const int K = m.K, oB = 8 + K;
+    if (sub == 0)
+      for (int q = 0; q < 4; ++q) {
+        z(q) = x(q); z(4 + q) = x(4 + q);
+        z(oB + q) = site_inv(x(oB + q), 0, ARP_LOG_100, a[oB + q], b[oB + q]);
+      }
+    for (int p = sub; p < K; p += LPC) {
+      const int gp = ldg(m.pidx + p);
+      const real mu_p = gp >= 0 ? (real)100 * x(gp) : (real)0;
+      z(8 + p) = site_inv(x(8 + p), mu_p, 0, a[8 + p], b[8 + p]);
+    }
+  } else {  // time series
+    const int T = m.K, oBeta = 2 + 2 * T;
+    const real lsa = r_log(r_softplus(x(0))), lsm = r_log(r_softplus(x(1)));
+    if (sub == 0) { z(0) = x(0); z(1) = x(1); z(oBeta) = x(oBeta); }
+    for (int t = sub; t < T; t += LPC) {
+      const int ia = 2 + 2 * t, im = 3 + 2 * t;
+      const real alp = t > 0 ? x(ia - 2) : (real)0, mup = t > 0 ? x(im - 2) : (real)0;
+      z(ia) = site_inv(x(ia), alp + mup, lsa, a[ia], b[ia]);
+      z(im) = site_inv(x(im), mup, lsm, a[im], b[im]);
+    }
+  }
+}
+
 // --------------------------------------------------------------- dispatch ---
 template <int KIND, int LPC, bool WITH_A, int FP>
 __device__ __forceinline__ real vg(const DevModel& m, const real* a, const real* b,

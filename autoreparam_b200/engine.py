@@ -137,6 +137,55 @@ def hmc_run(model, z0, eps0, a, b, *, num_leapfrog_steps, num_results, num_burni
     return out
 
 
+def hmc_interleaved_run(model, x0, eps0_a, eps0_b, rule_a, rule_b, *, num_leapfrog_steps_a, num_leapfrog_steps_b,
+                        num_results, num_burnin_steps, num_adaptation_steps, num_steps_between_results=1, seed=0,
+                        chain_offset=0, target_accept_prob=0.75, adaptation_rate=0.05, ext_momenta=None,
+                        ext_log_u=None, lanes_per_chain=0, precision="f32"):
+    """Interleaved sampler (``arp_hmc_interleaved_run``).  ``x0`` [C, D] centred initial states (numpy or
+    torch.cuda); ``rule_a`` / ``rule_b`` = (a, b) arrays.  Returns dict(samples [S,C,D] centred,
+    is_accepted_a, is_accepted_b [S,C], step_mult_a, step_mult_b [C])."""
+    lib = _lib.load(precision)
+    dt = _lib.np_dtype(precision)
+    D = model.num_coords
+    cfg = _lib.IlvConfig(num_leapfrog_steps_a, num_leapfrog_steps_b, num_results, num_burnin_steps,
+                         num_adaptation_steps, num_steps_between_results, seed, chain_offset, target_accept_prob,
+                         adaptation_rate, lanes_per_chain)
+    T = hmc_num_transitions(num_results, num_burnin_steps, num_steps_between_results)
+    S = num_results
+    aa, ba, ab, bb = [_np(v, dt) for v in (rule_a[0], rule_a[1], rule_b[0], rule_b[1])]
+    if _is_torch(x0):
+        import torch
+        tdt = _torch_dtype(precision)
+        x0 = x0.contiguous()
+        dev = x0.device
+        conv = lambda v: None if v is None else torch.as_tensor(v, dtype=tdt, device=dev).contiguous()
+        mk = lambda shape, dtype: torch.empty(shape, dtype=dtype, device=dev)
+        u8 = torch.uint8
+        mem, st = _lib.ARP_MEM_DEVICE, _stream()
+    else:
+        tdt = dt
+        x0 = _np(x0, dt)
+        conv = lambda v: _np(v, dt)
+        mk = lambda shape, dtype: np.empty(shape, dtype=dtype)
+        u8 = np.uint8
+        mem, st = _lib.ARP_MEM_HOST, None
+    Cn = x0.shape[0]
+    e1, e2, mom, lu = conv(eps0_a), conv(eps0_b), conv(ext_momenta), conv(ext_log_u)
+    if mom is not None:
+        assert tuple(mom.shape) == (2 * T, Cn, D)
+    if lu is not None:
+        assert tuple(lu.shape) == (2 * T, Cn)
+    out = dict(samples=mk((S, Cn, D), tdt), is_accepted_a=mk((S, Cn), u8), is_accepted_b=mk((S, Cn), u8),
+               step_mult_a=mk((Cn,), tdt), step_mult_b=mk((Cn,), tdt))
+    buf = _lib.IlvBuffers(_p(x0), _p(e1), _p(e2), _p(mom), _p(lu), _p(out["samples"]), _p(out["is_accepted_a"]),
+                          _p(out["is_accepted_b"]), _p(out["step_mult_a"]), _p(out["step_mult_b"]))
+    rc = lib.arp_hmc_interleaved_run(model.handle(precision), C.byref(cfg), _p(aa), _p(ba), _p(ab), _p(bb), Cn,
+                                     C.byref(buf), mem, st)
+    _lib.check(lib, rc, "arp_hmc_interleaved_run")
+    out["num_transitions"] = int(T)
+    return out
+
+
 def ess(samples, precision="f32", want_moments=False):
     """samples [S, C, D] -> ESS [C, D] (``arp_ess``; TFP effective_sample_size semantics).
     With ``want_moments`` also returns the per-chain mean and (biased) variance [C, D]."""

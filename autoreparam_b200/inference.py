@@ -144,3 +144,45 @@ def find_best_learning_rate(target, model_config, *, learning_rates, num_optimiz
         learned_reparam = collections.OrderedDict(
             (name + "_a", np.asarray(v, dtype=np.float32)) for (name, _), v in zip(mc.sites, mc.split(a)))
     return (best_elbo, list(out["elbo"][r]), best_lr, step_size_init, params, learned_reparam)
+
+
+class InterleavedResult(collections.namedtuple(
+        "InterleavedResult", "ess is_accepted_cp is_accepted_ncp samples rhat ess_flat num_transitions")):
+    pass
+
+
+def hmc_interleaved(model_config, target_cp, target_ncp, num_leapfrog_steps_cp, num_leapfrog_steps_ncp,
+                    step_size_cp, step_size_ncp, initial_states_cp, *, num_samples, num_burnin_steps,
+                    num_adaptation_steps, num_chains_to_save=0, seed=0, chain_offset=0, device="cuda",
+                    precision="f32"):
+    """Interleaved CP / NCP HMC (``inference.py:258-329`` + ``interleaved.py``): per transition one CP step and
+    one NCP step, each with ``SimpleStepSizeAdaptation(adaptation_rate=0.05, target_accept_prob=0.75)`` and base
+    step sizes ``sigma_q / (L / 4)**2`` of its own VI fit.  States / samples are in the centred space."""
+    import torch
+
+    mc = model_config
+    x0 = initial_states_cp if (isinstance(initial_states_cp, np.ndarray) and initial_states_cp.ndim == 2) \
+        else mc.join(list(initial_states_cp))
+    C, D = x0.shape
+    eps_cp = _flat_step_sizes(mc, step_size_cp) / (float(num_leapfrog_steps_cp) / 4.0) ** 2
+    eps_ncp = _flat_step_sizes(mc, step_size_ncp) / (float(num_leapfrog_steps_ncp) / 4.0) ** 2
+    dev = torch.device(device)
+    x_np = np.ascontiguousarray(x0, dtype=np.float32 if precision == "f32" else np.float64)
+    x_pin = _pinned_like(torch.from_numpy(x_np), "x0i")
+    x_pin.copy_(torch.from_numpy(x_np))
+    out = engine.hmc_interleaved_run(mc, x_pin.to(dev, non_blocking=True), eps_cp, eps_ncp,
+                                     (target_cp.a, target_cp.b), (target_ncp.a, target_ncp.b),
+                                     num_leapfrog_steps_a=num_leapfrog_steps_cp,
+                                     num_leapfrog_steps_b=num_leapfrog_steps_ncp, num_results=num_samples,
+                                     num_burnin_steps=num_burnin_steps, num_adaptation_steps=num_adaptation_steps,
+                                     seed=seed, chain_offset=chain_offset, precision=precision)
+    ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
+    ess_flat = ess_dev.cpu().numpy()
+    samples = None
+    if num_chains_to_save > 0:
+        samples = mc.split(out["samples"][:, :num_chains_to_save].cpu().numpy())
+    return InterleavedResult(
+        ess=mc.split(ess_flat), is_accepted_cp=out["is_accepted_a"].cpu().numpy().astype(bool),
+        is_accepted_ncp=out["is_accepted_b"].cpu().numpy().astype(bool), samples=samples,
+        rhat=util.rhat_from_moments(mean_dev.cpu().numpy(), var_dev.cpu().numpy(), num_samples) if C > 1 else None,
+        ess_flat=ess_flat, num_transitions=out["num_transitions"])

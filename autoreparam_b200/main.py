@@ -109,7 +109,9 @@ def create_target_graph(FLAGS, model_config, results_dir):
         target = graphs.make_dvip_graph(model_config, discrete, FLAGS.learnable_parameterisation_type)
         actual_reparam = discrete
     elif FLAGS.method == "i":
-        raise NotImplementedError("interleaved CP/NCP HMC (--method=i) is the next scope row; see DESIGN.md")
+        if FLAGS.inference == "VI":
+            raise Exception("Cannot run interleaved VI. Use `i` method with HMC only.")   # main.py:136-137
+        return (graphs.make_cp_graph(model_config), graphs.make_ncp_graph(model_config)), None
     else:
         raise Exception("unknown method {}".format(FLAGS.method))
     return target, actual_reparam
@@ -229,6 +231,75 @@ def run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False):
                  normalized_ess_final=normalized_ess_final, num_chains_to_save=FLAGS.num_chains_to_save)
 
 
+def _first_existing(results_dir, names):
+    for n in names:
+        p = os.path.join(results_dir, n)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def run_interleaved_hmc(FLAGS, model_config, results_dir, file_path):
+    """main.py:452-528.  The reference reads literally ``CP.json`` / ``NCP.json`` (the names VI writes with
+    ``--tied_pparams=False``); the default-flag names ``CP_tied.json`` / ``NCP_tied.json`` are accepted too.
+    (The published driver then dies on a NameError, ``main.py:515``; this one saves what it evidently meant.)"""
+    file_path_cp = _first_existing(results_dir, ["CP.json", "CP_tied.json"])
+    file_path_ncp = _first_existing(results_dir, ["NCP.json", "NCP_tied.json"])
+    if file_path_cp is None or file_path_ncp is None:
+        raise Exception("Run VI first to find initial step sizes, and HMCfirst to find num_leapfrog_steps.")
+    param_names = model_config.param_names
+    with open(file_path_cp) as f:
+        prev = json.load(f)
+    initial_step_size_cp = prev["initial_step_size"]
+    num_leapfrog_steps_cp = get_best_num_leapfrog_steps_from_tuning_runs(prev["tuning_runs"])
+    learned_variational_params_cp = prev["learned_variational_params"]
+    with open(file_path_ncp) as f:
+        prev = json.load(f)
+    initial_step_size_ncp = prev["initial_step_size"]
+    num_leapfrog_steps_ncp = get_best_num_leapfrog_steps_from_tuning_runs(prev["tuning_runs"])
+    rng = np.random.default_rng(FLAGS.seed + 1)
+    initial_states_cp = list(util.variational_inits_from_params(
+        learned_variational_params_cp, param_names=param_names, num_inits=FLAGS.num_chains, rng=rng).values())
+    (target_cp, target_ncp), _ = create_target_graph(FLAGS, model_config, results_dir)
+    rank, world = distributed.rank_world()
+    lo, hi = distributed.shard_range(FLAGS.num_chains, rank, world)
+    device = distributed.local_device()
+    x0 = model_config.join(initial_states_cp)[lo:hi]
+    best_ess_min, results = 0, None
+    for num_ls in sorted(set([num_leapfrog_steps_ncp, num_leapfrog_steps_cp])):
+        FLAGS.num_leapfrog_steps = num_ls + num_ls
+        util.print("\nNumber of leaprog steps is set to {}.\n".format(FLAGS.num_leapfrog_steps))
+        start_time = time.time()
+        res = inference.hmc_interleaved(
+            model_config, target_cp, target_ncp, num_ls, num_ls, initial_step_size_cp, initial_step_size_ncp, x0,
+            num_samples=FLAGS.num_samples, num_burnin_steps=FLAGS.num_burnin_steps,
+            num_adaptation_steps=FLAGS.num_adaptation_steps,
+            num_chains_to_save=min(FLAGS.num_chains_to_save, hi - lo) if rank == 0 else 0, seed=FLAGS.seed,
+            chain_offset=lo, device=device, precision=FLAGS.precision)
+        ess_flat = distributed.gather_chains(res.ess_flat, device)
+        n_cp = distributed.sum_scalar(float(res.is_accepted_cp.sum()), device)
+        n_ncp = distributed.sum_scalar(float(res.is_accepted_ncp.sum()), device)
+        mcmc_time = time.time() - start_time
+        normalized = [1000 * e / (FLAGS.num_samples * FLAGS.num_leapfrog_steps) for e in model_config.split(ess_flat)]
+        ess_min, sem_min = util.get_min_ess(normalized, FLAGS.num_chains)
+        util.print("ESS: {} +/- {}".format(ess_min, sem_min))
+        denom = float(FLAGS.num_samples * FLAGS.num_chains)
+        if results is None or float(ess_min) > best_ess_min:
+            best_ess_min = float(ess_min)
+            results = (num_ls, ess_min, sem_min, n_cp * 100. / denom, n_ncp * 100. / denom, mcmc_time, res.samples,
+                       normalized)
+    if rank != 0:
+        return
+    (best_num_ls, ess_min, sem_min, acc_cp, acc_ncp, mcmc_time, samples, normalized) = results
+    FLAGS.num_leapfrog_steps = best_num_ls + best_num_ls
+    save_hmc_results(file_path=file_path, initial_step_size_ncp=initial_step_size_ncp,
+                     initial_step_size_cp=initial_step_size_cp, num_leapfrog_steps=best_num_ls,
+                     ess_min=float(ess_min), sem_min=float(sem_min), acceptance_rate_cp=float(acc_cp),
+                     acceptance_rate_ncp=float(acc_ncp), mcmc_time_sec=mcmc_time)
+    save_ess(file_path_base=file_path[:-5], samples=samples, param_names=param_names,
+             normalized_ess_final=normalized, num_chains_to_save=FLAGS.num_chains_to_save)
+
+
 def save_hmc_results(file_path, **kwargs):
     """main.py:531-550: read-modify-append."""
     try:
@@ -283,7 +354,10 @@ def main(argv=None):
         if rank == 0:
             run_vi(FLAGS, model_config, results_dir, file_path)
     elif FLAGS.inference == "HMC":
-        run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False)
+        if FLAGS.method == "i":
+            run_interleaved_hmc(FLAGS, model_config, results_dir, file_path)
+        else:
+            run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False)
     elif FLAGS.inference == "HMCtuning":
         run_hmc(FLAGS, model_config, results_dir, file_path, tuning=True)
     else:

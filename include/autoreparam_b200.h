@@ -139,6 +139,42 @@ int64_t arp_hmc_num_transitions(const arp_hmc_config* cfg);
 int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_real* a, const arp_real* b, int64_t C,
                 const arp_hmc_buffers* buf, int mem, void* stream);
 
+/* Interleaved CP / NCP sampler (--method=i): replaces inference.hmc_interleaved (inference.py:258-329)
+ * + interleaved.Interleaved.one_step (interleaved.py:113-155): per transition one HMC step under rule A
+ * (CP), one under rule B (NCP), each preceded by a re-bootstrap of (log-prob, gradient) in that rule's
+ * coordinates, each with its own step sizes adapted by SimpleStepSizeAdaptation(adaptation_rate,
+ * target_accept_prob).  The chain state lives in the centred space. */
+typedef struct arp_ilv_config {
+  int32_t num_leapfrog_steps_a;   /* num_leapfrog_steps_cp */
+  int32_t num_leapfrog_steps_b;   /* num_leapfrog_steps_ncp */
+  int32_t num_results, num_burnin_steps, num_adaptation_steps, num_steps_between_results;
+  uint64_t seed;
+  int64_t chain_offset;
+  double target_accept_prob;      /* 0.75 (inference.py:294,304) */
+  double adaptation_rate;         /* 0.05 (inference.py:293,303) */
+  int32_t lanes_per_chain;        /* 0 = auto */
+} arp_ilv_config;
+
+/*   x0 [C,D] in  initial states in the CENTRED space;  eps0_a / eps0_b [D] base step sizes of the two rules
+ *   ext_momenta [2T,C,D], ext_log_u [2T,C] in  optional injected streams, index 2*transition + (0: rule A, 1: rule B)
+ *   samples [S,C,D] out centred;  is_accepted_a / _b [S,C] uint8;  step_mult_a / _b [C] final multipliers */
+typedef struct arp_ilv_buffers {
+  const arp_real* x0;
+  const arp_real* eps0_a;
+  const arp_real* eps0_b;
+  const arp_real* ext_momenta;
+  const arp_real* ext_log_u;
+  arp_real* samples;
+  uint8_t* is_accepted_a;
+  uint8_t* is_accepted_b;
+  arp_real* step_mult_a;
+  arp_real* step_mult_b;
+} arp_ilv_buffers;
+
+int arp_hmc_interleaved_run(arp_model* m, const arp_ilv_config* cfg, const arp_real* a_a, const arp_real* b_a,
+                            const arp_real* a_b, const arp_real* b_b, int64_t C, const arp_ilv_buffers* buf,
+                            int mem, void* stream);
+
 /* replaces tfp.mcmc.effective_sample_size (inference.py:240,327):
  * samples [S,C,D] -> ess [C,D].  Optional extra outputs (NULL to skip): per-series
  * mean [C,D] and biased variance [C,D] -- the per-chain moments R-hat is built

@@ -548,6 +548,61 @@ def hmc_chain(model, d, z0, eps0, L, num_results, num_burnin, num_adapt,
     return out
 
 
+def hmc_interleaved_chain(model, d, x0, eps0_a, eps0_b, L_a, L_b, num_results, num_burnin, num_adapt,
+                          rule_a=(1.0, 1.0), rule_b=(0.0, 0.0), momenta=None, log_u=None, seed=0, chain_ids=None,
+                          thin=1, target_accept=0.75, rate=0.05):
+    """Interleaved CP / NCP sampler: interleaved.py:113-155 + inference.py:258-329 [TFP
+    SimpleStepSizeAdaptation].  The state x lives in the centred space.  Per transition, for rule r in
+    (A = CP, B = NCP): z = to_rule_r(x) (to_noncentered); (lp, g) re-bootstrapped at z; one HMC step of L_r
+    leapfrog steps with step eps0_r * mult_r; x = to_centered(z'); while transition < num_adapt,
+    mult_r *= (1 + rate) if min(1, exp(log_alpha)) > target else 1 / (1 + rate).
+    Streams are indexed 2 * transition + r."""
+    x = np.array(x0, dtype=np.float64)
+    C, D = x.shape
+    if chain_ids is None:
+        chain_ids = np.arange(C)
+    T = num_transitions(num_results, num_burnin, thin)
+    rules = (rule_a, rule_b)
+    eps0 = (np.asarray(eps0_a, dtype=np.float64).reshape(1, D), np.asarray(eps0_b, dtype=np.float64).reshape(1, D))
+    Ls = (L_a, L_b)
+    mult = [np.ones(C), np.ones(C)]
+    samples, acc_a, acc_b = [], [], []
+    next_keep = num_burnin
+    for t in range(T):
+        accs = []
+        for r in (0, 1):
+            a, b = rules[r]
+            f = lambda zz: log_joint_and_grad(model, d, zz, a, b)
+            z = to_noncentered(model, d, x, a, b)
+            lp, g = f(z)
+            sid = 2 * t + r
+            v0 = (np.asarray(momenta[sid], dtype=np.float64) if momenta is not None
+                  else philox_normals(seed, chain_ids, sid, STREAM_MOMENTUM, D))
+            eps = eps0[r] * mult[r][:, None]
+            v, xx, gx = v0.copy(), z.copy(), g.copy()
+            for _ in range(Ls[r]):
+                v = v + 0.5 * eps * gx
+                xx = xx + eps * v
+                lpx, gx = f(xx)
+                v = v + 0.5 * eps * gx
+            la = lpx - lp + 0.5 * (v0 * v0).sum(1) - 0.5 * (v * v).sum(1)
+            la = np.where(np.isfinite(la) | (la == np.inf), la, -np.inf)
+            lu = (np.asarray(log_u[sid], dtype=np.float64) if log_u is not None
+                  else philox_log_uniform(seed, chain_ids, sid))
+            acc = lu < la
+            z = np.where(acc[:, None], xx, z)
+            x = to_centered(model, d, z, a, b)
+            if t < num_adapt:
+                pacc = np.exp(np.minimum(la, 0.0))
+                mult[r] = np.where(pacc > target_accept, mult[r] * (1 + rate), mult[r] / (1 + rate))
+            accs.append(acc)
+        if t == next_keep:
+            samples.append(x.copy()); acc_a.append(accs[0]); acc_b.append(accs[1])
+            next_keep += 1 + thin
+    return dict(samples=np.array(samples), is_accepted_a=np.array(acc_a), is_accepted_b=np.array(acc_b),
+                step_mult_a=mult[0], step_mult_b=mult[1], x=x)
+
+
 # --------------------------------------------------------------------------- #
 # ESS  [TFP effective_sample_size, inference.py:240] + util.get_min_ess
 # --------------------------------------------------------------------------- #

@@ -96,6 +96,17 @@ def test_cli_end_to_end_8schools(tmp_path, capsys):
     _run(base + ["--inference=HMC", "--method=cVIP", "--num_leapfrog_steps=4"])
     _run(base + ["--inference=HMC", "--method=dVIP", "--num_leapfrog_steps=4"])
     assert json.load(open(os.path.join(rd, "cVIP_eig_tied.json")))["ess_min"][0] > 0
+    # interleaved CP / NCP (--method=i): needs tuning runs for both CP and NCP (main.py:452-480)
+    for L in (2, 4):
+        _run(base + ["--inference=HMCtuning", "--method=CP", "--num_leapfrog_steps=%d" % L])
+    _run(base + ["--inference=HMC", "--method=i", "--num_chains_to_save=2"])
+    out = capsys.readouterr().out
+    assert "ESS: " in out
+    il = json.load(open(os.path.join(rd, "i_tied.json")))
+    assert set(il) == {"initial_step_size_ncp", "initial_step_size_cp", "num_leapfrog_steps", "ess_min", "sem_min",
+                       "acceptance_rate_cp", "acceptance_rate_ncp", "mcmc_time_sec"}
+    assert il["ess_min"][0] > 0 and 30 < il["acceptance_rate_ncp"][0] <= 100
+    assert np.load(os.path.join(rd, "i_tied_traces.npz"))["theta"].shape == (300, 2, 8)
     with pytest.raises(Exception, match="Run VI first"):
         _run(["--model=8schools", "--results_dir=" + str(tmp_path / "empty"), "--inference=HMC", "--method=CP",
               "--num_leapfrog_steps=2"])
