@@ -71,11 +71,31 @@ def lib_path(precision="f32"):
     return os.environ.get("ARP_LIB_%s" % precision.upper(), os.path.join(_HERE, "libarp_%s.so" % precision))
 
 
+def _try_build():
+    """A fresh checkout has no .so (they are git-ignored): compile them once with nvcc if it is available.
+    This only builds the CUDA library; nothing here can compute without it."""
+    root = os.path.dirname(_HERE)
+    entry = os.path.join(root, "__graft_entry__.py")
+    if not os.path.exists(entry):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("__graft_entry__", entry)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.compile_libraries()
+    except Exception as e:  # reported by the caller as "library missing"
+        import sys
+        sys.stderr.write("autoreparam_b200: building the CUDA library failed: %s\n" % e)
+
+
 def load(precision="f32"):
     """Load (once) and return the CUDA library for ``precision`` in {"f32","f64"}."""
     if precision in _libs:
         return _libs[precision]
     path = lib_path(precision)
+    if not os.path.exists(path):
+        _try_build()
     if not os.path.exists(path):
         raise RuntimeError(
             "autoreparam_b200: CUDA library %s is missing -- build it with "

@@ -60,7 +60,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int NF>
+// GAMMA = german_credit_gammascale (models.py:930-945): beta_log_scales is not a Normal site (never
+// reparameterised); beta ~ N(0, exp(overall_log_scale + beta_log_scales)).
+template <int NF, bool GAMMA>
 __global__ void __launch_bounds__(TCS_THREADS, 1)
 k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
   using K = Tcs<NF>;
@@ -199,7 +201,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     auto xch_at = [&](int slot, int q) -> float& { return xch[(slot * TC_NQ + q) * TC_CHAINS + r]; };
     // momentum: registers (NF = 32) or the global workspace (NF = 64); coordinate 0 is replicated in every
     // quarter, so its momentum always stays in a private register
-    float vreg[V_IN_REGS ? NLOC : 1];
+    float vreg[V_IN_REGS ? NLOC : 1] = {};
     float v0r = 0.f;
     auto vget = [&](int i) -> float {
       if (i == 0) return v0r;
@@ -261,8 +263,10 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             if (k < nf) {
               const int f = FPW * w + k;
               float dummy = 0.f;
-              const Site ss = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy);
-              const Site sb = site_fwd_fast(xs[(1 + FPW + k) * TC_WORKERS], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
+              float ls;
+              if (GAMMA) ls = s0.x + xs[(1 + k) * TC_WORKERS];
+              else ls = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy).x;
+              const Site sb = site_fwd_fast(xs[(1 + FPW + k) * TC_WORKERS], 0.f, ls, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
               be[k8] = sb.x * NLOG2E;   // GEMM1 then yields -log2(e) * eta: one FMUL less per likelihood element
             }
           }
@@ -328,12 +332,20 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             const int f = FPW * w + k;
             const float af = pa_s[1 + f], ab_ = pa_s[1 + F + f], bb_ = pb_s[1 + F + f];
             const float xs_s = xs[(1 + k) * TC_WORKERS], xs_b = xs[(1 + FPW + k) * TC_WORKERS];
-            const Site ss = site_fwd_unit(xs_s, s0.x, af, lps);
-            const Site sb = site_fwd_fast(xs_b, 0.f, ss.x, ab_, bb_, lps);
+            Site ss;
+            if (GAMMA) {
+              ss.x = xs_s;   // the coordinate is the centred value itself
+              // log Gamma(1/2, 1/2) density of v: v/2 - e^v/2 + log(1/2)/2 - lgamma(1/2)
+              lps += 0.5f * xs_s - 0.5f * exp_fast(xs_s) + (float)(-0.34657359027997264 - 0.57236494292470008);
+            } else {
+              ss = site_fwd_unit(xs_s, s0.x, af, lps);
+            }
+            const Site sb = site_fwd_fast(xs_b, 0.f, GAMMA ? s0.x + xs_s : ss.x, ab_, bb_, lps);
             float gb, mb, lb, ab;
             site_rev(sb, __uint_as_float(gv[k]), 0.f, ab_, bb_, gb, mb, lb, ab);
             float gs, mb2, lb2, ab2;
-            site_rev(ss, lb, s0.x, af, 1.f, gs, mb2, lb2, ab2);
+            if (GAMMA) { gs = 0.5f - 0.5f * exp_fast(xs_s) + lb; mb2 = lb; }
+            else site_rev(ss, lb, s0.x, af, 1.f, gs, mb2, lb2, ab2);
             acc0 += mb2;
             const float es = pe_s[1 + f] * mult, eb = pe_s[1 + F + f] * mult;
             float vs = vget(1 + k) + 0.5f * es * gs;
@@ -470,6 +482,21 @@ struct GermanTcs {
   bool ready() const { return ok; }
 };
 
+template <bool GAMMA>
+static inline cudaError_t tcs_launch(int nf_pad, dim3 grid, cudaStream_t st, const TcsParams& tp, const HmcWs& ws, const HmcArgs& p) {
+  cudaError_t e;
+  if (nf_pad == 32) {
+    e = cudaFuncSetAttribute(k_german_tcs_hmc<32, GAMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tcs<32>::BYTES);
+    if (e != cudaSuccess) return e;
+    k_german_tcs_hmc<32, GAMMA><<<grid, TCS_THREADS, Tcs<32>::BYTES, st>>>(tp, ws, p);
+  } else {
+    e = cudaFuncSetAttribute(k_german_tcs_hmc<64, GAMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tcs<64>::BYTES);
+    if (e != cudaSuccess) return e;
+    k_german_tcs_hmc<64, GAMMA><<<grid, TCS_THREADS, Tcs<64>::BYTES, st>>>(tp, ws, p);
+  }
+  return cudaGetLastError();
+}
+
 static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt, const HmcArgs& p, const real* z0,
                                  cudaStream_t st, bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
                                  std::atomic<long long>* launches, std::string* err) {
@@ -491,20 +518,19 @@ static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt,
   ws.nacc = nacc->as<int>();
   ws.sd = (int)Cpad; ws.sc = 1;
   const dim3 grid((unsigned)(Cpad / TC_CHAINS));
-  if (fp_simt == 32) k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 32><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
-  else k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 64><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
-  launches->fetch_add(1);
-  TCS_CUDA(cudaGetLastError());
-  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk};
-  if (tc.nf_pad == 32) {
-    TCS_CUDA(cudaFuncSetAttribute(k_german_tcs_hmc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tcs<32>::BYTES));
-    k_german_tcs_hmc<32><<<grid, TCS_THREADS, Tcs<32>::BYTES, st>>>(tp, ws, p);
+  const bool gamma = dm.kind == MODEL_GERMAN_GAMMA;
+  if (gamma) {
+    if (fp_simt == 32) k_hmc_init<MODEL_GERMAN_GAMMA, 1, 32><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
+    else k_hmc_init<MODEL_GERMAN_GAMMA, 1, 64><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
   } else {
-    TCS_CUDA(cudaFuncSetAttribute(k_german_tcs_hmc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tcs<64>::BYTES));
-    k_german_tcs_hmc<64><<<grid, TCS_THREADS, Tcs<64>::BYTES, st>>>(tp, ws, p);
+    if (fp_simt == 32) k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 32><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
+    else k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 64><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
   }
   launches->fetch_add(1);
   TCS_CUDA(cudaGetLastError());
+  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk};
+  TCS_CUDA(gamma ? tcs_launch<true>(tc.nf_pad, grid, st, tp, ws, p) : tcs_launch<false>(tc.nf_pad, grid, st, tp, ws, p));
+  launches->fetch_add(1);
   if (want_final) {
     TCS_CUDA(dfz->alloc((size_t)C * p.D * sizeof(real)));
     const long long n = C * p.D;

@@ -93,9 +93,10 @@ extern "C" int arp_model_create(const char* model_name, const arp_model_data* d,
       for (int f = 0; f < dm.F; ++f) X[(size_t)n * dm.Fpad + f] = (real)d->X[(size_t)n * dm.F + f];
     UP(X, X); UP(y, to_real(d->y, dm.N));
 #ifndef ARP_FP64
-    if (dm.kind == MODEL_GERMAN_LOGNORMAL) {
+    {
       std::string err;
-      if (!m->tc.build(d->X, d->y, dm.N, dm.F, &err)) return bail("tcgen05 operand build: " + err);
+      if (dm.kind == MODEL_GERMAN_LOGNORMAL && !m->tc.build(d->X, d->y, dm.N, dm.F, &err))
+        return bail("tcgen05 operand build: " + err);
       if (!m->tcs.build(d->X, d->y, dm.N, dm.F, &err)) return bail("tcgen05 streaming operand build: " + err);
     }
 #endif
@@ -294,10 +295,10 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
 
 #ifndef ARP_FP64
   const bool tc_res = m->dev.kind == MODEL_GERMAN_LOGNORMAL && m->tc.ready();   // resident-X kernel
-  const bool tc_str = m->dev.kind == MODEL_GERMAN_LOGNORMAL && m->tcs.ready();  // streaming kernel
+  const bool tc_str = (m->dev.kind == MODEL_GERMAN_LOGNORMAL || m->dev.kind == MODEL_GERMAN_GAMMA) && m->tcs.ready();
   const bool tc_ok = tc_res || tc_str;
   if ((cfg->engine == 2 || cfg->engine == 3) && !tc_ok)
-    return fail("arp_hmc_run: the tcgen05 engine needs german_credit_lognormalcentered with at most 64 features");
+    return fail("arp_hmc_run: the tcgen05 engine needs a german_credit model with at most 64 features");
   if (cfg->engine == 3 && !tc_str) return fail("arp_hmc_run: streaming tcgen05 engine not available for this model");
   const bool use_tc = tc_ok && (cfg->engine == 2 || cfg->engine == 3 || (cfg->engine == 0 && german_tc_auto(C)));
   const bool use_stream = use_tc && (cfg->engine == 3 || !tc_res);

@@ -115,12 +115,12 @@ def _case_model(model, method, C, seed):
     return mc, raw, D, a, b, z0
 
 
-@pytest.mark.parametrize("model", ["german_synth", MODEL])
+@pytest.mark.parametrize("model", ["german_synth", MODEL, "german_credit_gammascale"])
 @pytest.mark.parametrize("method", ["CP", "NCP", "VIP_ab"])
 def test_tcs_single_leapfrog_gradient(model, method):
     C = 9
     mc, raw, D, a, b, z0 = _case_model(model, method, C, seed=41)
-    _, g_ref = O.log_joint_and_grad(MODEL, raw, z0, a, b)
+    _, g_ref = O.log_joint_and_grad(MODEL if model == "german_synth" else model, raw, z0, a, b)
     eps = 2.0 ** -6
     out = engine.hmc_run(mc, z0, np.full(D, eps), a, b, num_leapfrog_steps=1, num_results=1, num_burnin_steps=0,
                          num_adaptation_steps=0, ext_momenta=np.zeros((1, C, D)), ext_log_u=np.full((1, C), -1e30),
@@ -132,7 +132,7 @@ def test_tcs_single_leapfrog_gradient(model, method):
     assert (err < allow).all(), (err, allow)
 
 
-@pytest.mark.parametrize("model", ["german_synth", MODEL])
+@pytest.mark.parametrize("model", ["german_synth", MODEL, "german_credit_gammascale"])
 def test_tcs_fixed_momenta_trajectory(model):
     C, L, S, burn, adapt = 6, 3, 3, 2, 4
     mc, raw, D, a, b, z0 = _case_model(model, "VIP_a", C, seed=42)
@@ -140,16 +140,18 @@ def test_tcs_fixed_momenta_trajectory(model):
     rng = np.random.default_rng(9)
     mom = rng.standard_normal((T, C, D)).astype(np.float32).astype(np.float64)
     lu = np.log(rng.uniform(size=(T, C))).astype(np.float32).astype(np.float64)
-    eps0 = (np.full(D, 0.01) * rng.uniform(0.5, 1.5, D)).astype(np.float32).astype(np.float64)
-    ref = O.hmc_chain(MODEL, raw, z0, eps0, L, S, burn, adapt, a, b, momenta=mom, log_u=lu)
+    eps0 = (np.full(D, 0.002 if "gamma" in model else 0.01) * rng.uniform(0.5, 1.5, D)).astype(np.float32).astype(np.float64)
+    ref = O.hmc_chain(MODEL if model == "german_synth" else model, raw, z0, eps0, L, S, burn, adapt, a, b, momenta=mom,
+                      log_u=lu)
     out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn,
                          num_adaptation_steps=adapt, ext_momenta=mom, ext_log_u=lu, want_orig=True,
                          engine=engine.ENGINE_TCGEN05_STREAM)
     assert (out["is_accepted"].astype(bool) == ref["is_accepted"]).all()
     assert ref["is_accepted"].mean() > 0
     err = common.rel_err(out["samples"].reshape(S * C, D), ref["samples_centered"].reshape(S * C, D)).max()
-    assert err < 2e-3, err
-    assert common.rel_err(out["final_z"], ref["z"]).max() < 2e-3
+    tol = 2e-2 if "gamma" in model else 2e-3   # exp(10 z0 + v) amplifies fp32 round-off (see test_gpu_hmc)
+    assert err < tol, err
+    assert common.rel_err(out["final_z"], ref["z"]).max() < tol
 
 
 @pytest.mark.parametrize("model", ["german_synth", MODEL])
