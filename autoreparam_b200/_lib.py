@@ -61,7 +61,7 @@ class ViBuffers(C.Structure):
 # every symbol include/autoreparam_b200.h declares
 EXPORTS = ["arp_model_create", "arp_model_destroy", "arp_model_num_coords", "arp_log_joint_grad",
            "arp_hmc_num_transitions", "arp_hmc_run", "arp_hmc_interleaved_run", "arp_ess", "arp_vi_run", "arp_kernel_launch_count",
-           "arp_last_error", "arp_precision"]
+           "arp_last_error", "arp_precision", "arp_release_cached_memory"]
 
 _libs = {}
 
@@ -124,6 +124,8 @@ def load(precision="f32"):
     lib.arp_kernel_launch_count.restype = i64
     lib.arp_last_error.argtypes = []
     lib.arp_last_error.restype = C.c_char_p
+    lib.arp_release_cached_memory.argtypes = []
+    lib.arp_release_cached_memory.restype = None
     lib.arp_precision.argtypes = []
     lib.arp_precision.restype = C.c_char_p
     assert lib.arp_precision().decode() == precision

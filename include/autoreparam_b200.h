@@ -212,6 +212,9 @@ int arp_vi_run(arp_model* m, const arp_vi_config* cfg, const arp_real* a, const 
 /* number of kernels this library has launched in this process (bench accounting) */
 int64_t arp_kernel_launch_count(void);
 const char* arp_last_error(void);
+/* scratch buffers are pooled across calls (no cudaMalloc / cudaFree inside a call after warm-up);
+ * this returns the pool to the driver */
+void arp_release_cached_memory(void);
 /* "f32" or "f64" */
 const char* arp_precision(void);
 
