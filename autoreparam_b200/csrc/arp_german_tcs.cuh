@@ -15,6 +15,9 @@
 
 namespace arp {
 
+#ifndef TCS_RCP_SHARE
+#define TCS_RCP_SHARE 0   // 1: four sigmoids share one MUFU.RCP (measured: no gain, the epilogue is not purely XU-bound)
+#endif
 #define TCS_NSTAGE 3
 #define TCS_THREADS (TC_WORKERS + 64)
 #define TCS_MMA_WARP (TC_WORKERS / 32)
@@ -34,8 +37,8 @@ struct Tcs {
   static constexpr uint32_t RING = 0;
   static constexpr uint32_t A1 = RING + TCS_NSTAGE * STAGE;
   static constexpr uint32_t A2 = A1 + AIMG;
-  static constexpr uint32_t XCH = A2 + AIMG;                        // float[4][TC_NQ][128]
-  static constexpr uint32_t XS = XCH + 4 * TC_NQ * TC_CHAINS * 4;   // float[NLOC][512]
+  static constexpr uint32_t XCH = A2 + AIMG;                        // float[2][4][TC_NQ][128] (double-buffered by step parity)
+  static constexpr uint32_t XS = XCH + 2 * 4 * TC_NQ * TC_CHAINS * 4;   // float[NLOC][512]
   static constexpr uint32_t PAR = XS + NLOC * TC_WORKERS * 4;       // float[3][2 NF + 4]
   static constexpr uint32_t BAR = PAR + 3 * (2 * NF + 4) * 4;       // 6 + 2 * NSTAGE mbarriers
   static constexpr uint32_t TMEM_PTR = BAR + 16 * 8;
@@ -198,7 +201,11 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const float NLOG2E = -1.4426950408889634f;
     auto dof = [&](int i) { return i == 0 ? 0 : (i <= FPW ? FPW * w + i : F + FPW * w + i - FPW); };
     auto owned = [&](int i) { return i == 0 || (i <= FPW ? (i - 1) < nf : (i - 1 - FPW) < nf); };
-    auto xch_at = [&](int slot, int q) -> float& { return xch[(slot * TC_NQ + q) * TC_CHAINS + r]; };
+    // cross-quarter exchange slots, double-buffered by the parity of the step counter so ONE named barrier per
+    // leapfrog step suffices (a thread can be at most one step ahead of the slowest one)
+    uint32_t par = 0;
+    auto xch_at = [&](int slot, int q) -> float& { return xch[((par * 4 + slot) * TC_NQ + q) * TC_CHAINS + r]; };
+    auto xch_sum = [&](int slot) { return (xch_at(slot, 0) + xch_at(slot, 1)) + (xch_at(slot, 2) + xch_at(slot, 3)); };
     // momentum: registers (NF = 32) or the global workspace (NF = 64); coordinate 0 is replicated in every
     // quarter, so its momentum always stays in a private register
     float vreg[V_IN_REGS ? NLOC : 1] = {};
@@ -235,7 +242,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           }
         }
       }
-      float ke0 = 0.f, ke1 = 0.f;
+      float ke0 = 0.f, ke1 = 0.f, ke0_tot = 0.f, ke1_tot = 0.f;
 #pragma unroll
       for (int i = 0; i < NLOC; ++i) {
         if (owned(i)) {
@@ -297,10 +304,33 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             const float4 y4 = *reinterpret_cast<const float4*>(sy + 32 * w + i);
             const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
             float rr[4];
+#if TCS_RCP_SHARE
+            // four sigmoids share ONE MUFU.RCP (Montgomery's trick): 1/d_k = (1 / prod d) * prod_{j != k} d_j.
+            // The epilogue is bound by the XU (MUFU) pipe -- 2 MUFU per element -- so this trades 0.75 MUFU
+            // per element for 2.25 FMULs.  h is clamped at 30 (sigmoid < 1e-9 there) so the product of four
+            // denominators stays below 2^124.
+            float dq[4], sg4[4], hq4[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+              hq4[q] = __uint_as_float(hv[i + q]);      // = -log2(e) * eta
+              dq[q] = 1.0f + ex2_approx(fminf(hq4[q], 30.f));
+            }
+            {
+              const float p01 = dq[0] * dq[1], p23 = dq[2] * dq[3];
+              const float inv = rcp_approx(p01 * p23);
+              const float i01 = inv * p23, i23 = inv * p01;
+              sg4[0] = i01 * dq[1]; sg4[1] = i01 * dq[0]; sg4[2] = i23 * dq[3]; sg4[3] = i23 * dq[2];
+            }
+#endif
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#if TCS_RCP_SHARE
+              const float hq = hq4[q];
+              const float sg = sg4[q];
+#else
               const float hq = __uint_as_float(hv[i + q]);      // = -log2(e) * eta
               const float sg = rcp_approx(1.0f + ex2_approx(hq));
+#endif
               rr[q] = yy[q] - sg;
               if (last) {
                 // y eta - softplus(eta), softplus(eta) = max(eta,0) - log(sigmoid(|eta|))
@@ -368,30 +398,30 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
         xch_at(0, w) = acc0;
         xch_at(1, w) = lik + lps;
+        xch_at(2, w) = ke0;   // partial kinetic energies ride along (meaningful on the first / last step)
+        xch_at(3, w) = ke1;
         epi_bar();
-        const float acc0_t = (xch_at(0, 0) + xch_at(0, 1)) + (xch_at(0, 2) + xch_at(0, 3));
-        lpx = (xch_at(1, 0) + xch_at(1, 1)) + (xch_at(1, 2) + xch_at(1, 3)) + lp_top;
+        const float acc0_t = xch_sum(0);
+        lpx = xch_sum(1) + lp_top;
+        if (l == 0) ke0_tot = xch_sum(2);
+        if (last) ke1_tot = xch_sum(3);
         {
           float g0, mb, lb, ab;
           site_rev(s0, acc0_t, 0.f, a0, b0, g0, mb, lb, ab);
           const float e = pe_s[0] * mult;
           float v0 = v0r + 0.5f * e * g0;
           if (last) {
-            if (w == 0) { ke1 = fmaf(v0, v0, ke1); ws.gx[co] = g0; ws.xcx[co] = s0.x; }
+            ke1_tot = fmaf(v0, v0, ke1_tot);   // coordinate 0 is replicated: every quarter adds it itself
+            if (w == 0) { ws.gx[co] = g0; ws.xcx[co] = s0.x; }
           } else {
             v0 = v0 + 0.5f * e * g0;
             xs[0] = xs[0] + e * v0;
           }
           v0r = v0;
         }
-        epi_bar();
+        par ^= 1;
       }
-      xch_at(2, w) = ke0;
-      xch_at(3, w) = ke1;
-      epi_bar();
-      ke0 = (xch_at(2, 0) + xch_at(2, 1)) + (xch_at(2, 2) + xch_at(2, 3));
-      ke1 = (xch_at(3, 0) + xch_at(3, 1)) + (xch_at(3, 2) + xch_at(3, 3));
-      float log_alpha = lpx - lp_cur + 0.5f * ke0 - 0.5f * ke1;
+      float log_alpha = lpx - lp_cur + 0.5f * ke0_tot - 0.5f * ke1_tot;
       if (!(log_alpha == log_alpha) || log_alpha == -INFINITY) log_alpha = -INFINITY;
       float log_u;
       if (p.ext_log_u) log_u = p.ext_log_u[(size_t)tg * p.C + (valid ? chain : 0)];
@@ -433,7 +463,6 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           if (p.is_accepted && w == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
         }
       }
-      epi_bar();
     }
     if (w == 0) {
       ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
