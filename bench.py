@@ -31,6 +31,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_GRAD = {25: 1.06e5, 62: 2.55e5}  # 4NF + 12F + 6N
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at the default workload
+# (profiles/r01_bench_kernel_traffic.csv: 0.05 GB read + 3.344 GB written); the algorithmic bytes are the
+# thinned sample store 1000 x 16384 x 51 x 4 B + is_accepted = 3.359 GB, i.e. no re-reads
+NCU_TRAFFIC_DEFAULT_WORKLOAD = 48132096 + 3344686592
 
 
 def parse():
@@ -290,7 +294,9 @@ def main():
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "frac": achieved_tf / peak_tf,
+                         "traffic": NCU_TRAFFIC_DEFAULT_WORKLOAD if (C, S, args.features, args.num_burnin_steps) ==
+                         (16384, 1000, 25, 500) else None,
                          "note": "algorithmic fp32 flop (%.3g per grad eval) / measured dense bf16 cuBLAS peak (%s, "
                                  "sustained); per GPU" % (flop, pk_src)},
             "ess": {"ess_per_sec": ess_per_sec, "ess_per_1000_grads_mean": ess_per_1000,
