@@ -137,7 +137,7 @@ def peaks():
 
 
 # ---------------------------------------------------------- reference arm ---
-def cpu_reference_run(args, raw, D, a, b, steps, warmup, chains=1024, transitions=12):
+def cpu_reference_run(args, raw, D, a, b, steps, warmup, chains=1024, transitions=50):
     """The reference's CPU implementation of the path, restated (oracle port:
     PyTorch CPU fp32, [C, D] tensors, autograd gradient at every leapfrog step,
     TFP op order), all host threads, on a bounded sample of the workload."""
@@ -304,7 +304,7 @@ def main():
             "wall_s_timed_region": wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(args, raw, D, a, b, steps=2, warmup=1)
+            r = cpu_reference_run(args, raw, D, a, b, steps=3, warmup=1)   # ~10-15 s of CPU work
             line["cpu_baseline"] = {"value": r["value"], "unit": "grad_evals/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         print(json.dumps(line))
