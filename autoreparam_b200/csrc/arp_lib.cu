@@ -118,7 +118,23 @@ extern "C" int arp_model_create(const char* model_name, const arp_model_data* d,
       const int pos = cur[d->idx0[n]]++;
       xs[pos] = (real)d->x1[n]; ys[pos] = (real)d->y[n];
     }
-    UP(offs, offs); UP(x1, xs); UP(y, ys); UP(u, to_real(d->u, dm.J));
+    // per-county sufficient statistics of the Gaussian likelihood, accumulated in double
+    std::vector<real> stats((size_t)6 * dm.J, (real)0);
+    for (int j = 0; j < dm.J; ++j) {
+      const int n0 = offs[j], n1 = offs[j + 1];
+      const double cnt = n1 - n0;
+      double sy = 0, sx = 0;
+      for (int n = n0; n < n1; ++n) { sy += (double)ys[n]; sx += (double)xs[n]; }
+      const double yb = cnt > 0 ? sy / cnt : 0, xb = cnt > 0 ? sx / cnt : 0;
+      double cyy = 0, cxy = 0, cxx = 0;
+      for (int n = n0; n < n1; ++n) {
+        const double dy = (double)ys[n] - yb, dx = (double)xs[n] - xb;
+        cyy += dy * dy; cxy += dx * dy; cxx += dx * dx;
+      }
+      real* st = &stats[(size_t)6 * j];
+      st[0] = (real)cnt; st[1] = (real)yb; st[2] = (real)xb; st[3] = (real)cyy; st[4] = (real)cxy; st[5] = (real)cxx;
+    }
+    UP(offs, offs); UP(x1, xs); UP(y, ys); UP(u, to_real(d->u, dm.J)); UP(w, stats);
   } else if (name == "election") {
     if (d->n <= 0 || d->j <= 0 || !d->idx0 || !d->x1 || !d->x2 || !d->y) return bail("needs n, j (n_state), idx0 (state), x1 (female), x2 (black), y");
     dm.kind = MODEL_ELECTION; dm.K = (int)d->j; dm.J = dm.K + 1; dm.D = dm.K + 4;

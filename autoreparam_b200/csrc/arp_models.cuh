@@ -47,7 +47,7 @@ struct DevModel {
   const real* y;    // observations (election: sum of y per cell)
   const real* x1;   // radon floor | election female | electric treatment | time_series year | 8schools sigma
   const real* x2;   // election black
-  const real* w;    // election: cell count
+  const real* w;    // election: cell count | radon: per-county sufficient statistics [J][6]
   const real* u;    // radon: log uranium [J]
   const int* offs;  // CSR offsets of the groups into the (sorted) observations [J+1]
   const int* gidx;  // electric: grade index per observation (-1 = one-hot out of range)
@@ -238,6 +238,7 @@ __device__ real vg_radon(const DevModel& m, const real* a, const real* b,
   Site sb2 = site_fwd_unit(z(2), (real)0, a2, lp_top);
   const real mua = smua.x, b1 = sb1.x, b2 = sb2.x;
   real lp = 0, acc_mua = 0, acc_b1 = 0, acc_b2 = 0;
+  double lik_d = 0;   // likelihood total in double: log-prob differences of O(0.1) matter to the accept test
   for (int j = sub; j < J; j += LPC) {
     const real uj = ldg(m.u + j);
     const real mu_j = mua + uj * b1;
@@ -252,17 +253,18 @@ __device__ real vg_radon(const DevModel& m, const real* a, const real* b,
       inv = r_exp(-lsj);
       inv2 = inv * inv;
     }
-    const int n0 = ldg(m.offs + j), n1 = ldg(m.offs + j + 1);
-    real se = 0, sex = 0, see = 0;
-    for (int n = n0; n < n1; ++n) {
-      const real xn = ldg(m.x1 + n);
-      const real e = ldg(m.y + n) - mj - xn * b2;
-      se += e;
-      sex = fma(e, xn, sex);
-      see = fma(e, e, see);
-    }
-    const real cnt = (real)(n1 - n0);
-    lp += (real)-0.5 * see * inv2 - cnt * (lsj + ARP_HALF_LOG_2PI);
+    // Gaussian likelihood of county j through its sufficient statistics (exact algebra, precomputed in
+    // double at model-create time): with d = ybar - m_j - b2 xbar and within-county centred moments C..,
+    //   sum e = n d,  sum e x = Cxy - b2 Cxx + n xbar d,  sum e^2 = Cyy - 2 b2 Cxy + b2^2 Cxx + n d^2.
+    // The reference evaluates every observation through a dense one-hot matmul (models.py:834-837); the
+    // roofline numerator stays the naive 6N + 8J flop of SURVEY.md 8d.
+    const real* st = m.w + (size_t)6 * j;
+    const real cnt = ldg(st), ybar = ldg(st + 1), xbar = ldg(st + 2), Cyy = ldg(st + 3), Cxy = ldg(st + 4), Cxx = ldg(st + 5);
+    const real dj = ybar - mj - xbar * b2;
+    const real se = cnt * dj;
+    const real sex = Cxy - b2 * Cxx + cnt * xbar * dj;
+    const real see = Cyy - (real)2 * b2 * Cxy + b2 * b2 * Cxx + cnt * dj * dj;
+    lik_d += (double)((real)-0.5 * see * inv2 - cnt * (lsj + ARP_HALF_LOG_2PI));   // up to 1e4 counties of O(100) each
     acc_b2 += sex * inv2;
     real zb, mb, lb, ab;
     site_rev(sm, se * inv2, mu_j, aj, (real)1, zb, mb, lb, ab);
@@ -281,7 +283,7 @@ __device__ real vg_radon(const DevModel& m, const real* a, const real* b,
   acc_mua = group_sum<LPC>(acc_mua);
   acc_b1 = group_sum<LPC>(acc_b1);
   acc_b2 = group_sum<LPC>(acc_b2);
-  lp = group_sum<LPC>(lp) + lp_top;
+  lp = (real)(group_sum<LPC>((double)lp + lik_d)) + lp_top;
   if (sub == 0) {
     real zb, mb, lb, ab;
     site_rev(smua, acc_mua, (real)0, a0, (real)1, zb, mb, lb, ab);
