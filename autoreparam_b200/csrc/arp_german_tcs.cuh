@@ -18,6 +18,9 @@ namespace arp {
 #ifndef TCS_RCP_SHARE
 #define TCS_RCP_SHARE 0   // 1: four sigmoids share one MUFU.RCP (measured: no gain, the epilogue is not purely XU-bound)
 #endif
+#ifndef TCS_EXPERIMENT
+#define TCS_EXPERIMENT 0   // != 0: timing-only variants used to locate the epilogue bound (results are wrong)
+#endif
 #define TCS_NSTAGE 3
 #define TCS_THREADS (TC_WORKERS + 64)
 #define TCS_MMA_WARP (TC_WORKERS / 32)
@@ -40,7 +43,7 @@ struct Tcs {
   static constexpr uint32_t XCH = A2 + AIMG;                        // float[2][4][TC_NQ][128] (double-buffered by step parity)
   static constexpr uint32_t XS = XCH + 2 * 4 * TC_NQ * TC_CHAINS * 4;   // float[NLOC][512]
   static constexpr uint32_t PAR = XS + NLOC * TC_WORKERS * 4;       // float[3][2 NF + 4]
-  static constexpr uint32_t BAR = PAR + 3 * (2 * NF + 4) * 4;       // 6 + 2 * NSTAGE mbarriers
+  static constexpr uint32_t BAR = PAR + 4 * (2 * NF + 4) * 4;       // 6 + 2 * NSTAGE mbarriers (PAR: a, b, eps0, c)
   static constexpr uint32_t TMEM_PTR = BAR + 16 * 8;
   static constexpr uint32_t BYTES = TMEM_PTR + 16;
   // TMEM columns
@@ -51,7 +54,8 @@ struct Tcs {
 };
 
 struct TcsParams {
-  const uint8_t* img;  // nchunk stage images
+  const uint8_t* img;   // nchunk stage images
+  const float* cvec;    // [F] c_f = sum_n X[n,f] (y_n - 1): the part of the log-likelihood that is linear in beta
   int N, F, nchunk;
 };
 
@@ -85,6 +89,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       par[(2 * NF + 4) + i] = p.b[i];
       par[2 * (2 * NF + 4) + i] = p.eps0[i];
     }
+    for (int i = tid; i < tp.F; i += TCS_THREADS) par[3 * (2 * NF + 4) + i] = tp.cvec[i];
   }
   if (warp == TCS_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
@@ -191,6 +196,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const float* pa_s = reinterpret_cast<const float*>(smem + K::PAR);
     const float* pb_s = pa_s + (2 * NF + 4);
     const float* pe_s = pb_s + (2 * NF + 4);
+    const float* pc_s = pe_s + (2 * NF + 4);
     float lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
     int nacc = ws.nacc[chain];
     const unsigned int gchain = p.chain_offset + (unsigned int)chain;
@@ -329,19 +335,30 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               const float sg = sg4[q];
 #else
               const float hq = __uint_as_float(hv[i + q]);      // = -log2(e) * eta
+#if TCS_EXPERIMENT == 2
+              const float sg = 0.5f * ex2_approx(hq);            // timing experiment: no MUFU.RCP
+#elif TCS_EXPERIMENT == 3
+              const float sg = rcp_approx(1.0f + hq * hq);       // timing experiment: no MUFU.EX2
+#else
               const float sg = rcp_approx(1.0f + ex2_approx(hq));
 #endif
+#endif
               rr[q] = yy[q] - sg;
-              if (last) {
-                // y eta - softplus(eta), softplus(eta) = max(eta,0) - log(sigmoid(|eta|))
-                const float eta = hq * -0.69314718055994531f;
-                const float m = fmaxf(sg, 1.0f - sg);
-                const float term = fmaf(lg2_approx(m), 0.69314718055994531f, yy[q] * eta - fmaxf(eta, 0.f));
-                lik += (n0 + i + q < tp.N) ? term : 0.f;
-              }
+              // log-likelihood (last step only): sum_n [y eta - softplus(eta)] = beta . c + sum_n ln sigmoid(eta_n)
+              // with c = X^T (y - 1) precomputed; only the log-sigmoid sum is per observation.  Padded rows have
+              // eta = 0, i.e. lg2(1/2) = -1 each: corrected by a constant below.
+              if (last) lik += lg2_approx(sg);
             }
+#if TCS_EXPERIMENT == 1
+            {  // timing experiment: head only (no tail split)
+              const __half2 h01 = __floats2half2_rn(rr[0], rr[1]), h23 = __floats2half2_rn(rr[2], rr[3]);
+              r1[i / 2] = *reinterpret_cast<const uint32_t*>(&h01); r1[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+              r2[i / 2] = 0; r2[i / 2 + 1] = 0;
+            }
+#else
             split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
             split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
+#endif
           }
           TC_ST16(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, r1);
           TC_ST16(tmem + lane_off + K::COL_R2 + b * 64 + 16 * w, r2);
@@ -355,7 +372,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         if constexpr (FPW == 8) { TC_LD8(tmem + lane_off + K::COL_G + 8 * w, gv); }
         else { TC_LD16(tmem + lane_off + K::COL_G + 16 * w, gv); }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float acc0 = 0.f, lps = 0.f;
+        float acc0 = 0.f, lps = 0.f, lin = 0.f;
 #pragma unroll
         for (int k = 0; k < FPW; ++k) {
           if (k < nf) {
@@ -371,6 +388,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               ss = site_fwd_unit(xs_s, s0.x, af, lps);
             }
             const Site sb = site_fwd_fast(xs_b, 0.f, GAMMA ? s0.x + xs_s : ss.x, ab_, bb_, lps);
+            lin = fmaf(sb.x, pc_s[f], lin);
             float gb, mb, lb, ab;
             site_rev(sb, __uint_as_float(gv[k]), 0.f, ab_, bb_, gb, mb, lb, ab);
             float gs, mb2, lb2, ab2;
@@ -395,6 +413,10 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             vset(1 + k, vs);
             vset(1 + FPW + k, vb);
           }
+        }
+        if (last) {
+          lik = 0.69314718055994531f * (lik + (w == 0 ? (float)(NCH * TC_CHUNK - tp.N) : 0.f));
+          lik += lin;
         }
         xch_at(0, w) = acc0;
         xch_at(1, w) = lik + lps;
@@ -477,7 +499,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
 
 // --------------------------------------------------------------------------- host ---
 struct GermanTcs {
-  DevBuf img;
+  DevBuf img, cvec;
   int N = 0, F = 0, nf_pad = 0, nchunk = 0;
   bool ok = false;
 
@@ -503,7 +525,14 @@ struct GermanTcs {
       }
       memcpy(st + 2 * XCHUNK + (size_t)rloc * 4, &y[i], 4);
     }
+    std::vector<float> cv(64, 0.f);
+    for (int j = 0; j < f; ++j) {
+      double acc = 0;
+      for (int i = 0; i < n; ++i) acc += (double)X[(size_t)i * f + j] * ((double)y[i] - 1.0);
+      cv[j] = (float)acc;
+    }
     cudaError_t e = upload(img, buf);
+    if (e == cudaSuccess) e = upload(cvec, cv);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return false; }
     N = n; F = f; ok = true;
     return true;
@@ -557,7 +586,7 @@ static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt,
   }
   launches->fetch_add(1);
   TCS_CUDA(cudaGetLastError());
-  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk};
+  TcsParams tp{tc.img.as<uint8_t>(), tc.cvec.as<float>(), tc.N, tc.F, tc.nchunk};
   TCS_CUDA(gamma ? tcs_launch<true>(tc.nf_pad, grid, st, tp, ws, p) : tcs_launch<false>(tc.nf_pad, grid, st, tp, ws, p));
   launches->fetch_add(1);
   if (want_final) {
