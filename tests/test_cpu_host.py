@@ -192,8 +192,12 @@ def test_sharded_reductions_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(GLOO_WORKER)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import socket
+    with socket.socket() as sk:      # a free rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29653", str(script), root, str(tmp_path)]
+           "127.0.0.1", "--master-port", str(port), str(script), root, str(tmp_path)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
