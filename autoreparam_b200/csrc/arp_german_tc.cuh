@@ -130,6 +130,28 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
       ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc), "r"(0u) : "memory");
 }
 
+// Warp-uniform issue: the whole issuer warp runs the issue loop convergently and each tcgen05.mma / commit sits
+// under elect.sync, which tells ptxas the region is single-threaded, so descriptors and TMEM addresses stay in
+// uniform registers and every MMA is one UTCHMMA.  (Inside an `if (lane == 0)` region nvcc wraps each UTCHMMA in
+// an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: ~45 clk of issue latency per MMA, which was on the critical path.)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void mma_ss_if(uint32_t, uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (elect_one()) mma_ss(d, a, b, idesc, acc);
+}
+__device__ __forceinline__ void mma_ts_if(uint32_t, uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (elect_one()) mma_ts(d, a_tmem, b, idesc, acc);
+}
+__device__ __forceinline__ void tc_commit_if(uint32_t, uint32_t bar) {
+  if (elect_one()) tc_commit(bar);
+}
+
 #define TC_LD32(taddr, v)                                                                                  \
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                   \
                "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                    \
@@ -274,19 +296,20 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
   if (warp == TC_MMA_WARP) {
     // =========================== MMA issuer ===========================
     uint32_t pa = 0, pr[2] = {0, 0};
+    const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy for the uniform datapath
     const uint32_t sX[2] = {sbase + TcSmem::X1, sbase + TcSmem::X2};
     const uint32_t sA[2] = {sbase + TcSmem::A1, sbase + TcSmem::A2};
     // the three split products (head x head, tail x head, head x tail)
     const int pa_sel[3] = {0, 0, 1}, pb_sel[3] = {0, 1, 0};
     auto issue_g1 = [&](int c) {
-      const uint32_t d = tmem + TC_COL_H + (uint32_t)(c & 1) * TC_CHUNK;
+      const uint32_t d = tmu + TC_COL_H + (uint32_t)(c & 1) * TC_CHUNK;
 #pragma unroll
       for (int q = 0; q < 3; ++q)
 #pragma unroll
         for (int ks = 0; ks < TC_NF / 16; ++ks) {
           const uint64_t ad = tc_desc(sA[pa_sel[q]] + ks * 2 * TC_SF, TC_SF, TC_SG);
           const uint64_t bd = tc_desc(sX[pb_sel[q]] + (uint32_t)c * (TC_CHUNK / 8) * TC_SG + ks * 2 * TC_SF, TC_SF, TC_SG);
-          mma_ss(d, ad, bd, TC_IDESC_G1, (q | ks) ? 1u : 0u);
+          mma_ss_if(1u, d, ad, bd, TC_IDESC_G1, (q | ks) ? 1u : 0u);
         }
     };
     auto issue_g2 = [&](int c) {
@@ -298,29 +321,30 @@ k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             // A: 16 observations = 8 packed columns; head in place of H, tail in its own buffer
-            const uint32_t a_t = pa_sel[q] == 0 ? tmem + TC_COL_H + b * TC_CHUNK + 32 * w + 8 * kk
-                                                : tmem + TC_COL_R2 + b * 64 + 16 * w + 8 * kk;
+            const uint32_t a_t = pa_sel[q] == 0 ? tmu + TC_COL_H + b * TC_CHUNK + 32 * w + 8 * kk
+                                                : tmu + TC_COL_R2 + b * 64 + 16 * w + 8 * kk;
             const uint32_t og = (uint32_t)c * (TC_CHUNK / 8) + 4 * w + 2 * kk;  // first 8-observation group
             // MN-major B: N = features (chunks of 8 at TC_SF), K = observations (groups of 8 at TC_SG)
             const uint64_t bd = tc_desc(sX[pb_sel[q]] + og * TC_SG, TC_SG, TC_SF);
-            mma_ts(tmem + TC_COL_G, a_t, bd, TC_IDESC_G2, (c | q | w | kk) ? 1u : 0u);
+            mma_ts_if(1u, tmu + TC_COL_G, a_t, bd, TC_IDESC_G2, (c | q | w | kk) ? 1u : 0u);
           }
     };
-    // ONE lane runs the whole issue loop (waits included).  If the other 31 lanes ran ahead into the next
-    // mbarrier.try_wait they could suspend the warp while lane 0 still has MMAs to issue.
-    if (lane == 0) {
+    // The whole warp runs the issue loop convergently (waits included); each MMA / commit is issued by the
+    // elected lane.  (With `if (lane == 0)` around single MMAs the other 31 lanes ran ahead into the next
+    // mbarrier.try_wait and could suspend the warp while lane 0 still had MMAs to issue.)
+    {
       for (int s = 0; s < n_lf; ++s) {
         mbar_wait(bar_a, pa); pa ^= 1;
         tc_fence_after();
-        issue_g1(0); tc_commit(bar_h0);
-        issue_g1(1); tc_commit(bar_h0 + 8);
+        issue_g1(0); tc_commit_if(1u, bar_h0);
+        issue_g1(1); tc_commit_if(1u, bar_h0 + 8);
         for (int c = 0; c < TC_NCHUNK; ++c) {
           const int b = c & 1;
           mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
           tc_fence_after();
           issue_g2(c);
-          if (c + 2 < TC_NCHUNK) { issue_g1(c + 2); tc_commit(bar_h0 + 8 * b); }
-          if (c == TC_NCHUNK - 1) tc_commit(bar_g);
+          if (c + 2 < TC_NCHUNK) { issue_g1(c + 2); tc_commit_if(1u, bar_h0 + 8 * b); }
+          if (c == TC_NCHUNK - 1) tc_commit_if(1u, bar_g);
         }
       }
     }

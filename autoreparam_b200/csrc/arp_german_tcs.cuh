@@ -15,12 +15,6 @@
 
 namespace arp {
 
-#ifndef TCS_RCP_SHARE
-#define TCS_RCP_SHARE 0   // 1: four sigmoids share one MUFU.RCP (measured: no gain, the epilogue is not purely XU-bound)
-#endif
-#ifndef TCS_EXPERIMENT
-#define TCS_EXPERIMENT 0   // != 0: timing-only variants used to locate the epilogue bound (results are wrong)
-#endif
 #define TCS_NSTAGE 3
 #define TCS_THREADS (TC_WORKERS + 64)
 #define TCS_MMA_WARP (TC_WORKERS / 32)
@@ -36,6 +30,7 @@ struct Tcs {
   static constexpr uint32_t AIMG = (TC_CHAINS / 8) * SG;
   static constexpr int FPW = NF / TC_NQ;                  // features per worker
   static constexpr int NLOC = 1 + 2 * FPW;
+  static constexpr bool RCP_SHARE = (NF == 32);
   // shared memory
   static constexpr uint32_t RING = 0;
   static constexpr uint32_t A1 = RING + TCS_NSTAGE * STAGE;
@@ -57,6 +52,7 @@ struct TcsParams {
   const uint8_t* img;   // nchunk stage images
   const float* cvec;    // [F] c_f = sum_n X[n,f] (y_n - 1): the part of the log-likelihood that is linear in beta
   int N, F, nchunk;
+  int skew;             // dual-tile kernel: clocks by which tile 1 starts late
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -65,6 +61,44 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Four likelihood elements: r = y - sigmoid(eta) from h = -log2(e) * eta (the GEMM1 output), and on the last
+// leapfrog step the running sum of log2 sigmoid(eta).
+// SHARE: the four sigmoids share ONE MUFU.RCP (Montgomery's trick: 1/d_k = (1 / prod d) * prod_{j != k} d_j), i.e.
+// 1.25 MUFU + 2.25 FMUL per element instead of 2 MUFU.  The epilogue is bound by the XU pipe (16 MUFU lanes / clk /
+// SM), so for F <= 32 this is +6.6 % end to end; for F = 64 the extra registers cost more than it saves.  h is
+// clamped at 30 (sigmoid < 1e-9 there) so the product of four denominators stays below 2^124; beyond the clamp
+// log2 sigmoid = -h to fp32 accuracy.
+template <bool SHARE>
+__device__ __forceinline__ void tcs_sigmoid4(const uint32_t* hv, const float* yy, float* rr, bool last, float& lik) {
+  if constexpr (SHARE) {
+    float hq[4], dq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      hq[q] = __uint_as_float(hv[q]);
+      dq[q] = 1.0f + ex2_approx(fminf(hq[q], 30.f));
+    }
+    const float p01 = dq[0] * dq[1], p23 = dq[2] * dq[3];
+    const float inv = rcp_approx(p01 * p23);
+    const float i01 = inv * p23, i23 = inv * p01;
+    const float sg[4] = {i01 * dq[1], i01 * dq[0], i23 * dq[3], i23 * dq[2]};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      rr[q] = yy[q] - sg[q];
+      if (last) lik += hq[q] > 30.f ? -hq[q] : lg2_approx(sg[q]);
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float sg = rcp_approx(1.0f + ex2_approx(__uint_as_float(hv[q])));
+      rr[q] = yy[q] - sg;
+      // log-likelihood (last step only): sum_n [y eta - softplus(eta)] = beta . c + sum_n ln sigmoid(eta_n) with
+      // c = X^T (y - 1) precomputed; only the log-sigmoid sum is per observation.  Padded rows have eta = 0,
+      // i.e. lg2(1/2) = -1 each: corrected by a constant after the chunk loop.
+      if (last) lik += lg2_approx(sg);
+    }
+  }
 }
 
 // GAMMA = german_credit_gammascale (models.py:930-945): beta_log_scales is not a Normal site (never
@@ -126,57 +160,59 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     }
     __syncwarp();
   } else if (warp == TCS_MMA_WARP) {
-    // =========================== MMA issuer (one lane runs the whole loop) ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (warp-uniform loop, lane 0 issues) ===========================
+    {
+      const uint32_t issue = lane == 0 ? 1u : 0u;   // all lanes run the loop; lane 0 issues
       uint32_t pa = 0, pr[2] = {0, 0};
       const uint32_t sA[2] = {sbase + K::A1, sbase + K::A2};
       const int pa_sel[3] = {0, 0, 1}, pb_sel[3] = {0, 1, 0};
+      const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy for the uniform datapath
       uint32_t cnt = 0;  // global chunk counter of the next GEMM1 to issue
       auto stage_of = [&](uint32_t k) { return sbase + K::RING + (k % TCS_NSTAGE) * K::STAGE; };
       auto issue_g1 = [&](int c, uint32_t k) {
         mbar_wait(bar_xf + 8 * (k % TCS_NSTAGE), (k / TCS_NSTAGE) & 1);
         tc_fence_after();
-        const uint32_t d = tmem + K::COL_H + (uint32_t)(c & 1) * TC_CHUNK;
-        const uint32_t xs = stage_of(k);
+        const uint32_t d = tmu + K::COL_H + (uint32_t)(c & 1) * TC_CHUNK;
+        const uint32_t xs = __shfl_sync(0xffffffffu, stage_of(k), 0);
 #pragma unroll
         for (int q = 0; q < 3; ++q)
 #pragma unroll
           for (int ks = 0; ks < NF / 16; ++ks) {
             const uint64_t ad = tc_desc(sA[pa_sel[q]] + ks * 2 * K::SF, K::SF, K::SG);
             const uint64_t bd = tc_desc(xs + pb_sel[q] * K::XCHUNK + ks * 2 * K::SF, K::SF, K::SG);
-            mma_ss(d, ad, bd, K::IDESC_G1, (q | ks) ? 1u : 0u);
+            mma_ss_if(issue, d, ad, bd, K::IDESC_G1, (q | ks) ? 1u : 0u);
           }
       };
       auto issue_g2 = [&](int c, uint32_t k) {
         const uint32_t b = (uint32_t)(c & 1);
-        const uint32_t xs = stage_of(k);
+        const uint32_t xs = __shfl_sync(0xffffffffu, stage_of(k), 0);
 #pragma unroll
         for (int q = 0; q < 3; ++q)
 #pragma unroll
           for (int w = 0; w < TC_NQ; ++w)
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
-              const uint32_t a_t = pa_sel[q] == 0 ? tmem + K::COL_H + b * TC_CHUNK + 32 * w + 8 * kk
-                                                  : tmem + K::COL_R2 + b * 64 + 16 * w + 8 * kk;
+              const uint32_t a_t = pa_sel[q] == 0 ? tmu + K::COL_H + b * TC_CHUNK + 32 * w + 8 * kk
+                                                  : tmu + K::COL_R2 + b * 64 + 16 * w + 8 * kk;
               const uint32_t og = 4 * w + 2 * kk;  // 8-observation group inside the chunk
               const uint64_t bd = tc_desc(xs + pb_sel[q] * K::XCHUNK + og * K::SG, K::SG, K::SF);
-              mma_ts(tmem + K::COL_G, a_t, bd, K::IDESC_G2, (c | q | w | kk) ? 1u : 0u);
+              mma_ts_if(issue, tmu + K::COL_G, a_t, bd, K::IDESC_G2, (c | q | w | kk) ? 1u : 0u);
             }
       };
       for (int s = 0; s < n_lf; ++s) {
         const uint32_t k0 = cnt;  // global index of chunk 0 of this step
         mbar_wait(bar_a, pa); pa ^= 1;
         tc_fence_after();
-        issue_g1(0, k0); tc_commit(bar_h0);
-        if (NCH > 1) { issue_g1(1, k0 + 1); tc_commit(bar_h0 + 8); }
+        issue_g1(0, k0); tc_commit_if(issue, bar_h0);
+        if (NCH > 1) { issue_g1(1, k0 + 1); tc_commit_if(issue, bar_h0 + 8); }
         for (int c = 0; c < NCH; ++c) {
           const int b = c & 1;
           mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
           tc_fence_after();
           issue_g2(c, k0 + c);
-          tc_commit(bar_xe + 8 * ((k0 + c) % TCS_NSTAGE));   // stage free once GEMM2(c) has read it
-          if (c + 2 < NCH) { issue_g1(c + 2, k0 + c + 2); tc_commit(bar_h0 + 8 * b); }
-          if (c == NCH - 1) tc_commit(bar_g);
+          tc_commit_if(issue, bar_xe + 8 * ((k0 + c) % TCS_NSTAGE));   // stage free once GEMM2(c) has read it
+          if (c + 2 < NCH) { issue_g1(c + 2, k0 + c + 2); tc_commit_if(issue, bar_h0 + 8 * b); }
+          if (c == NCH - 1) tc_commit_if(issue, bar_g);
         }
         cnt += NCH;
       }
@@ -202,6 +238,10 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const unsigned int gchain = p.chain_offset + (unsigned int)chain;
     uint32_t ph[2] = {0, 0}, pg = 0, kcnt = 0;
     const float a0 = pa_s[0], b0 = pb_s[0];
+    // coordinate 0 (overall_log_scale) is replicated in all four workers of a chain.  Each keeps its own copy of
+    // the current z / gradient in registers (all four take identical accept decisions), so no worker ever reads
+    // what another worker of the chain writes to the global workspace.
+    float z0_cur = Z(0), g0_cur = G(0), g0_prop = 0.f;
     uint8_t* a_row1 = smem + K::A1 + (r >> 3) * K::SG + (r & 7) * 16 + w * (FPW / 8) * K::SF;
     uint8_t* a_row2 = smem + K::A2 + (r >> 3) * K::SG + (r & 7) * 16 + w * (FPW / 8) * K::SF;
     const float NLOG2E = -1.4426950408889634f;
@@ -233,11 +273,22 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         for (int i = 0; i < NLOC; ++i)
           if (owned(i)) xs[i * TC_WORKERS] = mom[dof(i)];
       } else {
-        for (int seg = 0; seg < 3; ++seg) {
-          const int d_lo = seg == 0 ? 0 : (seg == 1 ? 1 + FPW * w : 1 + F + FPW * w);
-          const int d_hi = seg == 0 ? 1 : d_lo + nf;
-          const int i_lo = seg == 0 ? 0 : (seg == 1 ? 1 : 1 + FPW);
-          for (int j = d_lo >> 2; 4 * j < d_hi; ++j) {
+        // Philox block j holds coordinates 4j .. 4j+3; my ranges are d = 0, [1+FPW w, ..+nf), [1+F+FPW w, ..+nf).
+        // All blocks are generated unconditionally in unrolled loops (independent chains the scheduler can
+        // interleave); only the stores are predicated.
+        {
+          float n4[4];
+          philox_normal4_fast(p.seed, gchain, (unsigned int)tg, 0u, n4);
+          xs[0] = n4[0];
+        }
+#pragma unroll
+        for (int seg = 1; seg < 3; ++seg) {
+          const int d_lo = seg == 1 ? 1 + FPW * w : 1 + F + FPW * w;
+          const int d_hi = d_lo + nf;
+          const int i_lo = seg == 1 ? 1 : 1 + FPW;
+#pragma unroll
+          for (int jj = 0; jj < FPW / 4 + 1; ++jj) {
+            const int j = (d_lo >> 2) + jj;
             float n4[4];
             philox_normal4_fast(p.seed, gchain, (unsigned int)tg, (unsigned int)j, n4);
 #pragma unroll
@@ -249,16 +300,27 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
       }
       float ke0 = 0.f, ke1 = 0.f, ke0_tot = 0.f, ke1_tot = 0.f;
+      {
+        // all global loads first: with the loads inside the update loop every iteration waited a full L2
+        // round trip (load -> FMA -> store -> next load cannot be hoisted above the store)
+        float gq[NLOC], zq[NLOC];
 #pragma unroll
-      for (int i = 0; i < NLOC; ++i) {
-        if (owned(i)) {
-          const int d = dof(i);
-          float vi = xs[i * TC_WORKERS];
-          if (i > 0 || w == 0) ke0 = fmaf(vi, vi, ke0);
-          const float e = pe_s[d] * mult;
-          vi = vi + 0.5f * e * G(d);
-          vset(i, vi);
-          xs[i * TC_WORKERS] = Z(d) + e * vi;
+        for (int i = 0; i < NLOC; ++i) {
+          gq[i] = 0.f; zq[i] = 0.f;
+          if (i == 0) { gq[0] = g0_cur; zq[0] = z0_cur; }
+          else if (owned(i)) { const int d = dof(i); gq[i] = G(d); zq[i] = Z(d); }
+        }
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i) {
+          if (owned(i)) {
+            const int d = dof(i);
+            float vi = xs[i * TC_WORKERS];
+            if (i > 0 || w == 0) ke0 = fmaf(vi, vi, ke0);
+            const float e = pe_s[d] * mult;
+            vi = vi + 0.5f * e * gq[i];
+            vset(i, vi);
+            xs[i * TC_WORKERS] = zq[i] + e * vi;
+          }
         }
       }
       float lpx = 0.f;
@@ -303,62 +365,15 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           TC_LD32(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, hv);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const float* sy = reinterpret_cast<const float*>(smem + K::RING + (kcnt % TCS_NSTAGE) * K::STAGE + 2 * K::XCHUNK);
-          const int n0 = c * TC_CHUNK + 32 * w;
           uint32_t r1[16], r2[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 y4 = *reinterpret_cast<const float4*>(sy + 32 * w + i);
             const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
             float rr[4];
-#if TCS_RCP_SHARE
-            // four sigmoids share ONE MUFU.RCP (Montgomery's trick): 1/d_k = (1 / prod d) * prod_{j != k} d_j.
-            // The epilogue is bound by the XU (MUFU) pipe -- 2 MUFU per element -- so this trades 0.75 MUFU
-            // per element for 2.25 FMULs.  h is clamped at 30 (sigmoid < 1e-9 there) so the product of four
-            // denominators stays below 2^124.
-            float dq[4], sg4[4], hq4[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              hq4[q] = __uint_as_float(hv[i + q]);      // = -log2(e) * eta
-              dq[q] = 1.0f + ex2_approx(fminf(hq4[q], 30.f));
-            }
-            {
-              const float p01 = dq[0] * dq[1], p23 = dq[2] * dq[3];
-              const float inv = rcp_approx(p01 * p23);
-              const float i01 = inv * p23, i23 = inv * p01;
-              sg4[0] = i01 * dq[1]; sg4[1] = i01 * dq[0]; sg4[2] = i23 * dq[3]; sg4[3] = i23 * dq[2];
-            }
-#endif
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#if TCS_RCP_SHARE
-              const float hq = hq4[q];
-              const float sg = sg4[q];
-#else
-              const float hq = __uint_as_float(hv[i + q]);      // = -log2(e) * eta
-#if TCS_EXPERIMENT == 2
-              const float sg = 0.5f * ex2_approx(hq);            // timing experiment: no MUFU.RCP
-#elif TCS_EXPERIMENT == 3
-              const float sg = rcp_approx(1.0f + hq * hq);       // timing experiment: no MUFU.EX2
-#else
-              const float sg = rcp_approx(1.0f + ex2_approx(hq));
-#endif
-#endif
-              rr[q] = yy[q] - sg;
-              // log-likelihood (last step only): sum_n [y eta - softplus(eta)] = beta . c + sum_n ln sigmoid(eta_n)
-              // with c = X^T (y - 1) precomputed; only the log-sigmoid sum is per observation.  Padded rows have
-              // eta = 0, i.e. lg2(1/2) = -1 each: corrected by a constant below.
-              if (last) lik += lg2_approx(sg);
-            }
-#if TCS_EXPERIMENT == 1
-            {  // timing experiment: head only (no tail split)
-              const __half2 h01 = __floats2half2_rn(rr[0], rr[1]), h23 = __floats2half2_rn(rr[2], rr[3]);
-              r1[i / 2] = *reinterpret_cast<const uint32_t*>(&h01); r1[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
-              r2[i / 2] = 0; r2[i / 2 + 1] = 0;
-            }
-#else
+            tcs_sigmoid4<K::RCP_SHARE>(&hv[i], yy, rr, last, lik);
             split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
             split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
-#endif
           }
           TC_ST16(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, r1);
           TC_ST16(tmem + lane_off + K::COL_R2 + b * 64 + 16 * w, r2);
@@ -373,6 +388,15 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         else { TC_LD16(tmem + lane_off + K::COL_G + 16 * w, gv); }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float acc0 = 0.f, lps = 0.f, lin = 0.f;
+        // NF = 64: fetch all momenta before the update loop (inside it every iteration would wait an L2 round trip)
+        float vq[V_IN_REGS ? 1 : 2 * FPW];
+        if constexpr (!V_IN_REGS) {
+#pragma unroll
+          for (int k = 0; k < FPW; ++k) {
+            vq[k] = 0.f; vq[FPW + k] = 0.f;
+            if (k < nf) { vq[k] = VG(dof(1 + k)); vq[FPW + k] = VG(dof(1 + FPW + k)); }
+          }
+        }
 #pragma unroll
         for (int k = 0; k < FPW; ++k) {
           if (k < nf) {
@@ -396,8 +420,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             else site_rev(ss, lb, s0.x, af, 1.f, gs, mb2, lb2, ab2);
             acc0 += mb2;
             const float es = pe_s[1 + f] * mult, eb = pe_s[1 + F + f] * mult;
-            float vs = vget(1 + k) + 0.5f * es * gs;
-            float vb = vget(1 + FPW + k) + 0.5f * eb * gb;
+            float vs = (V_IN_REGS ? vget(1 + k) : vq[V_IN_REGS ? 0 : k]) + 0.5f * es * gs;
+            float vb = (V_IN_REGS ? vget(1 + FPW + k) : vq[V_IN_REGS ? 0 : FPW + k]) + 0.5f * eb * gb;
             if (last) {
               ke1 = fmaf(vs, vs, ke1);
               ke1 = fmaf(vb, vb, ke1);
@@ -434,7 +458,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           float v0 = v0r + 0.5f * e * g0;
           if (last) {
             ke1_tot = fmaf(v0, v0, ke1_tot);   // coordinate 0 is replicated: every quarter adds it itself
-            if (w == 0) { ws.gx[co] = g0; ws.xcx[co] = s0.x; }
+            g0_prop = g0;
+            if (w == 0) ws.xcx[co] = s0.x;
           } else {
             v0 = v0 + 0.5f * e * g0;
             xs[0] = xs[0] + e * v0;
@@ -450,13 +475,28 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
       const bool acc = log_u < log_alpha;
       if (acc) {
+        float gq[NLOC], xq[NLOC];   // loads first, then stores (see the first kick)
+#pragma unroll
+        for (int i = 0; i < NLOC; ++i) {
+          gq[i] = 0.f; xq[i] = 0.f;
+          if (i == 0) {
+            gq[0] = g0_prop;
+            if (w == 0) xq[0] = ws.xcx[co];
+          } else if (owned(i)) {
+            const int d = dof(i);
+            gq[i] = ws.gx[co + (size_t)d * ws.sd];
+            xq[i] = ws.xcx[co + (size_t)d * ws.sd];
+          }
+        }
+        z0_cur = xs[0];
+        g0_cur = g0_prop;
 #pragma unroll
         for (int i = 0; i < NLOC; ++i)
           if (owned(i) && (i > 0 || w == 0)) {
             const int d = dof(i);
             Z(d) = xs[i * TC_WORKERS];
-            G(d) = ws.gx[co + (size_t)d * ws.sd];
-            XC(d) = ws.xcx[co + (size_t)d * ws.sd];
+            G(d) = gq[i];
+            XC(d) = xq[i];
           }
         lp_cur = lpx;
         ++nacc;
@@ -475,12 +515,22 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         const int s = since / p.stride;
         if (s < p.S) {
           const size_t o = ((size_t)s * p.C + chain) * D;
+          float xq[NLOC], zq[NLOC];
+#pragma unroll
+          for (int i = 0; i < NLOC; ++i) {
+            xq[i] = 0.f; zq[i] = 0.f;
+            if (owned(i) && (i > 0 || w == 0)) {
+              const int d = dof(i);
+              if (p.samples) xq[i] = XC(d);
+              if (p.samples_orig) zq[i] = Z(d);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < NLOC; ++i)
             if (owned(i) && (i > 0 || w == 0)) {
               const int d = dof(i);
-              if (p.samples) p.samples[o + d] = XC(d);
-              if (p.samples_orig) p.samples_orig[o + d] = Z(d);
+              if (p.samples) p.samples[o + d] = xq[i];
+              if (p.samples_orig) p.samples_orig[o + d] = zq[i];
             }
           if (p.is_accepted && w == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
         }
@@ -555,8 +605,17 @@ static inline cudaError_t tcs_launch(int nf_pad, dim3 grid, cudaStream_t st, con
   return cudaGetLastError();
 }
 
+static inline int tcd_skew() {
+  static const int v = [] { const char* e = getenv("ARP_TCD_SKEW"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+template <bool GAMMA>
+static inline cudaError_t tcd_launch(dim3 grid, cudaStream_t st, const TcsParams& tp, const HmcWs& ws, const HmcArgs& p);
+
+// dual = true: the dual-tile kernel of arp_german_tcd.cuh (F <= 32 only)
 static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt, const HmcArgs& p, const real* z0,
-                                 cudaStream_t st, bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
+                                 cudaStream_t st, bool dual, bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
                                  std::atomic<long long>* launches, std::string* err) {
 #define TCS_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(_e); return 1; } } while (0)
   const long long C = p.C;
@@ -586,8 +645,9 @@ static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt,
   }
   launches->fetch_add(1);
   TCS_CUDA(cudaGetLastError());
-  TcsParams tp{tc.img.as<uint8_t>(), tc.cvec.as<float>(), tc.N, tc.F, tc.nchunk};
-  TCS_CUDA(gamma ? tcs_launch<true>(tc.nf_pad, grid, st, tp, ws, p) : tcs_launch<false>(tc.nf_pad, grid, st, tp, ws, p));
+  TcsParams tp{tc.img.as<uint8_t>(), tc.cvec.as<float>(), tc.N, tc.F, tc.nchunk, tcd_skew()};
+  if (dual && tc.nf_pad == 32) TCS_CUDA(gamma ? tcd_launch<true>(grid, st, tp, ws, p) : tcd_launch<false>(grid, st, tp, ws, p));
+  else TCS_CUDA(gamma ? tcs_launch<true>(tc.nf_pad, grid, st, tp, ws, p) : tcs_launch<false>(tc.nf_pad, grid, st, tp, ws, p));
   launches->fetch_add(1);
   if (want_final) {
     TCS_CUDA(dfz->alloc((size_t)C * p.D * sizeof(real)));

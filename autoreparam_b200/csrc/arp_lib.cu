@@ -19,6 +19,7 @@
 #ifndef ARP_FP64
 #include "arp_german_tc.cuh"
 #include "arp_german_tcs.cuh"
+#include "arp_german_tcd.cuh"
 #endif
 
 using namespace arp;
@@ -314,14 +315,17 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
   const bool tc_res = m->dev.kind == MODEL_GERMAN_LOGNORMAL && m->tc.ready();   // resident-X kernel
   const bool tc_str = (m->dev.kind == MODEL_GERMAN_LOGNORMAL || m->dev.kind == MODEL_GERMAN_GAMMA) && m->tcs.ready();
   const bool tc_ok = tc_res || tc_str;
-  if ((cfg->engine == 2 || cfg->engine == 3) && !tc_ok)
+  if ((cfg->engine == 2 || cfg->engine == 3 || cfg->engine == 4) && !tc_ok)
     return fail("arp_hmc_run: the tcgen05 engine needs a german_credit model with at most 64 features");
-  if (cfg->engine == 3 && !tc_str) return fail("arp_hmc_run: streaming tcgen05 engine not available for this model");
-  const bool use_tc = tc_ok && (cfg->engine == 2 || cfg->engine == 3 || (cfg->engine == 0 && german_tc_auto(C)));
+  if ((cfg->engine == 3 || cfg->engine == 4) && !tc_str)
+    return fail("arp_hmc_run: streaming tcgen05 engine not available for this model");
+  if (cfg->engine == 4 && m->tcs.nf_pad != 32) return fail("arp_hmc_run: the dual-tile tcgen05 engine needs at most 32 features");
+  const bool use_tc = tc_ok && (cfg->engine >= 2 || (cfg->engine == 0 && german_tc_auto(C)));
+  const bool use_dual = cfg->engine == 4;
   // auto prefers the streaming kernel: it measures ~2 % faster than the resident one and has no size limits
   const bool use_stream = use_tc && tc_str && (cfg->engine != 2 || !tc_res);
 #else
-  if (cfg->engine == 2) return fail("arp_hmc_run: the fp64 check build has no tcgen05 engine");
+  if (cfg->engine >= 2) return fail("arp_hmc_run: the fp64 check build has no tcgen05 engine");
   const bool use_tc = false;
 #endif
 
@@ -362,7 +366,7 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
 #ifndef ARP_FP64
   if (use_tc) {
     int rc = use_stream
-                 ? german_tcs_hmc(m->tcs, m->dev, m->fp, p, z0, st, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc,
+                 ? german_tcs_hmc(m->tcs, m->dev, m->fp, p, z0, st, use_dual, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc,
                                   &g_launches, &g_last_error)
                  : german_tc_hmc(m->tc, m->dev, p, z0, st, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc, &g_launches,
                                  &g_last_error);

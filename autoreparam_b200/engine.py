@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib
 
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_STREAM = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_STREAM, ENGINE_TCGEN05_DUAL = 0, 1, 2, 3, 4
 
 
 def _is_torch(x):

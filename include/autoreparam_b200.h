@@ -102,7 +102,8 @@ typedef struct arp_hmc_config {
   double target_accept_prob;    /* 0.75 [TFP default] */
   int32_t lanes_per_chain;      /* 0 = auto; 1,8,32 = force */
   int32_t engine;               /* 0 = auto, 1 = generic FP32 SIMT kernels, 2 = tcgen05 (german credit), 3 = tcgen05 with
-                                   the design matrix streamed from L2 (up to 64 features, any N) */
+                                   the design matrix streamed from L2 (up to 64 features, any N), 4 = streamed, two 64-chain
+                                   tiles per CTA out of phase (up to 32 features) */
 } arp_hmc_config;
 
 /* Buffers of one HMC run.  `mem` applies to every non-NULL pointer here.

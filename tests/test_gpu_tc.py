@@ -168,3 +168,67 @@ def test_tcs_matches_simt_engine_many_chains(model):
     ok = same.all(axis=0)
     err = common.rel_err(o2["samples"][:, ok].reshape(-1, D), o1["samples"][:, ok].reshape(-1, D))
     assert np.median(err) < 1e-5 and np.quantile(err, 0.99) < 1e-2, (np.median(err), np.quantile(err, 0.99))
+
+
+# --------------------------------------------------------------------------------------------
+# dual-tile variant (two 64-chain M = 64 tiles per CTA, half-warp TMEM accesses): F <= 32
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", ["CP", "NCP", "VIP_ab"])
+def test_tcd_single_leapfrog_gradient(method):
+    C = 128 + 70      # both tiles of CTA 0, tile 0 and part of tile 1 of CTA 1
+    mc, raw, D, a, b, z0 = _case_model("german_synth", method, C, seed=51)
+    _, g_ref = O.log_joint_and_grad(MODEL, raw, z0, a, b)
+    eps = 2.0 ** -6
+    out = engine.hmc_run(mc, z0, np.full(D, eps), a, b, num_leapfrog_steps=1, num_results=1, num_burnin_steps=0,
+                         num_adaptation_steps=0, ext_momenta=np.zeros((1, C, D)), ext_log_u=np.full((1, C), -1e30),
+                         want_orig=True, engine=engine.ENGINE_TCGEN05_DUAL)
+    assert out["is_accepted"].all()
+    g_tc = (out["samples_orig"][0].astype(np.float64) - z0) / (0.5 * eps * eps)
+    err = np.abs(g_tc - g_ref).max(axis=1)
+    allow = 1e-5 * np.maximum(np.abs(g_ref).max(axis=1), 1.0) + 2.0 ** -23 * np.abs(z0).max() / (0.5 * eps * eps)
+    assert (err < allow).all(), (err, allow)
+
+
+def test_tcd_fixed_momenta_trajectory():
+    C, L, S, burn, adapt = 70, 3, 3, 2, 4
+    mc, raw, D, a, b, z0 = _case_model("german_synth", "VIP_a", C, seed=52)
+    T = O.num_transitions(S, burn)
+    rng = np.random.default_rng(9)
+    mom = rng.standard_normal((T, C, D)).astype(np.float32).astype(np.float64)
+    lu = np.log(rng.uniform(size=(T, C))).astype(np.float32).astype(np.float64)
+    eps0 = (np.full(D, 0.01) * rng.uniform(0.5, 1.5, D)).astype(np.float32).astype(np.float64)
+    sel = [0, 15, 16, 63, 64, 69]     # oracle on a few chains of both tiles
+    ref = O.hmc_chain(MODEL, raw, z0[sel], eps0, L, S, burn, adapt, a, b, momenta=mom[:, sel], log_u=lu[:, sel])
+    out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn,
+                         num_adaptation_steps=adapt, ext_momenta=mom, ext_log_u=lu, want_orig=True,
+                         engine=engine.ENGINE_TCGEN05_DUAL)
+    assert (out["is_accepted"][:, sel].astype(bool) == ref["is_accepted"]).all()
+    err = common.rel_err(out["samples"][:, sel].reshape(-1, D), ref["samples_centered"].reshape(-1, D)).max()
+    assert err < 2e-3, err
+    assert common.rel_err(out["final_z"][sel], ref["z"]).max() < 2e-3
+
+
+@pytest.mark.parametrize("model", ["german_synth", "german_credit_gammascale_f24"])
+def test_tcd_identical_to_streaming_engine(model):
+    """Per chain the dual-tile kernel does the same arithmetic in the same order as the single-tile
+    streaming kernel: results must be identical (Philox momenta, several CTAs, ragged tail)."""
+    C, L, S, burn, adapt = 128 * 3 + 37, 4, 3, 4, 5
+    if model == "german_synth":
+        mc, raw, D, a, b, z0 = _case_model(model, "NCP", C, seed=53)
+    else:   # gamma-scale prior on the synthetic 1000 x 25 design matrix
+        from autoreparam_b200 import models
+        base = common.raw_data("german_synth")
+        mc = models.from_data("german_credit_gammascale", base)
+        D = mc.num_coords
+        a, b = common.ab_for("NCP", D)
+        z0 = common.random_states("german_credit_gammascale", D, C, seed=53, scale=0.3).astype(np.float32).astype(np.float64)
+    eps0 = np.full(D, 0.002 if "gamma" in model else 0.01)
+    kw = dict(num_leapfrog_steps=L, num_results=S, num_burnin_steps=burn, num_adaptation_steps=adapt, seed=78,
+              chain_offset=5, want_orig=True)
+    o1 = engine.hmc_run(mc, z0, eps0, a, b, engine=engine.ENGINE_TCGEN05_STREAM, **kw)
+    o2 = engine.hmc_run(mc, z0, eps0, a, b, engine=engine.ENGINE_TCGEN05_DUAL, **kw)
+    assert (o1["is_accepted"] == o2["is_accepted"]).all()
+    assert np.array_equal(o1["samples"], o2["samples"])
+    assert np.array_equal(o1["final_z"], o2["final_z"])
+    assert np.array_equal(o1["step_mult"], o2["step_mult"])
+    assert o1["is_accepted"].mean() > 0.2
