@@ -30,7 +30,7 @@ struct Tcd {
   static constexpr int NF = 32;
   static constexpr uint32_t SF = 128, SG = 512;
   static constexpr uint32_t XCHUNK = (TC_CHUNK / 8) * SG;          // 8192
-  static constexpr uint32_t STAGE = 2 * XCHUNK + TC_CHUNK * 4;     // head | tail | y
+  static constexpr uint32_t STAGE = 2 * XCHUNK;                    // head | tail of the t-scaled rows
   static constexpr uint32_t AIMG = (TCD_TILE / 8) * SG;            // 4096 per part per tile
   static constexpr int FPW = 8, NLOC = 17;
   static constexpr uint32_t RING = 0;                               // [2 tiles][NSTAGE][STAGE]
@@ -95,7 +95,6 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       par[(2 * NF + 4) + i] = p.b[i];
       par[2 * (2 * NF + 4) + i] = p.eps0[i];
     }
-    for (int i = tid; i < tp.F; i += TCD_THREADS) par[3 * (2 * NF + 4) + i] = tp.cvec[i];
   }
   if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
@@ -210,7 +209,10 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const int chain = blockIdx.x * TC_CHAINS + r;
     const bool valid = chain < p.C;
     const int D = p.D, F = tp.F;
-    const int nf = max(0, min(FPW, F - FPW * w));
+    // features are dealt to the four workers of a chain in contiguous, balanced ranges (25 -> 7, 6, 6, 6); worker w
+    // owns K-slots [FPW w, FPW w + nf) of the A operand / X images and the matching columns of G
+    const int nf = F / TC_NQ + (w < F % TC_NQ ? 1 : 0);
+    const int fstart = w * (F / TC_NQ) + min(w, F % TC_NQ);
     const uint32_t tq = tmem + ((uint32_t)(32 * qk) << 16);   // lane base of this warp's 16 rows
     const size_t co = (size_t)chain * ws.sc;
     Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
@@ -218,11 +220,10 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const float* pa_s = reinterpret_cast<const float*>(smem + K::PAR);
     const float* pb_s = pa_s + (2 * NF + 4);
     const float* pe_s = pb_s + (2 * NF + 4);
-    const float* pc_s = pe_s + (2 * NF + 4);
     float lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
     int nacc = ws.nacc[chain];
     const unsigned int gchain = p.chain_offset + (unsigned int)chain;
-    uint32_t ph[2] = {0, 0}, pg = 0, kcnt = 0;
+    uint32_t ph[2] = {0, 0}, pg = 0;
     const float a0 = pa_s[0], b0 = pb_s[0];
     // coordinate 0 (overall_log_scale) is replicated in all four workers of a chain.  Each keeps its own copy of
     // the current z / gradient in registers (all four take identical accept decisions), so no worker ever reads
@@ -230,8 +231,8 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     float z0_cur = Z(0), g0_cur = G(0), g0_prop = 0.f;
     uint8_t* a_row1 = smem + K::A1 + tile * K::AIMG + (r64 >> 3) * K::SG + (r64 & 7) * 16 + w * K::SF;
     uint8_t* a_row2 = smem + K::A2 + tile * K::AIMG + (r64 >> 3) * K::SG + (r64 & 7) * 16 + w * K::SF;
-    const float NLOG2E = -1.4426950408889634f;
-    auto dof = [&](int i) { return i == 0 ? 0 : (i <= FPW ? FPW * w + i : F + FPW * w + i - FPW); };
+    const float LOG2E = 1.4426950408889634f;
+    auto dof = [&](int i) { return i == 0 ? 0 : (i <= FPW ? fstart + i : F + fstart + i - FPW); };
     auto owned = [&](int i) { return i == 0 || (i <= FPW ? (i - 1) < nf : (i - 1 - FPW) < nf); };
     uint32_t par = 0;
     auto xch_at = [&](int slot, int q) -> float& { return xch[((par * 4 + slot) * TC_NQ + q) * TC_CHAINS + r]; };
@@ -267,7 +268,7 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
 #pragma unroll
         for (int seg = 1; seg < 3; ++seg) {
-          const int d_lo = seg == 1 ? 1 + FPW * w : 1 + F + FPW * w;
+          const int d_lo = seg == 1 ? 1 + fstart : 1 + F + fstart;
           const int d_hi = d_lo + nf;
           const int i_lo = seg == 1 ? 1 : 1 + FPW;
 #pragma unroll
@@ -309,6 +310,9 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
       }
       float lpx = 0.f;
+      // a coefficient that leaves the fp16 range of the A operand (only on wildly diverging trajectories) would make
+      // GEMM1 return inf / NaN and the clamp below would swallow it: such a trajectory is rejected outright
+      bool ovf = false;
       TCD_TICK(0)   // Philox + first kick
       for (int l = 0; l < p.L; ++l) {
         const bool last = (l == p.L - 1);
@@ -320,13 +324,14 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           for (int k = 0; k < 8; ++k) {
             be[k] = 0.f;
             if (k < nf) {
-              const int f = FPW * w + k;
+              const int f = fstart + k;
               float dummy = 0.f;
               float ls;
               if (GAMMA) ls = s0.x + xs[(1 + k) * TC_WORKERS];
               else ls = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy).x;
               const Site sb = site_fwd_fast(xs[(1 + FPW + k) * TC_WORKERS], 0.f, ls, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
-              be[k] = sb.x * NLOG2E;   // GEMM1 then yields -log2(e) * eta
+              be[k] = sb.x * LOG2E;   // GEMM1 then yields log2(e) t eta
+              ovf |= !(fabsf(be[k]) < 60000.f);   // outside the fp16 range of the A operand (or NaN)
             }
           }
           uint4 hi, lo;
@@ -342,7 +347,7 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         mbar_arrive(bar_a);
         TCD_TICK(1)   // site forward + A operand
         float lik = 0.f;
-        for (int c = 0; c < NCH; ++c, ++kcnt) {
+        for (int c = 0; c < NCH; ++c) {
           const int b = c & 1;
           mbar_wait(bar_h0 + 8 * b, ph[b]); ph[b] ^= 1;
           TCD_TICK(2)   // wait for H
@@ -351,18 +356,9 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           TCD_LD32(tq + K::COL_H + b * TC_CHUNK + 64 * pp, hv);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           TCD_TICK(3)   // tcgen05.ld
-          const float* sy = reinterpret_cast<const float*>(smem + K::RING + (tile * TCS_NSTAGE + kcnt % TCS_NSTAGE) * K::STAGE +
-                                                           2 * K::XCHUNK);
           uint32_t r1[16], r2[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 y4 = *reinterpret_cast<const float4*>(sy + 32 * w + i);
-            const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
-            float rr[4];
-            tcs_sigmoid4<true>(&hv[i], yy, rr, last, lik);
-            split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
-            split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
-          }
+          if (last) tcs_epilogue32<true, true>(hv, r1, r2, lik);
+          else tcs_epilogue32<true, false>(hv, r1, r2, lik);
           TCD_ST16(tq + K::COL_H + b * TC_CHUNK + 64 * pp, 32, r1);   // packed head over the first half of each worker's H block
           TCD_ST16(tq + K::COL_R2 + b * 64 + 32 * pp, 16, r2);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -376,11 +372,11 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         uint32_t gv[FPW];
         TCD_LD8(tq + K::COL_G + 16 * pp, gv);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float acc0 = 0.f, lps = 0.f, lin = 0.f;
+        float acc0 = 0.f, lps = 0.f;
 #pragma unroll
         for (int k = 0; k < FPW; ++k) {
           if (k < nf) {
-            const int f = FPW * w + k;
+            const int f = fstart + k;
             const float af = pa_s[1 + f], ab_ = pa_s[1 + F + f], bb_ = pb_s[1 + F + f];
             const float xs_s = xs[(1 + k) * TC_WORKERS], xs_b = xs[(1 + FPW + k) * TC_WORKERS];
             Site ss;
@@ -391,7 +387,6 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               ss = site_fwd_unit(xs_s, s0.x, af, lps);
             }
             const Site sb = site_fwd_fast(xs_b, 0.f, GAMMA ? s0.x + xs_s : ss.x, ab_, bb_, lps);
-            lin = fmaf(sb.x, pc_s[f], lin);
             float gb, mb, lb, ab;
             site_rev(sb, __uint_as_float(gv[k]), 0.f, ab_, bb_, gb, mb, lb, ab);
             float gs, mb2, lb2, ab2;
@@ -418,10 +413,9 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
         if (last) {
           lik = 0.69314718055994531f * (lik + (w == 0 ? (float)(NCH * TC_CHUNK - tp.N) : 0.f));
-          lik += lin;
         }
         xch_at(0, w) = acc0;
-        xch_at(1, w) = lik + lps;
+        xch_at(1, w) = ovf ? -INFINITY : lik + lps;
         xch_at(2, w) = ke0;
         xch_at(3, w) = ke1;
         TCD_TICK(6)   // G load + site reverse + kicks

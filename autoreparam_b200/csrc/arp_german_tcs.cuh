@@ -16,6 +16,14 @@
 namespace arp {
 
 #define TCS_NSTAGE 3
+#ifdef TCS_PARK
+#define TCS_ROLE_WAIT mbar_wait_parked   // measured: no gain (-0.5 %)
+#else
+#define TCS_ROLE_WAIT mbar_wait
+#endif
+#ifndef TCS_PROFILE
+#define TCS_PROFILE 0   // 1: one lane per worker warp accumulates clock() per phase and printf()s it (timing study only)
+#endif
 #define TCS_THREADS (TC_WORKERS + 64)
 #define TCS_MMA_WARP (TC_WORKERS / 32)
 #define TCS_PROD_WARP (TC_WORKERS / 32 + 1)
@@ -26,7 +34,7 @@ struct Tcs {
   static constexpr uint32_t SF = 128;                     // bytes between feature chunks
   static constexpr uint32_t SG = NFC * 128;               // bytes between 8-row groups
   static constexpr uint32_t XCHUNK = (TC_CHUNK / 8) * SG; // one part of one 128-observation chunk
-  static constexpr uint32_t STAGE = 2 * XCHUNK + TC_CHUNK * 4;   // head | tail | y
+  static constexpr uint32_t STAGE = 2 * XCHUNK;                  // head | tail of the t-scaled rows
   static constexpr uint32_t AIMG = (TC_CHAINS / 8) * SG;
   static constexpr int FPW = NF / TC_NQ;                  // features per worker
   static constexpr int NLOC = 1 + 2 * FPW;
@@ -38,7 +46,7 @@ struct Tcs {
   static constexpr uint32_t XCH = A2 + AIMG;                        // float[2][4][TC_NQ][128] (double-buffered by step parity)
   static constexpr uint32_t XS = XCH + 2 * 4 * TC_NQ * TC_CHAINS * 4;   // float[NLOC][512]
   static constexpr uint32_t PAR = XS + NLOC * TC_WORKERS * 4;       // float[3][2 NF + 4]
-  static constexpr uint32_t BAR = PAR + 4 * (2 * NF + 4) * 4;       // 6 + 2 * NSTAGE mbarriers (PAR: a, b, eps0, c)
+  static constexpr uint32_t BAR = PAR + 4 * (2 * NF + 4) * 4;       // 6 + 2 * NSTAGE mbarriers (PAR: a, b, eps0)
   static constexpr uint32_t TMEM_PTR = BAR + 16 * 8;
   static constexpr uint32_t BYTES = TMEM_PTR + 16;
   // TMEM columns
@@ -50,7 +58,6 @@ struct Tcs {
 
 struct TcsParams {
   const uint8_t* img;   // nchunk stage images
-  const float* cvec;    // [F] c_f = sum_n X[n,f] (y_n - 1): the part of the log-likelihood that is linear in beta
   int N, F, nchunk;
   int skew;             // dual-tile kernel: clocks by which tile 1 starts late
 };
@@ -63,48 +70,82 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// Four likelihood elements: r = y - sigmoid(eta) from h = -log2(e) * eta (the GEMM1 output), and on the last
-// leapfrog step the running sum of log2 sigmoid(eta).
-// SHARE: the four sigmoids share ONE MUFU.RCP (Montgomery's trick: 1/d_k = (1 / prod d) * prod_{j != k} d_j), i.e.
-// 1.25 MUFU + 2.25 FMUL per element instead of 2 MUFU.  The epilogue is bound by the XU pipe (16 MUFU lanes / clk /
-// SM), so for F <= 32 this is +6.6 % end to end; for F = 64 the extra registers cost more than it saves.  h is
-// clamped at 30 (sigmoid < 1e-9 there) so the product of four denominators stays below 2^124; beyond the clamp
-// log2 sigmoid = -h to fp32 accuracy.
-template <bool SHARE>
-__device__ __forceinline__ void tcs_sigmoid4(const uint32_t* hv, const float* yy, float* rr, bool last, float& lik) {
-  if constexpr (SHARE) {
-    float hq[4], dq[4];
+// Likelihood epilogue of one worker: 32 elements of one chunk.  The chunk images hold the rows of X scaled by
+// t_n = 2 y_n - 1 (exact in fp16) and the A operand is +log2(e) beta, so GEMM1 yields h_n = log2(e) t_n eta_n and
+//   q_n = sigmoid(-t_n eta_n) = 1 / (1 + 2^h_n),   y_n - sigmoid(eta_n) = t_n q_n,
+// i.e. GEMM2 over the SAME scaled rows needs q itself: X^T (y - sigmoid(eta)) = (t X)^T q.  No y in the epilogue.
+// log-likelihood (last leapfrog step only): ln sigmoid(t eta) = ln(1 - q) = ln2 (h + log2 q).
+// SHARE: four sigmoids share ONE MUFU.RCP (Montgomery's trick: 1/d_k = (1 / prod d) * prod_{j != k} d_j), i.e.
+// 1.25 MUFU + 2.25 FMUL per element instead of 2 MUFU.  h is clamped at 30 (q < 1e-9 there) so the product of four
+// denominators stays below 2^124; with m = min(h, 30) the log-likelihood term is m + log2 q(m) (= 0 to fp32 accuracy
+// beyond the clamp, as it should).
+// The eight groups of four elements run through a three-stage software pipeline (A: clamp + EX2, B: denominators
+// + shared RCP, C: sigmoids + fp16 head / tail split), group g + 3 in A while g + 2 is in B and g in C: every MUFU
+// result is consumed ~40 instructions after its issue, and the MUFU ops (the binding pipe: 8 clk per warp
+// instruction per SM sub-partition, profiles/micro/pipes.cu) are spread evenly over the chunk instead of arriving
+// as one burst per warp.  (Written group by group, ptxas put each MUFU.RCP directly in front of its consumers:
+// 0.5 IPC inside the epilogue with four worker warps per scheduler, measured with clock().)
+// (A clamp-free fast path -- one chained FSETP per group on the product of the denominators instead of the 32
+// half-rate FMNMX, with a clamped cold path -- was measured 4 % SLOWER end to end and is not kept.)
+template <bool SHARE, bool LAST>
+__device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1, uint32_t* r2, float& lik) {
+  float m[8][4], e[8][4], p01[8], p23[8], inv[8];
+  auto stage_a = [&](int g) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      hq[q] = __uint_as_float(hv[q]);
-      dq[q] = 1.0f + ex2_approx(fminf(hq[q], 30.f));
+      m[g][q] = fminf(__uint_as_float(hv[4 * g + q]), 30.f);
+      e[g][q] = ex2_approx(m[g][q]);
     }
-    const float p01 = dq[0] * dq[1], p23 = dq[2] * dq[3];
-    const float inv = rcp_approx(p01 * p23);
-    const float i01 = inv * p23, i23 = inv * p01;
-    const float sg[4] = {i01 * dq[1], i01 * dq[0], i23 * dq[3], i23 * dq[2]};
+  };
+  auto stage_b = [&](int g) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      rr[q] = yy[q] - sg[q];
-      if (last) lik += hq[q] > 30.f ? -hq[q] : lg2_approx(sg[q]);
-    }
-  } else {
+    for (int q = 0; q < 4; ++q) e[g][q] += 1.0f;
+    if constexpr (SHARE) {
+      p01[g] = e[g][0] * e[g][1];
+      p23[g] = e[g][2] * e[g][3];
+      inv[g] = rcp_approx(p01[g] * p23[g]);
+    } else {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float sg = rcp_approx(1.0f + ex2_approx(__uint_as_float(hv[q])));
-      rr[q] = yy[q] - sg;
-      // log-likelihood (last step only): sum_n [y eta - softplus(eta)] = beta . c + sum_n ln sigmoid(eta_n) with
-      // c = X^T (y - 1) precomputed; only the log-sigmoid sum is per observation.  Padded rows have eta = 0,
-      // i.e. lg2(1/2) = -1 each: corrected by a constant after the chunk loop.
-      if (last) lik += lg2_approx(sg);
+      for (int q = 0; q < 4; ++q) e[g][q] = rcp_approx(e[g][q]);
     }
+  };
+  auto stage_c = [&](int g) {
+    float qv[4];
+    if constexpr (SHARE) {
+      const float i01 = inv[g] * p23[g], i23 = inv[g] * p01[g];
+      qv[0] = i01 * e[g][1]; qv[1] = i01 * e[g][0]; qv[2] = i23 * e[g][3]; qv[3] = i23 * e[g][2];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) qv[q] = e[g][q];
+    }
+    if (LAST) {
+      // ln sigmoid(t eta) / ln2 = h + log2 q; the two terms cancel for well-predicted observations, so the
+      // difference is formed per element and only the (small) differences are accumulated
+      const float t0 = m[g][0] + lg2_approx(qv[0]), t1 = m[g][1] + lg2_approx(qv[1]);
+      const float t2 = m[g][2] + lg2_approx(qv[2]), t3 = m[g][3] + lg2_approx(qv[3]);
+      lik += (t0 + t1) + (t2 + t3);
+    }
+    split_pack(qv[0], qv[1], r1[2 * g], r2[2 * g]);
+    split_pack(qv[2], qv[3], r1[2 * g + 1], r2[2 * g + 1]);
+  };
+  stage_a(0); stage_a(1); stage_b(0); stage_a(2); stage_b(1);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    if (g + 3 < 8) stage_a(g + 3);
+    if (g + 2 < 8) stage_b(g + 2);
+    stage_c(g);
   }
 }
 
 // GAMMA = german_credit_gammascale (models.py:930-945): beta_log_scales is not a Normal site (never
 // reparameterised); beta ~ N(0, exp(overall_log_scale + beta_log_scales)).
 template <int NF, bool GAMMA>
-__global__ void __launch_bounds__(TCS_THREADS, 1)
+__global__ void
+#ifdef TCS_MAXNREG
+__maxnreg__(TCS_MAXNREG)
+#else
+__launch_bounds__(TCS_THREADS, 1)
+#endif
 k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
   using K = Tcs<NF>;
   constexpr int FPW = K::FPW, NLOC = K::NLOC;
@@ -123,7 +164,6 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       par[(2 * NF + 4) + i] = p.b[i];
       par[2 * (2 * NF + 4) + i] = p.eps0[i];
     }
-    for (int i = tid; i < tp.F; i += TCS_THREADS) par[3 * (2 * NF + 4) + i] = tp.cvec[i];
   }
   if (warp == TCS_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
@@ -153,7 +193,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       for (int s = 0; s < n_lf; ++s)
         for (int c = 0; c < NCH; ++c, ++cnt) {
           const uint32_t st = cnt % TCS_NSTAGE, use = cnt / TCS_NSTAGE;
-          if (use > 0) mbar_wait(bar_xe + 8 * st, (use - 1) & 1);
+          if (use > 0) TCS_ROLE_WAIT(bar_xe + 8 * st, (use - 1) & 1);
           mbar_expect_tx(bar_xf + 8 * st, K::STAGE);
           bulk_g2s(sbase + K::RING + st * K::STAGE, tp.img + (size_t)c * K::STAGE, K::STAGE, bar_xf + 8 * st);
         }
@@ -170,7 +210,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       uint32_t cnt = 0;  // global chunk counter of the next GEMM1 to issue
       auto stage_of = [&](uint32_t k) { return sbase + K::RING + (k % TCS_NSTAGE) * K::STAGE; };
       auto issue_g1 = [&](int c, uint32_t k) {
-        mbar_wait(bar_xf + 8 * (k % TCS_NSTAGE), (k / TCS_NSTAGE) & 1);
+        TCS_ROLE_WAIT(bar_xf + 8 * (k % TCS_NSTAGE), (k / TCS_NSTAGE) & 1);
         tc_fence_after();
         const uint32_t d = tmu + K::COL_H + (uint32_t)(c & 1) * TC_CHUNK;
         const uint32_t xs = __shfl_sync(0xffffffffu, stage_of(k), 0);
@@ -201,13 +241,13 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       };
       for (int s = 0; s < n_lf; ++s) {
         const uint32_t k0 = cnt;  // global index of chunk 0 of this step
-        mbar_wait(bar_a, pa); pa ^= 1;
+        TCS_ROLE_WAIT(bar_a, pa); pa ^= 1;
         tc_fence_after();
         issue_g1(0, k0); tc_commit_if(issue, bar_h0);
         if (NCH > 1) { issue_g1(1, k0 + 1); tc_commit_if(issue, bar_h0 + 8); }
         for (int c = 0; c < NCH; ++c) {
           const int b = c & 1;
-          mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
+          TCS_ROLE_WAIT(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
           tc_fence_after();
           issue_g2(c, k0 + c);
           tc_commit_if(issue, bar_xe + 8 * ((k0 + c) % TCS_NSTAGE));   // stage free once GEMM2(c) has read it
@@ -224,7 +264,10 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const int chain = blockIdx.x * TC_CHAINS + r;
     const bool valid = chain < p.C;
     const int D = p.D, F = tp.F;
-    const int nf = max(0, min(FPW, F - FPW * w));
+    // features are dealt to the four workers of a chain in contiguous, balanced ranges (25 -> 7, 6, 6, 6); worker w
+    // owns K-slots [FPW w, FPW w + nf) of the A operand / X images and the matching columns of G
+    const int nf = F / TC_NQ + (w < F % TC_NQ ? 1 : 0);
+    const int fstart = w * (F / TC_NQ) + min(w, F % TC_NQ);
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const size_t co = (size_t)chain * ws.sc;
     Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd}, VG{ws.v + co, ws.sd};
@@ -232,11 +275,10 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const float* pa_s = reinterpret_cast<const float*>(smem + K::PAR);
     const float* pb_s = pa_s + (2 * NF + 4);
     const float* pe_s = pb_s + (2 * NF + 4);
-    const float* pc_s = pe_s + (2 * NF + 4);
     float lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
     int nacc = ws.nacc[chain];
     const unsigned int gchain = p.chain_offset + (unsigned int)chain;
-    uint32_t ph[2] = {0, 0}, pg = 0, kcnt = 0;
+    uint32_t ph[2] = {0, 0}, pg = 0;
     const float a0 = pa_s[0], b0 = pb_s[0];
     // coordinate 0 (overall_log_scale) is replicated in all four workers of a chain.  Each keeps its own copy of
     // the current z / gradient in registers (all four take identical accept decisions), so no worker ever reads
@@ -244,8 +286,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     float z0_cur = Z(0), g0_cur = G(0), g0_prop = 0.f;
     uint8_t* a_row1 = smem + K::A1 + (r >> 3) * K::SG + (r & 7) * 16 + w * (FPW / 8) * K::SF;
     uint8_t* a_row2 = smem + K::A2 + (r >> 3) * K::SG + (r & 7) * 16 + w * (FPW / 8) * K::SF;
-    const float NLOG2E = -1.4426950408889634f;
-    auto dof = [&](int i) { return i == 0 ? 0 : (i <= FPW ? FPW * w + i : F + FPW * w + i - FPW); };
+    const float LOG2E = 1.4426950408889634f;
+    auto dof = [&](int i) { return i == 0 ? 0 : (i <= FPW ? fstart + i : F + fstart + i - FPW); };
     auto owned = [&](int i) { return i == 0 || (i <= FPW ? (i - 1) < nf : (i - 1 - FPW) < nf); };
     // cross-quarter exchange slots, double-buffered by the parity of the step counter so ONE named barrier per
     // leapfrog step suffices (a thread can be at most one step ahead of the slowest one)
@@ -264,9 +306,16 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       if (i == 0) { v0r = x; return; }
       if constexpr (V_IN_REGS) vreg[i] = x; else VG(dof(i)) = x;
     };
+#if TCS_PROFILE
+    uint32_t pt[16] = {}, plast = (uint32_t)clock();
+#define TCS_TICK(i) { const uint32_t now_ = (uint32_t)clock(); pt[i] += now_ - plast; plast = now_; }
+#else
+#define TCS_TICK(i)
+#endif
 
     for (int t = 0; t < p.T; ++t) {
       const int tg = p.t_begin + t;
+      TCS_TICK(9)
       if (p.ext_momenta) {
         const float* mom = p.ext_momenta + ((size_t)tg * p.C + (valid ? chain : 0)) * D;
 #pragma unroll
@@ -283,7 +332,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
 #pragma unroll
         for (int seg = 1; seg < 3; ++seg) {
-          const int d_lo = seg == 1 ? 1 + FPW * w : 1 + F + FPW * w;
+          const int d_lo = seg == 1 ? 1 + fstart : 1 + F + fstart;
           const int d_hi = d_lo + nf;
           const int i_lo = seg == 1 ? 1 : 1 + FPW;
 #pragma unroll
@@ -299,6 +348,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           }
         }
       }
+      TCS_TICK(10)
       float ke0 = 0.f, ke1 = 0.f, ke0_tot = 0.f, ke1_tot = 0.f;
       {
         // all global loads first: with the loads inside the update loop every iteration waited a full L2
@@ -324,6 +374,10 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
       }
       float lpx = 0.f;
+      // a coefficient that leaves the fp16 range of the A operand (only on wildly diverging trajectories) would make
+      // GEMM1 return inf / NaN and the clamp below would swallow it: such a trajectory is rejected outright
+      bool ovf = false;
+      TCS_TICK(0)
       for (int l = 0; l < p.L; ++l) {
         const bool last = (l == p.L - 1);
         float lp_top = 0.f;
@@ -336,13 +390,14 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             const int k = 8 * fc + k8;
             be[k8] = 0.f;
             if (k < nf) {
-              const int f = FPW * w + k;
+              const int f = fstart + k;
               float dummy = 0.f;
               float ls;
               if (GAMMA) ls = s0.x + xs[(1 + k) * TC_WORKERS];
               else ls = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy).x;
               const Site sb = site_fwd_fast(xs[(1 + FPW + k) * TC_WORKERS], 0.f, ls, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
-              be[k8] = sb.x * NLOG2E;   // GEMM1 then yields -log2(e) * eta: one FMUL less per likelihood element
+              be[k8] = sb.x * LOG2E;   // GEMM1 then yields log2(e) t eta: one FMUL less per likelihood element
+              ovf |= !(fabsf(be[k8]) < 60000.f);   // outside the fp16 range of the A operand (or NaN)
             }
           }
           uint4 hi, lo;
@@ -356,38 +411,37 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(bar_a);
+        TCS_TICK(1)
         float lik = 0.f;
-        for (int c = 0; c < NCH; ++c, ++kcnt) {
+        for (int c = 0; c < NCH; ++c) {
           const int b = c & 1;
           mbar_wait(bar_h0 + 8 * b, ph[b]); ph[b] ^= 1;
+          TCS_TICK(2)
           tc_fence_after();
-          uint32_t hv[32];
-          TC_LD32(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, hv);
+          const uint32_t h_addr = tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w;
+          uint32_t hv[32], r1[16], r2[16];
+          TC_LD32(h_addr, hv);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const float* sy = reinterpret_cast<const float*>(smem + K::RING + (kcnt % TCS_NSTAGE) * K::STAGE + 2 * K::XCHUNK);
-          uint32_t r1[16], r2[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 y4 = *reinterpret_cast<const float4*>(sy + 32 * w + i);
-            const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
-            float rr[4];
-            tcs_sigmoid4<K::RCP_SHARE>(&hv[i], yy, rr, last, lik);
-            split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
-            split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
-          }
+          TCS_TICK(3)
+          if (last) tcs_epilogue32<K::RCP_SHARE, true>(hv, r1, r2, lik);
+          else tcs_epilogue32<K::RCP_SHARE, false>(hv, r1, r2, lik);
+          TCS_TICK(14)
           TC_ST16(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, r1);
           TC_ST16(tmem + lane_off + K::COL_R2 + b * 64 + 16 * w, r2);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          TCS_TICK(15)
           tc_fence_before();
           mbar_arrive(bar_r0 + 8 * b);
+          TCS_TICK(4)
         }
         mbar_wait(bar_g, pg); pg ^= 1;
+        TCS_TICK(5)
         tc_fence_after();
         uint32_t gv[FPW];
         if constexpr (FPW == 8) { TC_LD8(tmem + lane_off + K::COL_G + 8 * w, gv); }
         else { TC_LD16(tmem + lane_off + K::COL_G + 16 * w, gv); }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float acc0 = 0.f, lps = 0.f, lin = 0.f;
+        float acc0 = 0.f, lps = 0.f;
         // NF = 64: fetch all momenta before the update loop (inside it every iteration would wait an L2 round trip)
         float vq[V_IN_REGS ? 1 : 2 * FPW];
         if constexpr (!V_IN_REGS) {
@@ -400,7 +454,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
 #pragma unroll
         for (int k = 0; k < FPW; ++k) {
           if (k < nf) {
-            const int f = FPW * w + k;
+            const int f = fstart + k;
             const float af = pa_s[1 + f], ab_ = pa_s[1 + F + f], bb_ = pb_s[1 + F + f];
             const float xs_s = xs[(1 + k) * TC_WORKERS], xs_b = xs[(1 + FPW + k) * TC_WORKERS];
             Site ss;
@@ -412,7 +466,6 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               ss = site_fwd_unit(xs_s, s0.x, af, lps);
             }
             const Site sb = site_fwd_fast(xs_b, 0.f, GAMMA ? s0.x + xs_s : ss.x, ab_, bb_, lps);
-            lin = fmaf(sb.x, pc_s[f], lin);
             float gb, mb, lb, ab;
             site_rev(sb, __uint_as_float(gv[k]), 0.f, ab_, bb_, gb, mb, lb, ab);
             float gs, mb2, lb2, ab2;
@@ -439,14 +492,16 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           }
         }
         if (last) {
+          // padded rows have h = 0, q = 1/2: -1 each
           lik = 0.69314718055994531f * (lik + (w == 0 ? (float)(NCH * TC_CHUNK - tp.N) : 0.f));
-          lik += lin;
         }
         xch_at(0, w) = acc0;
-        xch_at(1, w) = lik + lps;
+        xch_at(1, w) = ovf ? -INFINITY : lik + lps;
         xch_at(2, w) = ke0;   // partial kinetic energies ride along (meaningful on the first / last step)
         xch_at(3, w) = ke1;
+        TCS_TICK(6)
         epi_bar();
+        TCS_TICK(7)
         const float acc0_t = xch_sum(0);
         lpx = xch_sum(1) + lp_top;
         if (l == 0) ke0_tot = xch_sum(2);
@@ -467,6 +522,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           v0r = v0;
         }
         par ^= 1;
+        TCS_TICK(8)
       }
       float log_alpha = lpx - lp_cur + 0.5f * ke0_tot - 0.5f * ke1_tot;
       if (!(log_alpha == log_alpha) || log_alpha == -INFINITY) log_alpha = -INFINITY;
@@ -474,6 +530,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       if (p.ext_log_u) log_u = p.ext_log_u[(size_t)tg * p.C + (valid ? chain : 0)];
       else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
       const bool acc = log_u < log_alpha;
+      TCS_TICK(11)
       if (acc) {
         float gq[NLOC], xq[NLOC];   // loads first, then stores (see the first kick)
 #pragma unroll
@@ -501,6 +558,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         lp_cur = lpx;
         ++nacc;
       }
+      TCS_TICK(12)
       const int t1 = tg + 1;
       if (t1 <= p.num_adapt) {
         const float ft = (float)t1;
@@ -510,6 +568,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         lavg = eta * log_step + (1.f - eta) * lavg;
         mult = (t1 < p.num_adapt) ? expf(log_step) : expf(lavg);
       }
+      TCS_TICK(13)
       const int since = tg - p.num_burnin;
       if (since >= 0 && (since % p.stride) == 0 && valid) {
         const int s = since / p.stride;
@@ -536,6 +595,11 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
       }
     }
+#if TCS_PROFILE
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5 || warp == 15))
+      printf("tcs warp %d: philox %u kick0 %u fwd %u waitH %u ld %u compute %u st+wait %u arrive %u waitG %u rev %u bar %u top %u | alpha+u %u accept %u adapt %u store %u\n",
+             warp, pt[10], pt[0], pt[1], pt[2], pt[3], pt[14], pt[15], pt[4], pt[5], pt[6], pt[7], pt[8], pt[11], pt[12], pt[13], pt[9]);
+#endif
     if (w == 0) {
       ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
     }
@@ -549,40 +613,43 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
 
 // --------------------------------------------------------------------------- host ---
 struct GermanTcs {
-  DevBuf img, cvec;
+  DevBuf img;
   int N = 0, F = 0, nf_pad = 0, nchunk = 0;
   bool ok = false;
 
-  // X [N, F] fp32 row-major, y [N] -> per-chunk stage images (head | tail | y), zero padded
+  // X [N, F] fp32 row-major, y [N] in {0, 1} -> per-chunk stage images (head | tail) of the rows t_n X_n,
+  // t_n = 2 y_n - 1, zero padded
   bool build(const float* X, const float* y, int n, int f, std::string* err) {
     ok = false;
     if (f > 64) return true;   // SIMT engine only
     nf_pad = f <= 32 ? 32 : 64;
     nchunk = (n + TC_CHUNK - 1) / TC_CHUNK;
-    const uint32_t SG = (uint32_t)(nf_pad / 8) * 128, XCHUNK = (TC_CHUNK / 8) * SG, STAGE = 2 * XCHUNK + TC_CHUNK * 4;
+    const uint32_t SG = (uint32_t)(nf_pad / 8) * 128, XCHUNK = (TC_CHUNK / 8) * SG, STAGE = 2 * XCHUNK;
     std::vector<uint8_t> buf((size_t)nchunk * STAGE, 0);
+    // K-slot of feature j: the kernels deal the features to the four workers of a chain in balanced contiguous
+    // ranges; worker w owns slots [fpw w, fpw (w + 1))
+    std::vector<int> slot(f);
+    {
+      const int fpw = nf_pad / TC_NQ, q = f / TC_NQ, r = f % TC_NQ;
+      for (int w = 0, j = 0; w < TC_NQ; ++w)
+        for (int k = 0; k < q + (w < r ? 1 : 0); ++k, ++j) slot[j] = w * fpw + k;
+    }
     for (int i = 0; i < n; ++i) {
       const int c = i / TC_CHUNK, rloc = i % TC_CHUNK;
       uint8_t* st = buf.data() + (size_t)c * STAGE;
+      if (y[i] != 0.f && y[i] != 1.f) return true;   // not a Bernoulli outcome: SIMT engine only
+      const float t = 2.f * y[i] - 1.f;
       for (int j = 0; j < f; ++j) {
-        const float x = X[(size_t)i * f + j];
+        const float x = t * X[(size_t)i * f + j];
         if (!(fabsf(x) < 60000.f)) return true;  // outside fp16 range: SIMT engine only
         const __half h1 = __float2half_rn(x);
         const __half h2 = __float2half_rn(x - __half2float(h1));
-        const size_t off = (size_t)(rloc / 8) * SG + (size_t)(j / 8) * 128 + (size_t)(rloc % 8) * 16 + (size_t)(j % 8) * 2;
+        const size_t off = (size_t)(rloc / 8) * SG + (size_t)(slot[j] / 8) * 128 + (size_t)(rloc % 8) * 16 + (size_t)(slot[j] % 8) * 2;
         memcpy(st + off, &h1, 2);
         memcpy(st + XCHUNK + off, &h2, 2);
       }
-      memcpy(st + 2 * XCHUNK + (size_t)rloc * 4, &y[i], 4);
-    }
-    std::vector<float> cv(64, 0.f);
-    for (int j = 0; j < f; ++j) {
-      double acc = 0;
-      for (int i = 0; i < n; ++i) acc += (double)X[(size_t)i * f + j] * ((double)y[i] - 1.0);
-      cv[j] = (float)acc;
     }
     cudaError_t e = upload(img, buf);
-    if (e == cudaSuccess) e = upload(cvec, cv);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return false; }
     N = n; F = f; ok = true;
     return true;
@@ -645,7 +712,7 @@ static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt,
   }
   launches->fetch_add(1);
   TCS_CUDA(cudaGetLastError());
-  TcsParams tp{tc.img.as<uint8_t>(), tc.cvec.as<float>(), tc.N, tc.F, tc.nchunk, tcd_skew()};
+  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk, tcd_skew()};
   if (dual && tc.nf_pad == 32) TCS_CUDA(gamma ? tcd_launch<true>(grid, st, tp, ws, p) : tcd_launch<false>(grid, st, tp, ws, p));
   else TCS_CUDA(gamma ? tcs_launch<true>(tc.nf_pad, grid, st, tp, ws, p) : tcs_launch<false>(tc.nf_pad, grid, st, tp, ws, p));
   launches->fetch_add(1);

@@ -1,0 +1,115 @@
+// Micro-benchmark of the likelihood-epilogue arithmetic in isolation (no TMEM, no barriers): clocks per
+// 32-element chunk per SM sub-partition with W warps per sub-partition.  Variants isolate the cost of the clamp,
+// the shared reciprocal and the fp16 head / tail split.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o epi epi.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void split_pack(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// truncation split: head = top 10 mantissa bits (exact in fp16 for normal-range values), full-rate LOP3 instead of
+// the half-rate HADD2.F32 unpack
+__device__ __forceinline__ void split_trunc(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+  const __half2 h = __floats2half2_rn(h0, h1);
+  const __half2 l = __floats2half2_rn(x0 - h0, x1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int V>
+__device__ __forceinline__ void epi32(const uint32_t* hv, uint32_t* r1, uint32_t* r2) {
+  float d[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float m = __uint_as_float(hv[i]);
+    if (V != 1 && V != 3) m = fminf(m, 30.f);
+    d[i] = ex2a(m) + 1.0f;
+  }
+  float q[32];
+  if (V == 3) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) q[i] = rcpa(d[i]);
+  } else if (V == 4) {
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      const float inv = rcpa(d[2 * g] * d[2 * g + 1]);
+      q[2 * g] = inv * d[2 * g + 1]; q[2 * g + 1] = inv * d[2 * g];
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float p01 = d[4 * g] * d[4 * g + 1], p23 = d[4 * g + 2] * d[4 * g + 3];
+      const float inv = rcpa(p01 * p23);
+      const float i01 = inv * p23, i23 = inv * p01;
+      q[4 * g] = i01 * d[4 * g + 1]; q[4 * g + 1] = i01 * d[4 * g]; q[4 * g + 2] = i23 * d[4 * g + 3]; q[4 * g + 3] = i23 * d[4 * g + 2];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (V == 5) { r1[i] = __float_as_uint(q[2 * i]); r2[i] = __float_as_uint(q[2 * i + 1]); }
+    else if (V == 2) split_trunc(q[2 * i], q[2 * i + 1], r1[i], r2[i]);
+    else split_pack(q[2 * i], q[2 * i + 1], r1[i], r2[i]);
+  }
+}
+
+#define ITERS 512
+template <int V>
+__global__ void __launch_bounds__(512, 1) k(uint32_t* out, long long* clk, float seed) {
+  uint32_t acc = 0;
+  float base = seed + threadIdx.x * 1e-3f;
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {
+    uint32_t hv[32], r1[16], r2[16];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) hv[i] = __float_as_uint(base + (float)i * 0.37f - 6.0f);
+    if (V == 6) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) split_pack(__uint_as_float(hv[2 * i]), __uint_as_float(hv[2 * i + 1]), r1[i], r2[i]);
+    } else {
+      epi32<V>(hv, r1, r2);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc ^= r1[i] + r2[i];
+    base += __uint_as_float((acc & 0xff) | 0x3a000000u);   // serialises iterations lightly, defeats hoisting
+  }
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (threadIdx.x == 0 && blockIdx.x == 0) *clk = t1 - t0;
+}
+
+template <int V>
+void run(const char* name) {
+  uint32_t* out; long long* clk;
+  cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&clk, 8);
+  for (int w : {1, 2, 4}) {
+    k<V><<<148, 128 * w>>>(out, clk, 1.0f);
+    k<V><<<148, 128 * w>>>(out, clk, 1.0f);
+    cudaDeviceSynchronize();
+    long long h; cudaMemcpy(&h, clk, 8, cudaMemcpyDeviceToHost);
+    printf("%-44s warps/SMSP %d: %7.1f clk per chunk (all warps of the sub-partition)\n", name, w, (double)h / ITERS);
+  }
+  cudaFree(out); cudaFree(clk);
+}
+
+int main() {
+  run<0>("V0 clamp + share4 + split (current)");
+  run<1>("V1 no clamp");
+  run<2>("V2 truncation split (LOP3)");
+  run<3>("V3 no share (2 MUFU / element), no clamp");
+  run<4>("V4 share2");
+  run<5>("V5 no split");
+  run<6>("V6 split only");
+  return 0;
+}

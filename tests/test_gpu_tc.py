@@ -132,6 +132,57 @@ def test_tcs_single_leapfrog_gradient(model, method):
     assert (err < allow).all(), (err, allow)
 
 
+@pytest.mark.parametrize("eng", ["stream", "dual"])
+@pytest.mark.parametrize("s0", [0.2, 0.35, 0.6])
+def test_tcs_confident_logits_gradient(eng, s0):
+    """Large coefficients (|eta| up to several hundred): the clamp that keeps the product of four sigmoid
+    denominators (one shared reciprocal) finite is active, and far tails (sigmoid == 0 or 1 in fp32) must still
+    give the fp64 gradient to 1e-5 of its max-norm."""
+    C = 37
+    mc, raw, D, a, b, z0 = _case_model("german_synth", "NCP", C, seed=47)
+    z0[:, 0] = s0          # NCP: overall_log_scale = 10 z  ->  beta ~ exp(10 s0) * 0.3 z
+    lp_ref, g_ref = O.log_joint_and_grad(MODEL, raw, z0, a, b)
+    eps = 2.0 ** -9
+    out = engine.hmc_run(mc, z0, np.full(D, eps), a, b, num_leapfrog_steps=1, num_results=1, num_burnin_steps=0,
+                         num_adaptation_steps=0, ext_momenta=np.zeros((1, C, D)), ext_log_u=np.full((1, C), -1e30),
+                         want_orig=True,
+                         engine=engine.ENGINE_TCGEN05_STREAM if eng == "stream" else engine.ENGINE_TCGEN05_DUAL)
+    assert out["is_accepted"].all()
+    g_tc = (out["samples_orig"][0].astype(np.float64) - z0) / (0.5 * eps * eps)
+    err = np.abs(g_tc - g_ref).max(axis=1)
+    allow = 1e-5 * np.maximum(np.abs(g_ref).max(axis=1), 1.0) + 2.0 ** -23 * np.abs(z0).max() / (0.5 * eps * eps)
+    assert (err < allow).all(), (err / allow).max()
+
+
+@pytest.mark.parametrize("eng", ["stream", "dual"])
+@pytest.mark.parametrize("s0", [0.0, 0.35])
+def test_tcs_log_likelihood_value_pins_accept(eng, s0):
+    """The log-joint value of the proposal (last leapfrog step: ln2 * sum (h + log2 q)) decides the Metropolis test:
+    with log u placed just below / above the fp64 oracle's log alpha the chain must accept / reject."""
+    C = 64
+    mc, raw, D, a, b, z0 = _case_model("german_synth", "NCP", C, seed=48)
+    z0[:, 0] = s0
+    rng = np.random.default_rng(5)
+    # s0 = 0.35: |grad| ~ 1e5, so the step must be tiny for the kinetic energies (fp32) to stay O(1)
+    L, eps = 2, (1e-3 if s0 == 0.0 else 2e-6)
+    mom = rng.standard_normal((1, C, D))
+    f = lambda zz: O.log_joint_and_grad(MODEL, raw, zz, a, b)
+    lp0, g = f(z0)
+    v, x = mom[0].copy(), z0.copy()
+    for _ in range(L):   # TFP op order, fp64
+        v = v + 0.5 * eps * g
+        x = x + eps * v
+        lpx, g = f(x)
+        v = v + 0.5 * eps * g
+    la = lpx - lp0 + 0.5 * (mom[0] ** 2).sum(1) - 0.5 * (v ** 2).sum(1)
+    tol = 2e-3 + 5e-6 * np.abs(lpx)
+    e = engine.ENGINE_TCGEN05_STREAM if eng == "stream" else engine.ENGINE_TCGEN05_DUAL
+    for sign, want in ((-1.0, 1), (1.0, 0)):
+        out = engine.hmc_run(mc, z0, np.full(D, eps), a, b, num_leapfrog_steps=L, num_results=1, num_burnin_steps=0,
+                             num_adaptation_steps=0, ext_momenta=mom, ext_log_u=(la + sign * tol)[None, :], engine=e)
+        assert (out["is_accepted"][0] == want).all(), (sign, out["is_accepted"][0], la)
+
+
 @pytest.mark.parametrize("model", ["german_synth", MODEL, "german_credit_gammascale"])
 def test_tcs_fixed_momenta_trajectory(model):
     C, L, S, burn, adapt = 6, 3, 3, 2, 4
