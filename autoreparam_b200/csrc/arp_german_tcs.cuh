@@ -21,6 +21,16 @@ namespace arp {
 #else
 #define TCS_ROLE_WAIT mbar_wait
 #endif
+// Worker -> MMA-issuer hand-offs ("A operand written", "residual of chunk c stored") use hardware NAMED barriers:
+// the 512 workers bar.arrive, the issuer warp bar.sync's and is descheduled until the last arrival.  With an
+// mbarrier the issuer's try_wait returned immediately and its BRA / YIELD / TRYWAIT spin loop was 13.6 % of all
+// instructions the kernel executed (ncu source page), all of them on the one SM sub-partition that hosts the issuer
+// warp next to four worker warps -- and the slowest sub-partition paces every chunk.
+#define TCS_NB_A 2          // named barrier ids (1 = epi_bar among the workers); 3, 4 = residual buffers 0, 1
+#define TCS_NB_R 3
+#define TCS_NB_COUNT (TC_WORKERS + 32)
+__device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(TCS_NB_COUNT) : "memory"); }
+__device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TCS_NB_COUNT) : "memory"); }
 #ifndef TCS_PROFILE
 #define TCS_PROFILE 0   // 1: one lane per worker warp accumulates clock() per phase and printf()s it (timing study only)
 #endif
@@ -87,6 +97,22 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // 0.5 IPC inside the epilogue with four worker warps per scheduler, measured with clock().)
 // (A clamp-free fast path -- one chained FSETP per group on the product of the denominators instead of the 32
 // half-rate FMNMX, with a clamped cold path -- was measured 4 % SLOWER end to end and is not kept.)
+// fp32 pair -> packed fp16 head / tail by TRUNCATION: head = the top 10 mantissa bits (one full-rate LOP3 instead of
+// the half-rate F2FP -> HADD2.F32 round trip of split_pack), tail = x - head (exact), both then packed with F2FP.
+// |head| < 2^-14 (fp16 subnormal) rounds in the pack: an absolute error below 2^-25 on a sigmoid value.
+__device__ __forceinline__ void split_pack_trunc(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+  const __half2 h = __floats2half2_rn(h0, h1);
+  const __half2 l = __floats2half2_rn(x0 - h0, x1 - h1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+#ifdef TCS_TRUNC_SPLIT
+#define TCS_SPLIT split_pack_trunc
+#else
+#define TCS_SPLIT split_pack
+#endif
+
 template <bool SHARE, bool LAST>
 __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1, uint32_t* r2, float& lik) {
   float m[8][4], e[8][4], p01[8], p23[8], inv[8];
@@ -119,14 +145,19 @@ __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1,
       for (int q = 0; q < 4; ++q) qv[q] = e[g][q];
     }
     if (LAST) {
-      // ln sigmoid(t eta) / ln2 = h + log2 q; the two terms cancel for well-predicted observations, so the
-      // difference is formed per element and only the (small) differences are accumulated
-      const float t0 = m[g][0] + lg2_approx(qv[0]), t1 = m[g][1] + lg2_approx(qv[1]);
-      const float t2 = m[g][2] + lg2_approx(qv[2]), t3 = m[g][3] + lg2_approx(qv[3]);
-      lik += (t0 + t1) + (t2 + t3);
+      // ln sigmoid(t eta) / ln2 = h + log2 q.  The two terms cancel for well-predicted observations, so the
+      // difference is formed per group and only the (small) differences are accumulated.  With the shared
+      // reciprocal sum_group log2 q = log2 prod q = log2(inv): ONE MUFU.LG2 per four observations.
+      if constexpr (SHARE) {
+        lik += ((m[g][0] + m[g][1]) + (m[g][2] + m[g][3])) + lg2_approx(inv[g]);
+      } else {
+        const float t0 = m[g][0] + lg2_approx(qv[0]), t1 = m[g][1] + lg2_approx(qv[1]);
+        const float t2 = m[g][2] + lg2_approx(qv[2]), t3 = m[g][3] + lg2_approx(qv[3]);
+        lik += (t0 + t1) + (t2 + t3);
+      }
     }
-    split_pack(qv[0], qv[1], r1[2 * g], r2[2 * g]);
-    split_pack(qv[2], qv[3], r1[2 * g + 1], r2[2 * g + 1]);
+    TCS_SPLIT(qv[0], qv[1], r1[2 * g], r2[2 * g]);
+    TCS_SPLIT(qv[2], qv[3], r1[2 * g + 1], r2[2 * g + 1]);
   };
   stage_a(0); stage_a(1); stage_b(0); stage_a(2); stage_b(1);
 #pragma unroll
@@ -209,49 +240,59 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy for the uniform datapath
       uint32_t cnt = 0;  // global chunk counter of the next GEMM1 to issue
       auto stage_of = [&](uint32_t k) { return sbase + K::RING + (k % TCS_NSTAGE) * K::STAGE; };
-      auto issue_g1 = [&](int c, uint32_t k) {
+      auto issue_g1 = [&](int c, uint32_t k, uint32_t commit_bar) {
         TCS_ROLE_WAIT(bar_xf + 8 * (k % TCS_NSTAGE), (k / TCS_NSTAGE) & 1);
         tc_fence_after();
         const uint32_t d = tmu + K::COL_H + (uint32_t)(c & 1) * TC_CHUNK;
         const uint32_t xs = __shfl_sync(0xffffffffu, stage_of(k), 0);
+        // one elected lane issues the whole batch; the descriptors of a batch differ only in the 14-bit start
+        // address field (16-byte units, no carry for shared-memory addresses), so each one is base + constant
+        if (elect_one()) {
+          const uint64_t a_base[2] = {tc_desc(sA[0], K::SF, K::SG), tc_desc(sA[1], K::SF, K::SG)};
+          const uint64_t b_base = tc_desc(xs, K::SF, K::SG);
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+          for (int q = 0; q < 3; ++q)
 #pragma unroll
-          for (int ks = 0; ks < NF / 16; ++ks) {
-            const uint64_t ad = tc_desc(sA[pa_sel[q]] + ks * 2 * K::SF, K::SF, K::SG);
-            const uint64_t bd = tc_desc(xs + pb_sel[q] * K::XCHUNK + ks * 2 * K::SF, K::SF, K::SG);
-            mma_ss_if(issue, d, ad, bd, K::IDESC_G1, (q | ks) ? 1u : 0u);
-          }
+            for (int ks = 0; ks < NF / 16; ++ks)
+              mma_ss(d, a_base[pa_sel[q]] + (uint64_t)((ks * 2 * K::SF) >> 4),
+                     b_base + (uint64_t)((pb_sel[q] * K::XCHUNK + ks * 2 * K::SF) >> 4), K::IDESC_G1, (q | ks) ? 1u : 0u);
+          if (commit_bar) tc_commit(commit_bar);
+        }
+        __syncwarp();
       };
-      auto issue_g2 = [&](int c, uint32_t k) {
+      auto issue_g2 = [&](int c, uint32_t k, uint32_t stage_free_bar) {
         const uint32_t b = (uint32_t)(c & 1);
         const uint32_t xs = __shfl_sync(0xffffffffu, stage_of(k), 0);
+        if (elect_one()) {
+          const uint64_t b_base = tc_desc(xs, K::SG, K::SF);
+          const uint32_t a_h = tmu + K::COL_H + b * TC_CHUNK, a_r2 = tmu + K::COL_R2 + b * 64;
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+          for (int q = 0; q < 3; ++q)
 #pragma unroll
-          for (int w = 0; w < TC_NQ; ++w)
+            for (int w = 0; w < TC_NQ; ++w)
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              const uint32_t a_t = pa_sel[q] == 0 ? tmu + K::COL_H + b * TC_CHUNK + 32 * w + 8 * kk
-                                                  : tmu + K::COL_R2 + b * 64 + 16 * w + 8 * kk;
-              const uint32_t og = 4 * w + 2 * kk;  // 8-observation group inside the chunk
-              const uint64_t bd = tc_desc(xs + pb_sel[q] * K::XCHUNK + og * K::SG, K::SG, K::SF);
-              mma_ts_if(issue, tmu + K::COL_G, a_t, bd, K::IDESC_G2, (c | q | w | kk) ? 1u : 0u);
-            }
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t a_t = pa_sel[q] == 0 ? a_h + 32 * w + 8 * kk : a_r2 + 16 * w + 8 * kk;
+                const uint32_t og = 4 * w + 2 * kk;  // 8-observation group inside the chunk
+                mma_ts(tmu + K::COL_G, a_t, b_base + (uint64_t)((pb_sel[q] * K::XCHUNK + og * K::SG) >> 4), K::IDESC_G2,
+                       (c | q | w | kk) ? 1u : 0u);
+              }
+          tc_commit(stage_free_bar);   // stage free once GEMM2(c) has read it
+        }
+        __syncwarp();
       };
       for (int s = 0; s < n_lf; ++s) {
         const uint32_t k0 = cnt;  // global index of chunk 0 of this step
-        TCS_ROLE_WAIT(bar_a, pa); pa ^= 1;
+        nb_sync(TCS_NB_A);
         tc_fence_after();
-        issue_g1(0, k0); tc_commit_if(issue, bar_h0);
-        if (NCH > 1) { issue_g1(1, k0 + 1); tc_commit_if(issue, bar_h0 + 8); }
+        issue_g1(0, k0, bar_h0);
+        if (NCH > 1) issue_g1(1, k0 + 1, bar_h0 + 8);
         for (int c = 0; c < NCH; ++c) {
           const int b = c & 1;
-          TCS_ROLE_WAIT(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
+          nb_sync(TCS_NB_R + b);
           tc_fence_after();
-          issue_g2(c, k0 + c);
-          tc_commit_if(issue, bar_xe + 8 * ((k0 + c) % TCS_NSTAGE));   // stage free once GEMM2(c) has read it
-          if (c + 2 < NCH) { issue_g1(c + 2, k0 + c + 2); tc_commit_if(issue, bar_h0 + 8 * b); }
+          issue_g2(c, k0 + c, bar_xe + 8 * ((k0 + c) % TCS_NSTAGE));
+          if (c + 2 < NCH) issue_g1(c + 2, k0 + c + 2, bar_h0 + 8 * b);
           if (c == NCH - 1) tc_commit_if(issue, bar_g);
         }
         cnt += NCH;
@@ -284,6 +325,14 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     // the current z / gradient in registers (all four take identical accept decisions), so no worker ever reads
     // what another worker of the chain writes to the global workspace.
     float z0_cur = Z(0), g0_cur = G(0), g0_prop = 0.f;
+    // The gradient / centred values of the current state and of the proposal live in two buffer sets
+    // (g, xc) and (gx, xcx) that swap roles on accept: no copy.  ocur = element offset of the current set.
+    const uint32_t oflip = (uint32_t)(ws.gx - ws.g);   // == ws.xcx - ws.xc (checked by the host)
+    uint32_t ocur = 0;
+    auto Gc = [&](int d) -> float& { return ws.g[co + (size_t)d * ws.sd + ocur]; };
+    auto XCc = [&](int d) -> float& { return ws.xc[co + (size_t)d * ws.sd + ocur]; };
+    auto Gp = [&](int d) -> float& { return ws.g[co + (size_t)d * ws.sd + (oflip - ocur)]; };
+    auto XCp = [&](int d) -> float& { return ws.xc[co + (size_t)d * ws.sd + (oflip - ocur)]; };
     uint8_t* a_row1 = smem + K::A1 + (r >> 3) * K::SG + (r & 7) * 16 + w * (FPW / 8) * K::SF;
     uint8_t* a_row2 = smem + K::A2 + (r >> 3) * K::SG + (r & 7) * 16 + w * (FPW / 8) * K::SF;
     const float LOG2E = 1.4426950408889634f;
@@ -316,6 +365,14 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     for (int t = 0; t < p.T; ++t) {
       const int tg = p.t_begin + t;
       TCS_TICK(9)
+      // current state: global loads issued before the Philox block so that their L2 round trip hides behind it
+      float gq0[NLOC], zq0[NLOC];
+#pragma unroll
+      for (int i = 0; i < NLOC; ++i) {
+        gq0[i] = 0.f; zq0[i] = 0.f;
+        if (i == 0) { gq0[0] = g0_cur; zq0[0] = z0_cur; }
+        else if (owned(i)) { const int d = dof(i); gq0[i] = Gc(d); zq0[i] = Z(d); }
+      }
       if (p.ext_momenta) {
         const float* mom = p.ext_momenta + ((size_t)tg * p.C + (valid ? chain : 0)) * D;
 #pragma unroll
@@ -324,7 +381,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       } else {
         // Philox block j holds coordinates 4j .. 4j+3; my ranges are d = 0, [1+FPW w, ..+nf), [1+F+FPW w, ..+nf).
         // All blocks are generated unconditionally in unrolled loops (independent chains the scheduler can
-        // interleave); only the stores are predicated.
+        // interleave); only the stores are predicated.  (Skipping the blocks that lie entirely outside my ranges with a
+        // warp-uniform test was measured 1.5 % slower: the branches serialise the blocks.)
         {
           float n4[4];
           philox_normal4_fast(p.seed, gchain, (unsigned int)tg, 0u, n4);
@@ -351,15 +409,6 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       TCS_TICK(10)
       float ke0 = 0.f, ke1 = 0.f, ke0_tot = 0.f, ke1_tot = 0.f;
       {
-        // all global loads first: with the loads inside the update loop every iteration waited a full L2
-        // round trip (load -> FMA -> store -> next load cannot be hoisted above the store)
-        float gq[NLOC], zq[NLOC];
-#pragma unroll
-        for (int i = 0; i < NLOC; ++i) {
-          gq[i] = 0.f; zq[i] = 0.f;
-          if (i == 0) { gq[0] = g0_cur; zq[0] = z0_cur; }
-          else if (owned(i)) { const int d = dof(i); gq[i] = G(d); zq[i] = Z(d); }
-        }
 #pragma unroll
         for (int i = 0; i < NLOC; ++i) {
           if (owned(i)) {
@@ -367,9 +416,9 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             float vi = xs[i * TC_WORKERS];
             if (i > 0 || w == 0) ke0 = fmaf(vi, vi, ke0);
             const float e = pe_s[d] * mult;
-            vi = vi + 0.5f * e * gq[i];
+            vi = vi + 0.5f * e * gq0[i];
             vset(i, vi);
-            xs[i * TC_WORKERS] = zq[i] + e * vi;
+            xs[i * TC_WORKERS] = zq0[i] + e * vi;
           }
         }
       }
@@ -410,7 +459,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
         fence_async_smem();
         tc_fence_before();
-        mbar_arrive(bar_a);
+        nb_arrive(TCS_NB_A);
         TCS_TICK(1)
         float lik = 0.f;
         for (int c = 0; c < NCH; ++c) {
@@ -431,7 +480,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           TCS_TICK(15)
           tc_fence_before();
-          mbar_arrive(bar_r0 + 8 * b);
+          nb_arrive(TCS_NB_R + b);
           TCS_TICK(4)
         }
         mbar_wait(bar_g, pg); pg ^= 1;
@@ -479,8 +528,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               ke1 = fmaf(vs, vs, ke1);
               ke1 = fmaf(vb, vb, ke1);
               // proposal gradient / centred values: parked in the global proposal slots until the accept decision
-              ws.gx[co + (size_t)(1 + f) * ws.sd] = gs; ws.gx[co + (size_t)(1 + F + f) * ws.sd] = gb;
-              ws.xcx[co + (size_t)(1 + f) * ws.sd] = ss.x; ws.xcx[co + (size_t)(1 + F + f) * ws.sd] = sb.x;
+              Gp(1 + f) = gs; Gp(1 + F + f) = gb;
+              XCp(1 + f) = ss.x; XCp(1 + F + f) = sb.x;
             } else {
               vs = vs + 0.5f * es * gs;
               vb = vb + 0.5f * eb * gb;
@@ -514,7 +563,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           if (last) {
             ke1_tot = fmaf(v0, v0, ke1_tot);   // coordinate 0 is replicated: every quarter adds it itself
             g0_prop = g0;
-            if (w == 0) ws.xcx[co] = s0.x;
+            if (w == 0) XCp(0) = s0.x;
           } else {
             v0 = v0 + 0.5f * e * g0;
             xs[0] = xs[0] + e * v0;
@@ -532,29 +581,12 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       const bool acc = log_u < log_alpha;
       TCS_TICK(11)
       if (acc) {
-        float gq[NLOC], xq[NLOC];   // loads first, then stores (see the first kick)
-#pragma unroll
-        for (int i = 0; i < NLOC; ++i) {
-          gq[i] = 0.f; xq[i] = 0.f;
-          if (i == 0) {
-            gq[0] = g0_prop;
-            if (w == 0) xq[0] = ws.xcx[co];
-          } else if (owned(i)) {
-            const int d = dof(i);
-            gq[i] = ws.gx[co + (size_t)d * ws.sd];
-            xq[i] = ws.xcx[co + (size_t)d * ws.sd];
-          }
-        }
         z0_cur = xs[0];
         g0_cur = g0_prop;
 #pragma unroll
         for (int i = 0; i < NLOC; ++i)
-          if (owned(i) && (i > 0 || w == 0)) {
-            const int d = dof(i);
-            Z(d) = xs[i * TC_WORKERS];
-            G(d) = gq[i];
-            XC(d) = xq[i];
-          }
+          if (owned(i) && (i > 0 || w == 0)) Z(dof(i)) = xs[i * TC_WORKERS];
+        ocur = oflip - ocur;   // the proposal's gradient / centred values become the current ones
         lp_cur = lpx;
         ++nacc;
       }
@@ -580,7 +612,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             xq[i] = 0.f; zq[i] = 0.f;
             if (owned(i) && (i > 0 || w == 0)) {
               const int d = dof(i);
-              if (p.samples) xq[i] = XC(d);
+              if (p.samples) xq[i] = XCc(d);
               if (p.samples_orig) zq[i] = Z(d);
             }
           }
@@ -600,6 +632,11 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       printf("tcs warp %d: philox %u kick0 %u fwd %u waitH %u ld %u compute %u st+wait %u arrive %u waitG %u rev %u bar %u top %u | alpha+u %u accept %u adapt %u store %u\n",
              warp, pt[10], pt[0], pt[1], pt[2], pt[3], pt[14], pt[15], pt[4], pt[5], pt[6], pt[7], pt[8], pt[11], pt[12], pt[13], pt[9]);
 #endif
+    if (ocur != 0) {   // leave the current gradient / centred values in (g, xc), as the workspace contract says
+#pragma unroll
+      for (int i = 0; i < NLOC; ++i)
+        if (owned(i) && (i > 0 || w == 0)) { const int d = dof(i); const float gv_ = Gc(d), xv_ = XCc(d); G(d) = gv_; XC(d) = xv_; }
+    }
     if (w == 0) {
       ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
     }
@@ -701,6 +738,7 @@ static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt,
   ws.mult = sb; ws.lp = sb + Cpad; ws.H = sb + 2 * Cpad; ws.lavg = sb + 3 * Cpad;
   ws.nacc = nacc->as<int>();
   ws.sd = (int)Cpad; ws.sc = 1;
+  if (ws.gx - ws.g != ws.xcx - ws.xc) { *err = "german_tcs_hmc: workspace layout"; return 1; }   // buffer-set flip
   const dim3 grid((unsigned)(Cpad / TC_CHAINS));
   const bool gamma = dm.kind == MODEL_GERMAN_GAMMA;
   if (gamma) {
