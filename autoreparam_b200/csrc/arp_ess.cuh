@@ -52,6 +52,11 @@ __global__ void k_ess_transpose(const real* __restrict__ x, int S, long long n, 
 
 // x is [n][S] with n = C*D series in [c][d] order.  Thread j owns series (d = j / C, c = j % C) so the
 // lanes of a warp own the same coordinate of 32 consecutive chains (similar autocorrelation lengths).
+// VEC: S is a multiple of 4 (series are then 16-byte aligned: fp32 build only), samples are fetched four at a time.
+// Every lane walks its own series, so a warp-wide load touches 32 different sectors whatever its width: with scalar
+// loads the kernel sat on the L1 wavefront rate (ncu: 17 sectors per request, 8.6e9 sectors for 836k series x 1000
+// samples); 128-bit loads need a quarter of the requests for the same bytes.
+template <bool VEC>
 __global__ void __launch_bounds__(ARP_ESS_BLOCK)
 k_ess(const real* __restrict__ x, int S, int C, int D, real* __restrict__ ess_cd, real* __restrict__ mean_cd,
       real* __restrict__ var_cd) {
@@ -65,7 +70,15 @@ k_ess(const real* __restrict__ x, int S, int C, int D, real* __restrict__ ess_cd
   const size_t n = 1;                         // stride between consecutive samples of a series
   const real* xs = x + (size_t)i * S;
   double mean = 0;
-  for (int t = 0; t < S; ++t) mean += (double)xs[(size_t)t * n];
+  if constexpr (VEC && !ARP_REAL_IS_DOUBLE) {
+    const float4* x4 = reinterpret_cast<const float4*>(xs);
+    for (int t = 0; t < S / 4; ++t) {
+      const float4 v = x4[t];
+      mean += (double)((v.x + v.y) + (v.z + v.w));
+    }
+  } else {
+    for (int t = 0; t < S; ++t) mean += (double)xs[(size_t)t * n];
+  }
   mean /= S;
   if (mean_out) *mean_out = (real)mean;
   // centring in `real` with a two-term mean (hi + lo) keeps the conversions off the XU pipe
@@ -75,6 +88,8 @@ k_ess(const real* __restrict__ x, int S, int C, int D, real* __restrict__ ess_cd
   double acov0 = 0;
   bool done = false;
   for (int k0 = 0; k0 < S && !done; k0 += ARP_ESS_W) {
+    // (double totals in shared memory / a register cap for 4-5 resident blocks per SM were measured: no gain,
+    // the kernel is not occupancy-bound)
     double acc[ARP_ESS_W];
     real ring[ARP_ESS_W], part[ARP_ESS_W];
 #pragma unroll
@@ -82,6 +97,28 @@ k_ess(const real* __restrict__ x, int S, int C, int D, real* __restrict__ ess_cd
     const int ns = S - k0;  // pairs (s + k0, s - w), s = 0 .. ns-1
     int fold = 0;
     for (int s0 = 0; s0 < ns; s0 += ARP_ESS_W) {
+      if constexpr (VEC && !ARP_REAL_IS_DOUBLE) {
+        // ns = S - k0 is a multiple of 4 (k0 is a multiple of 32): whole float4 groups are in or out of range
+        const float4* p4 = reinterpret_cast<const float4*>(xs + s0);
+        const float4* q4 = reinterpret_cast<const float4*>(xs + s0 + k0);
+#pragma unroll
+        for (int u4 = 0; u4 < ARP_ESS_W / 4; ++u4) {
+          float4 pv = make_float4(mean_hi, mean_hi, mean_hi, mean_hi), qv = pv;   // out of range -> centred value 0
+          const bool in = s0 + 4 * u4 < ns;
+          if (in) { pv = p4[u4]; qv = (k0 == 0) ? pv : q4[u4]; }
+          const float lo = in ? mean_lo : 0.f;
+          const float pa[4] = {(pv.x - mean_hi) - lo, (pv.y - mean_hi) - lo, (pv.z - mean_hi) - lo, (pv.w - mean_hi) - lo};
+          const float pr[4] = {(qv.x - mean_hi) - lo, (qv.y - mean_hi) - lo, (qv.z - mean_hi) - lo, (qv.w - mean_hi) - lo};
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int u = 4 * u4 + v;
+            ring[u] = pa[v];
+#pragma unroll
+            for (int w = 0; w < ARP_ESS_W; ++w)
+              part[w] = fma(pr[v], ring[(u - w + ARP_ESS_W) % ARP_ESS_W], part[w]);
+          }
+        }
+      } else {
 #pragma unroll
       for (int u = 0; u < ARP_ESS_W; ++u) {
         const int s = s0 + u;
@@ -94,6 +131,7 @@ k_ess(const real* __restrict__ x, int S, int C, int D, real* __restrict__ ess_cd
 #pragma unroll
         for (int w = 0; w < ARP_ESS_W; ++w)
           part[w] = fma(pres, ring[(u - w + ARP_ESS_W) % ARP_ESS_W], part[w]);
+      }
       }
       if (++fold == ARP_ESS_FOLD) {   // fold the `real` partial sums into the double totals
         fold = 0;

@@ -538,7 +538,13 @@ extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D,
     k_ess_transpose<<<tg, tb, 0, st>>>(in, (int)S, (long long)n, dxt.as<real>());
     ARP_LAUNCH_CHECK();
   }
-  k_ess<<<(unsigned)((n + ARP_ESS_BLOCK - 1) / ARP_ESS_BLOCK), ARP_ESS_BLOCK, 0, st>>>(dxt.as<real>(), (int)S, (int)C, (int)D, out, omean, ovar);
+  {
+    const unsigned eg = (unsigned)((n + ARP_ESS_BLOCK - 1) / ARP_ESS_BLOCK);
+    if (!ARP_REAL_IS_DOUBLE && S % 4 == 0)
+      k_ess<true><<<eg, ARP_ESS_BLOCK, 0, st>>>(dxt.as<real>(), (int)S, (int)C, (int)D, out, omean, ovar);
+    else
+      k_ess<false><<<eg, ARP_ESS_BLOCK, 0, st>>>(dxt.as<real>(), (int)S, (int)C, (int)D, out, omean, ovar);
+  }
   ARP_LAUNCH_CHECK();
   ARP_CUDA(cudaStreamSynchronize(st));  // the transposed copy is freed on return
   if (mem == ARP_MEM_HOST) {

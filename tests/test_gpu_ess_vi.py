@@ -31,6 +31,22 @@ def test_ess_matches_fft_oracle(S, precision):
     assert np.abs(got / ref - 1).max() < tol, np.abs(got / ref - 1).max()
 
 
+@pytest.mark.parametrize("precision,S", [("f32", 200), ("f32", 203), ("f64", 200)])
+@pytest.mark.parametrize("C,D", [(70, 3), (33, 300), (1, 1)])
+def test_ess_shapes_and_moments(C, D, precision, S):
+    """Ragged chain / coordinate counts, the 128-bit-load path (fp32, S % 4 == 0) and the scalar path, and the
+    per-chain moments the R-hat reduction consumes."""
+    rng = np.random.default_rng(C * 1000 + D)
+    phi = rng.uniform(-0.5, 0.9, (C, D))
+    x = (_ar1(S, (C, D), phi, rng) + rng.standard_normal((C, D))).astype(np.float32).astype(np.float64)
+    ref = O.effective_sample_size(x)
+    got, mean, var = engine.ess(x, precision=precision, want_moments=True)
+    tol = 2e-3 if precision == "f32" else 1e-8
+    assert np.abs(got / ref - 1).max() < tol
+    mtol = 1e-5 if precision == "f32" else 1e-10
+    assert np.abs(mean - x.mean(0)).max() < mtol * (1 + np.abs(x).max()) and np.abs(var / x.var(0) - 1).max() < 10 * mtol
+
+
 def test_ess_edge_cases():
     S, C, D = 64, 2, 3
     x = np.zeros((S, C, D))
