@@ -69,6 +69,11 @@ struct Tcd {
                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
                  "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory")
 
+// named barriers: 1, 2 = tile_bar of tile 0 / 1; tile t: 3 + 3t = "A operand written", 4 + 3t + b = "residual buffer b
+// stored" (workers bar.arrive, the tile's issuer warp bar.sync's: see arp_german_tcs.cuh)
+#define TCD_NB_COUNT (TCD_TW + 32)
+__device__ __forceinline__ void tcd_nb_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(TCD_NB_COUNT) : "memory"); }
+__device__ __forceinline__ void tcd_nb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TCD_NB_COUNT) : "memory"); }
 __device__ __forceinline__ void tile_bar(int tile) {
   asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "n"(TCD_TW) : "memory");
 }
@@ -150,49 +155,58 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy for the uniform datapath
       uint32_t cnt = 0;
       auto stage_of = [&](uint32_t k) { return ring + (k % TCS_NSTAGE) * K::STAGE; };
-      auto issue_g1 = [&](int c, uint32_t k) {
+      const int nb0 = 3 + 3 * (int)tl;
+      auto issue_g1 = [&](int c, uint32_t k, uint32_t commit_bar) {
         mbar_wait(bar_xf + 8 * (k % TCS_NSTAGE), (k / TCS_NSTAGE) & 1);
         tc_fence_after();
         const uint32_t d = tmu + K::COL_H + (uint32_t)(c & 1) * TC_CHUNK;
         const uint32_t xs = __shfl_sync(0xffffffffu, stage_of(k), 0);
+        if (elect_one()) {
+          const uint64_t a_base[2] = {tc_desc(sA[0], K::SF, K::SG), tc_desc(sA[1], K::SF, K::SG)};
+          const uint64_t b_base = tc_desc(xs, K::SF, K::SG);
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+          for (int q = 0; q < 3; ++q)
 #pragma unroll
-          for (int ks = 0; ks < NF / 16; ++ks) {
-            const uint64_t ad = tc_desc(sA[pa_sel[q]] + ks * 2 * K::SF, K::SF, K::SG);
-            const uint64_t bd = tc_desc(xs + pb_sel[q] * K::XCHUNK + ks * 2 * K::SF, K::SF, K::SG);
-            mma_ss_if(issue, d, ad, bd, K::IDESC_G1, (q | ks) ? 1u : 0u);
-          }
+            for (int ks = 0; ks < NF / 16; ++ks)
+              mma_ss(d, a_base[pa_sel[q]] + (uint64_t)((ks * 2 * K::SF) >> 4),
+                     b_base + (uint64_t)((pb_sel[q] * K::XCHUNK + ks * 2 * K::SF) >> 4), K::IDESC_G1, (q | ks) ? 1u : 0u);
+          if (commit_bar) tc_commit(commit_bar);
+        }
+        __syncwarp();
       };
-      auto issue_g2 = [&](int c, uint32_t k) {
+      auto issue_g2 = [&](int c, uint32_t k, uint32_t stage_free_bar) {
         const uint32_t b = (uint32_t)(c & 1);
         const uint32_t xs = __shfl_sync(0xffffffffu, stage_of(k), 0);
+        if (elect_one()) {
+          const uint64_t b_base = tc_desc(xs, K::SG, K::SF);
+          const uint32_t a_h = tmu + K::COL_H + b * TC_CHUNK, a_r2 = tmu + K::COL_R2 + b * 64;
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
+          for (int q = 0; q < 3; ++q)
 #pragma unroll
-          for (int w = 0; w < TC_NQ; ++w)
+            for (int w = 0; w < TC_NQ; ++w)
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              const uint32_t a_t = pa_sel[q] == 0 ? tmu + K::COL_H + b * TC_CHUNK + 32 * w + 8 * kk
-                                                  : tmu + K::COL_R2 + b * 64 + 16 * w + 8 * kk;
-              const uint32_t og = 4 * w + 2 * kk;
-              const uint64_t bd = tc_desc(xs + pb_sel[q] * K::XCHUNK + og * K::SG, K::SG, K::SF);
-              mma_ts_if(issue, tmu + K::COL_G, a_t, bd, K::IDESC_G2, (c | q | w | kk) ? 1u : 0u);
-            }
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t a_t = pa_sel[q] == 0 ? a_h + 32 * w + 8 * kk : a_r2 + 16 * w + 8 * kk;
+                const uint32_t og = 4 * w + 2 * kk;
+                mma_ts(tmu + K::COL_G, a_t, b_base + (uint64_t)((pb_sel[q] * K::XCHUNK + og * K::SG) >> 4), K::IDESC_G2,
+                       (c | q | w | kk) ? 1u : 0u);
+              }
+          tc_commit(stage_free_bar);
+        }
+        __syncwarp();
       };
       for (int s = 0; s < n_lf; ++s) {
         const uint32_t k0 = cnt;
-        mbar_wait(bar_a, pa); pa ^= 1;
+        tcd_nb_sync(nb0);
         tc_fence_after();
-        issue_g1(0, k0); tc_commit_if(issue, bar_h0);
-        if (NCH > 1) { issue_g1(1, k0 + 1); tc_commit_if(issue, bar_h0 + 8); }
+        issue_g1(0, k0, bar_h0);
+        if (NCH > 1) issue_g1(1, k0 + 1, bar_h0 + 8);
         for (int c = 0; c < NCH; ++c) {
           const int b = c & 1;
-          mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
+          tcd_nb_sync(nb0 + 1 + b);
           tc_fence_after();
-          issue_g2(c, k0 + c);
-          tc_commit_if(issue, bar_xe + 8 * ((k0 + c) % TCS_NSTAGE));
-          if (c + 2 < NCH) { issue_g1(c + 2, k0 + c + 2); tc_commit_if(issue, bar_h0 + 8 * b); }
+          issue_g2(c, k0 + c, bar_xe + 8 * ((k0 + c) % TCS_NSTAGE));
+          if (c + 2 < NCH) issue_g1(c + 2, k0 + c + 2, bar_h0 + 8 * b);
           if (c == NCH - 1) tc_commit_if(issue, bar_g);
         }
         cnt += NCH;
@@ -344,7 +358,7 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         }
         fence_async_smem();
         tc_fence_before();
-        mbar_arrive(bar_a);
+        tcd_nb_arrive(3 + 3 * tile);
         TCD_TICK(1)   // site forward + A operand
         float lik = 0.f;
         for (int c = 0; c < NCH; ++c) {
@@ -363,7 +377,7 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           TCD_ST16(tq + K::COL_R2 + b * 64 + 32 * pp, 16, r2);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
-          mbar_arrive(bar_r0 + 8 * b);
+          tcd_nb_arrive(4 + 3 * tile + b);
           TCD_TICK(4)   // sigmoid + split + st
         }
         mbar_wait(bar_g, pg); pg ^= 1;
