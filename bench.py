@@ -285,6 +285,13 @@ def main():
         flop = FLOP_PER_GRAD.get(args.features, 4.0 * 1000 * args.features)
         achieved_tf = evals_per_step * args.steps * flop / (ms * 1e-3) / 1e12   # this rank's kernel
         peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        # the pipe that actually binds the dominant kernel: MUFU ops per observation on the XU pipe,
+        # 16 results / clk / SM (profiles/micro/pipes.cu), on the SMs the 128-chain tiles occupy
+        n_pad = (1000 + 127) // 128 * 128
+        mufu_per_obs = (1.0 + 0.25 + 0.25 / L) if args.features <= 32 else (2.0 + 1.0 / L)
+        sms_used = min(148, (C + 127) // 128)
+        f_clk = 1e6 * (clocks.get("sm_mhz") or pk.get("sm_max_mhz", 1965.0))
+        xu_roof = sms_used * f_clk / (n_pad * mufu_per_obs / 16.0)
         line = {
             "metric": metric, "value": value, "unit": "grad_evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -298,7 +305,13 @@ def main():
                          "traffic": NCU_TRAFFIC_DEFAULT_WORKLOAD if (C, S, args.features, args.num_burnin_steps) ==
                          (16384, 1000, 25, 500) else None,
                          "note": "algorithmic fp32 flop (%.3g per grad eval) / measured dense bf16 cuBLAS peak (%s, "
-                                 "sustained); per GPU" % (flop, pk_src)},
+                                 "sustained); per GPU" % (flop, pk_src),
+                         "binding_pipe": {"pipe": "xu (MUFU), co-limited by instruction dispatch",
+                                          "achieved": value / world, "peak": xu_roof, "unit": "grad_evals/s per GPU",
+                                          "frac": value / world / xu_roof,
+                                          "note": "%.4g MUFU ops per observation x %d padded observations, 16 MUFU "
+                                                  "results/clk/SM (measured), %d SMs occupied by the 128-chain tiles, "
+                                                  "SM clock sampled under load" % (mufu_per_obs, n_pad, sms_used)}},
             "ess": {"ess_per_sec": ess_per_sec, "ess_per_1000_grads_mean": ess_per_1000,
                     "acceptance_rate": acc_rate, "rhat_max": None if res.rhat is None else float(np.nanmax(res.rhat))},
             "wall_s_timed_region": wall,
