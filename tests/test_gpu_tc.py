@@ -132,6 +132,48 @@ def test_tcs_single_leapfrog_gradient(model, method):
     assert (err < allow).all(), (err, allow)
 
 
+@pytest.mark.parametrize("n,f", [(100, 7), (128, 25), (300, 25), (1153, 32), (300, 33), (517, 64), (1000, 3)])
+def test_tcs_ragged_shapes(n, f):
+    """Chunk counts 1, 3 (odd), 10 and feature counts at the edges of the two kernel variants (F <= 32 / F <= 64,
+    balanced ranges 7 = 2+2+2+1, 33 = 9+8+8+8, 3 = 1+1+1+0): gradient to 1e-5 and the log-joint value through a pinned
+    Metropolis test, against the fp64 oracle."""
+    from autoreparam_b200 import data as arp_data, models as arp_models
+    raw = arp_data.synthetic_german_credit(n=n, f=f, seed=n * 100 + f)
+    mc = arp_models.from_data(MODEL, raw)
+    D, C = mc.num_coords, 130          # two CTAs, the second one with two valid chains
+    a, b = common.ab_for("VIP_ab", D)
+    z0 = common.random_states(MODEL, D, C, seed=n + f, scale=0.3).astype(np.float32).astype(np.float64)
+    fgrad = lambda zz: O.log_joint_and_grad(MODEL, raw, zz, a, b)
+    lp0, g_ref = fgrad(z0)
+    eps = 2.0 ** -7
+    out = engine.hmc_run(mc, z0, np.full(D, eps), a, b, num_leapfrog_steps=1, num_results=1, num_burnin_steps=0,
+                         num_adaptation_steps=0, ext_momenta=np.zeros((1, C, D)), ext_log_u=np.full((1, C), -1e30),
+                         want_orig=True, engine=engine.ENGINE_TCGEN05_STREAM)
+    assert out["is_accepted"].all()
+    g_tc = (out["samples_orig"][0].astype(np.float64) - z0) / (0.5 * eps * eps)
+    err = np.abs(g_tc - g_ref).max(axis=1)
+    allow = 1e-5 * np.maximum(np.abs(g_ref).max(axis=1), 1.0) + 2.0 ** -23 * np.abs(z0).max() / (0.5 * eps * eps)
+    assert (err < allow).all(), (err / allow).max()
+    # value of the log-joint: two leapfrog steps with random momenta, log u just below / above the oracle's log alpha
+    rng = np.random.default_rng(n + 7 * f)
+    L, eps = 2, 1e-3
+    mom = rng.standard_normal((1, C, D))
+    g = g_ref
+    v, x = mom[0].copy(), z0.copy()
+    for _ in range(L):
+        v = v + 0.5 * eps * g
+        x = x + eps * v
+        lpx, g = fgrad(x)
+        v = v + 0.5 * eps * g
+    la = lpx - lp0 + 0.5 * (mom[0] ** 2).sum(1) - 0.5 * (v ** 2).sum(1)
+    tol = 2e-3 + 5e-6 * np.abs(lpx)
+    for sign, want in ((-1.0, 1), (1.0, 0)):
+        o2 = engine.hmc_run(mc, z0, np.full(D, eps), a, b, num_leapfrog_steps=L, num_results=1, num_burnin_steps=0,
+                            num_adaptation_steps=0, ext_momenta=mom, ext_log_u=(la + sign * tol)[None, :],
+                            engine=engine.ENGINE_TCGEN05_STREAM)
+        assert (o2["is_accepted"][0] == want).all(), (sign, o2["is_accepted"][0])
+
+
 @pytest.mark.parametrize("eng", ["stream", "dual"])
 @pytest.mark.parametrize("s0", [0.2, 0.35, 0.6])
 def test_tcs_confident_logits_gradient(eng, s0):
