@@ -77,19 +77,27 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
                          num_adaptation_steps=num_adaptation_steps, seed=seed, chain_offset=chain_offset,
                          want_final=False, engine=engine_kind, precision=precision)
     ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
+    # R-hat from the per-chain moments, reduced on the device ([C, D] -> [D], fp64): util.rhat_from_moments
+    rhat_dev = None
+    if C > 1:
+        s_ = float(num_samples)
+        w_ = var_dev.double().mul_(s_ / (s_ - 1.0)).mean(dim=0)
+        b_over_n = mean_dev.double().var(dim=0, unbiased=True)
+        rhat_dev = torch.sqrt(((s_ - 1.0) / s_ * w_ + b_over_n) / w_)
     # device -> host through pinned buffers, one synchronisation: only what the caller consumes
-    host = [_pinned_like(t, tag) for tag, t in enumerate((ess_dev, out["is_accepted"], mean_dev, var_dev,
-                                                          out["step_mult"], out["accept_count"]))]
-    for h, t in zip(host, (ess_dev, out["is_accepted"], mean_dev, var_dev, out["step_mult"], out["accept_count"])):
+    dev_out = [ess_dev, out["is_accepted"], out["step_mult"], out["accept_count"]] + ([rhat_dev] if C > 1 else [])
+    host = [_pinned_like(t, tag) for tag, t in enumerate(dev_out)]
+    for h, t in zip(host, dev_out):
         h.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    ess_flat, is_acc_u8, mean_h, var_h, step_mult, accept_count = [h.numpy().copy() for h in host]
+    ess_flat, is_acc_u8, step_mult, accept_count = [h.numpy().copy() for h in host[:4]]
+    rhat = host[4].numpy().copy() if C > 1 else None
     is_acc = is_acc_u8.view(np.bool_)
     samples = None
     if num_chains_to_save > 0:
         samples = mc.split(out["samples"][:, :num_chains_to_save].cpu().numpy())
     res = HmcResult(ess=mc.split(ess_flat), is_accepted=is_acc, samples=samples,
-                    rhat=util.rhat_from_moments(mean_h, var_h, num_samples) if C > 1 else None,
+                    rhat=rhat,
                     step_mult=step_mult, accept_count=accept_count,
                     num_transitions=out["num_transitions"], ess_flat=ess_flat)
     if keep_on_device:

@@ -253,7 +253,7 @@ def main():
     target = graphs.TargetGraph(mc, args.method, a, b, False)
     step_sizes = mc.split(sigma_q)
     h2d = z0.nbytes + eps0.astype(np.float32).nbytes + 2 * D * 4
-    d2h = C * D * 4 * 3 + S * C + C * 8
+    d2h = C * D * 4 + S * C + C * 8 + D * 8   # ESS [C, D], is_accepted [S, C] u8, step_mult + accept_count [C], R-hat [D] f64
     inference.hmc(target, mc, step_sizes, z0, num_leapfrog_steps=L, num_samples=S,
                   num_burnin_steps=args.num_burnin_steps, num_adaptation_steps=args.num_adaptation_steps,
                   seed=1, chain_offset=rank * C, device=dev, engine_kind=args.engine)
