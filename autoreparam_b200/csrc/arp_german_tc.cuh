@@ -100,19 +100,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
 }
-// same wait with an explicit suspend-time hint (ns): the waiting thread stays suspended until the phase completes
-// instead of re-polling every system-default time-out.  Used by the single-lane MMA-issuer / producer loops, whose
-// polling otherwise competes for issue slots with the four worker warps of their SM sub-partition.
-__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
-  } while (!ok);
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

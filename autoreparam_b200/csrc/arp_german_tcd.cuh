@@ -149,7 +149,6 @@ k_german_tcd_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       const uint32_t bar_a = sbase + K::BAR + tl * 128, bar_h0 = bar_a + 8, bar_r0 = bar_a + 24, bar_g = bar_a + 40;
       const uint32_t bar_xf = bar_a + 48, bar_xe = bar_xf + 8 * TCS_NSTAGE;
       const uint32_t ring = sbase + K::RING + tl * TCS_NSTAGE * K::STAGE;
-      uint32_t pa = 0, pr[2] = {0, 0};
       const uint32_t sA[2] = {sbase + K::A1 + tl * K::AIMG, sbase + K::A2 + tl * K::AIMG};
       const int pa_sel[3] = {0, 0, 1}, pb_sel[3] = {0, 1, 0};
       const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy for the uniform datapath

@@ -16,11 +16,6 @@
 namespace arp {
 
 #define TCS_NSTAGE 3
-#ifdef TCS_PARK
-#define TCS_ROLE_WAIT mbar_wait_parked   // measured: no gain (-0.5 %)
-#else
-#define TCS_ROLE_WAIT mbar_wait
-#endif
 // Worker -> MMA-issuer hand-offs ("A operand written", "residual of chunk c stored") use hardware NAMED barriers:
 // the 512 workers bar.arrive, the issuer warp bar.sync's and is descheduled until the last arrival.  With an
 // mbarrier the issuer's try_wait returned immediately and its BRA / YIELD / TRYWAIT spin loop was 13.6 % of all
@@ -224,7 +219,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       for (int s = 0; s < n_lf; ++s)
         for (int c = 0; c < NCH; ++c, ++cnt) {
           const uint32_t st = cnt % TCS_NSTAGE, use = cnt / TCS_NSTAGE;
-          if (use > 0) TCS_ROLE_WAIT(bar_xe + 8 * st, (use - 1) & 1);
+          if (use > 0) mbar_wait(bar_xe + 8 * st, (use - 1) & 1);
           mbar_expect_tx(bar_xf + 8 * st, K::STAGE);
           bulk_g2s(sbase + K::RING + st * K::STAGE, tp.img + (size_t)c * K::STAGE, K::STAGE, bar_xf + 8 * st);
         }
@@ -234,14 +229,13 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     // =========================== MMA issuer (warp-uniform loop, lane 0 issues) ===========================
     {
       const uint32_t issue = lane == 0 ? 1u : 0u;   // all lanes run the loop; lane 0 issues
-      uint32_t pa = 0, pr[2] = {0, 0};
       const uint32_t sA[2] = {sbase + K::A1, sbase + K::A2};
       const int pa_sel[3] = {0, 0, 1}, pb_sel[3] = {0, 1, 0};
       const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy for the uniform datapath
       uint32_t cnt = 0;  // global chunk counter of the next GEMM1 to issue
       auto stage_of = [&](uint32_t k) { return sbase + K::RING + (k % TCS_NSTAGE) * K::STAGE; };
       auto issue_g1 = [&](int c, uint32_t k, uint32_t commit_bar) {
-        TCS_ROLE_WAIT(bar_xf + 8 * (k % TCS_NSTAGE), (k / TCS_NSTAGE) & 1);
+        mbar_wait(bar_xf + 8 * (k % TCS_NSTAGE), (k / TCS_NSTAGE) & 1);
         tc_fence_after();
         const uint32_t d = tmu + K::COL_H + (uint32_t)(c & 1) * TC_CHUNK;
         const uint32_t xs = __shfl_sync(0xffffffffu, stage_of(k), 0);
