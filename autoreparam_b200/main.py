@@ -224,9 +224,14 @@ def run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False):
             "acceptance_rate": float(acceptance_rate), "mcmc_time": mcmc_time, "num_samples": FLAGS.num_samples,
             "num_burnin_steps": FLAGS.num_burnin_steps})
     else:
+        # superset of main.py:375-391: analyze.py:44-50 reads num_leapfrog_steps; ESS per second (un-normalised minimum
+        # ESS summed over chains / wall time) and the largest R-hat of this rank's chains are new
+        min_ess_raw = np.nan_to_num(ess_flat).min(axis=1)
         save_hmc_results(file_path=file_path, ess_min=float(ess_min), sem_min=float(sem_min),
                          acceptance_rate=float(acceptance_rate), mcmc_time_sec=mcmc_time,
-                         num_leapfrog_steps=FLAGS.num_leapfrog_steps)   # superset: analyze.py:44-50 reads it
+                         num_leapfrog_steps=FLAGS.num_leapfrog_steps,
+                         ess_per_sec=float(min_ess_raw.sum() / mcmc_time),
+                         rhat_max=None if res.rhat is None else float(np.nanmax(res.rhat)))
         save_ess(file_path_base=file_path[:-5], samples=samples, param_names=param_names,
                  normalized_ess_final=normalized_ess_final, num_chains_to_save=FLAGS.num_chains_to_save)
 

@@ -110,3 +110,13 @@ def test_cli_end_to_end_8schools(tmp_path, capsys):
     with pytest.raises(Exception, match="Run VI first"):
         _run(["--model=8schools", "--results_dir=" + str(tmp_path / "empty"), "--inference=HMC", "--method=CP",
               "--num_leapfrog_steps=2"])
+    # the results-dir reader (mirror of analyze.py) finds the writer's file names and validates the directory
+    from autoreparam_b200 import analyze
+    lines = []
+    rc = analyze.main(["--results_dir", str(tmp_path), "--model", "8schools_", "--elbos", "--ess", "--validate"],
+                      log=lambda x: lines.append(str(x)))
+    assert rc == 0 and " ******  8schools_  ****** ok" in lines
+    assert any(l.endswith(": NCP") and "+/-" in l for l in lines)                      # ELBO line
+    assert any(l.endswith(": NCP (%d leapfrog steps)" % ncp["num_leapfrog_steps"][0]) for l in lines)
+    assert any(l.endswith(": i (%d leapfrog steps)" % il["num_leapfrog_steps"][0]) for l in lines)
+    assert any("ess_per_sec" in l and "rhat_max" in l for l in lines)
