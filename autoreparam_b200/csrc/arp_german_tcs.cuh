@@ -53,7 +53,11 @@ struct Tcs {
   static constexpr uint32_t PAR = XS + NLOC * TC_WORKERS * 4;       // float[3][2 NF + 4]
   static constexpr uint32_t BAR = PAR + 4 * (2 * NF + 4) * 4;       // 6 + 2 * NSTAGE mbarriers (PAR: a, b, eps0)
   static constexpr uint32_t TMEM_PTR = BAR + 16 * 8;
-  static constexpr uint32_t BYTES = TMEM_PTR + 16;
+  // NF = 32: momenta of the NEXT transition, float[NLOC][512] (drawn while the workers wait for the first GEMM1 of the
+  // last leapfrog step; NF = 64 has no shared memory left and draws them at the start of the transition)
+  static constexpr bool MOM_AHEAD = (NF == 32);
+  static constexpr uint32_t MOM = TMEM_PTR + 16;
+  static constexpr uint32_t BYTES = MOM + (MOM_AHEAD ? NLOC * TC_WORKERS * 4 : 0);
   // TMEM columns
   static constexpr uint32_t COL_H = 0, COL_G = 256, COL_R2 = 320;
   static constexpr uint32_t IDESC_G1 = (1u << 4) | ((uint32_t)(TC_CHUNK >> 3) << 17) | ((128u >> 4) << 24);
@@ -161,6 +165,48 @@ __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1,
     if (g + 2 < 8) stage_b(g + 2);
     stage_c(g);
   }
+}
+
+// Standard-normal momenta of transition `tgen` for the coordinates of one worker, written to dst[i * TC_WORKERS].
+// Philox block j holds coordinates 4j .. 4j+3; the worker's ranges are d = 0, [1 + fstart, .. + nf) and
+// [1 + F + fstart, .. + nf).  All blocks are generated unconditionally in unrolled loops (independent chains the
+// scheduler can interleave); only the stores are predicated.  (Skipping the blocks that lie entirely outside the
+// ranges with a warp-uniform test was measured 1.5 % slower: the branches serialise the blocks.)
+// NOINLINE: a real call keeps the ~40 registers of the Philox rounds out of the register allocation of the leapfrog
+// loop it is called from (inlined there it caused spills in the hot loop: -6 %).
+template <int FPW, bool NOINLINE>
+__device__ __forceinline__ void tcs_draw_momenta_body(uint64_t seed, uint32_t gchain, uint32_t tgen, int fstart, int nf, int F,
+                                                      float* dst, int parts) {
+  // parts: bit 0 = coordinate 0 and the log-scale range, bit 1 = the coefficient range (the draw is split over the wait
+  // windows of the last two leapfrog steps)
+  if (parts & 1) {
+    float n4[4];
+    philox_normal4_fast(seed, gchain, tgen, 0u, n4);
+    dst[0] = n4[0];
+  }
+#pragma unroll
+  for (int seg = 1; seg < 3; ++seg) {
+    if (!(parts & seg)) continue;
+    const int d_lo = seg == 1 ? 1 + fstart : 1 + F + fstart;
+    const int d_hi = d_lo + nf;
+    const int i_lo = seg == 1 ? 1 : 1 + FPW;
+#pragma unroll
+    for (int jj = 0; jj < FPW / 4 + 1; ++jj) {
+      const int j = (d_lo >> 2) + jj;
+      float n4[4];
+      philox_normal4_fast(seed, gchain, tgen, (unsigned int)j, n4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int d = 4 * j + q;
+        if (d >= d_lo && d < d_hi) dst[(i_lo + d - d_lo) * TC_WORKERS] = n4[q];
+      }
+    }
+  }
+}
+template <int FPW>
+__device__ __noinline__ void tcs_draw_momenta_call(uint64_t seed, uint32_t gchain, uint32_t tgen, int fstart, int nf, int F,
+                                                   float* dst, int parts) {
+  tcs_draw_momenta_body<FPW, true>(seed, gchain, tgen, fstart, nf, F, dst, parts);
 }
 
 // GAMMA = german_credit_gammascale (models.py:930-945): beta_log_scales is not a Normal site (never
@@ -356,6 +402,10 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
 #define TCS_TICK(i)
 #endif
 
+    float* mom_next = reinterpret_cast<float*>(smem + K::MOM) + tid;
+    const bool mom_ahead = K::MOM_AHEAD && !p.ext_momenta;
+    if (mom_ahead) tcs_draw_momenta_call<FPW>(p.seed, gchain, (unsigned int)p.t_begin, fstart, nf, F, mom_next, 3);
+
     for (int t = 0; t < p.T; ++t) {
       const int tg = p.t_begin + t;
       TCS_TICK(9)
@@ -372,33 +422,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
 #pragma unroll
         for (int i = 0; i < NLOC; ++i)
           if (owned(i)) xs[i * TC_WORKERS] = mom[dof(i)];
-      } else {
-        // Philox block j holds coordinates 4j .. 4j+3; my ranges are d = 0, [1+FPW w, ..+nf), [1+F+FPW w, ..+nf).
-        // All blocks are generated unconditionally in unrolled loops (independent chains the scheduler can
-        // interleave); only the stores are predicated.  (Skipping the blocks that lie entirely outside my ranges with a
-        // warp-uniform test was measured 1.5 % slower: the branches serialise the blocks.)
-        {
-          float n4[4];
-          philox_normal4_fast(p.seed, gchain, (unsigned int)tg, 0u, n4);
-          xs[0] = n4[0];
-        }
-#pragma unroll
-        for (int seg = 1; seg < 3; ++seg) {
-          const int d_lo = seg == 1 ? 1 + fstart : 1 + F + fstart;
-          const int d_hi = d_lo + nf;
-          const int i_lo = seg == 1 ? 1 : 1 + FPW;
-#pragma unroll
-          for (int jj = 0; jj < FPW / 4 + 1; ++jj) {
-            const int j = (d_lo >> 2) + jj;
-            float n4[4];
-            philox_normal4_fast(p.seed, gchain, (unsigned int)tg, (unsigned int)j, n4);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int d = 4 * j + q;
-              if (d >= d_lo && d < d_hi) xs[(i_lo + d - d_lo) * TC_WORKERS] = n4[q];
-            }
-          }
-        }
+      } else if (!K::MOM_AHEAD) {
+        tcs_draw_momenta_body<FPW, false>(p.seed, gchain, (unsigned int)tg, fstart, nf, F, xs, 3);
       }
       TCS_TICK(10)
       float ke0 = 0.f, ke1 = 0.f, ke0_tot = 0.f, ke1_tot = 0.f;
@@ -407,7 +432,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         for (int i = 0; i < NLOC; ++i) {
           if (owned(i)) {
             const int d = dof(i);
-            float vi = xs[i * TC_WORKERS];
+            float vi = mom_ahead ? mom_next[i * TC_WORKERS] : xs[i * TC_WORKERS];
             if (i > 0 || w == 0) ke0 = fmaf(vi, vi, ke0);
             const float e = pe_s[d] * mult;
             vi = vi + 0.5f * e * gq0[i];
@@ -454,6 +479,14 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         fence_async_smem();
         tc_fence_before();
         nb_arrive(TCS_NB_A);
+        // the momenta of the next transition do not depend on the state: draw them now, while GEMM1 of chunk 0 runs
+        // and every worker of the CTA would otherwise idle (~2.3k clk per step); half of the draw in each of the last
+        // two leapfrog steps (all of it in the only step when L = 1)
+        {
+          const int parts = (last ? 2 : 0) | ((l == p.L - 2 || p.L == 1) ? 1 : 0);
+          if (mom_ahead && parts && t + 1 < p.T)
+            tcs_draw_momenta_call<FPW>(p.seed, gchain, (unsigned int)(tg + 1), fstart, nf, F, mom_next, parts);
+        }
         TCS_TICK(1)
         float lik = 0.f;
         for (int c = 0; c < NCH; ++c) {

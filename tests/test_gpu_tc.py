@@ -174,6 +174,24 @@ def test_tcs_ragged_shapes(n, f):
         assert (o2["is_accepted"][0] == want).all(), (sign, o2["is_accepted"][0])
 
 
+@pytest.mark.parametrize("L", [1, 2, 3, 5])
+def test_tcs_internal_momenta_any_leapfrog_count(L):
+    """The streaming engine draws the Philox momenta of transition t + 1 inside transition t (split over the wait
+    windows of its last two leapfrog steps; all in the only step when L = 1): with small steps the run must
+    reproduce the SIMT engine, which draws them at the start of each transition, to fp32 round-off."""
+    C, S = 128 + 9, 4
+    mc, raw, D, a, b, z0 = _case_model("german_synth", "NCP", C, seed=61)
+    eps0 = np.full(D, 0.004)
+    kw = dict(num_leapfrog_steps=L, num_results=S, num_burnin_steps=1, num_adaptation_steps=0, seed=123, chain_offset=3)
+    o1 = engine.hmc_run(mc, z0, eps0, a, b, engine=engine.ENGINE_SIMT, **kw)
+    o2 = engine.hmc_run(mc, z0, eps0, a, b, engine=engine.ENGINE_TCGEN05_STREAM, **kw)
+    same = (o1["is_accepted"] == o2["is_accepted"]).all(axis=0)
+    assert same.mean() > 0.98, same.mean()
+    assert o1["is_accepted"].mean() > 0.5
+    err = common.rel_err(o2["samples"][:, same].reshape(-1, D), o1["samples"][:, same].reshape(-1, D))
+    assert err.max() < 2e-4, err.max()
+
+
 @pytest.mark.parametrize("eng", ["stream", "dual"])
 @pytest.mark.parametrize("s0", [0.2, 0.35, 0.6])
 def test_tcs_confident_logits_gradient(eng, s0):
