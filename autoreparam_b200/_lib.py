@@ -59,7 +59,7 @@ class ViBuffers(C.Structure):
 
 
 # every symbol include/autoreparam_b200.h declares
-EXPORTS = ["arp_model_create", "arp_model_destroy", "arp_model_num_coords", "arp_log_joint_grad",
+EXPORTS = ["arp_model_create", "arp_model_destroy", "arp_model_num_coords", "arp_log_joint_grad", "arp_log_joint_grad_engine",
            "arp_hmc_num_transitions", "arp_hmc_run", "arp_hmc_interleaved_run", "arp_ess", "arp_vi_run", "arp_kernel_launch_count",
            "arp_last_error", "arp_precision", "arp_release_cached_memory"]
 
@@ -110,6 +110,8 @@ def load(precision="f32"):
     lib.arp_model_num_coords.restype = i32
     lib.arp_log_joint_grad.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, vp]
     lib.arp_log_joint_grad.restype = i32
+    lib.arp_log_joint_grad_engine.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, i32, i32, vp]
+    lib.arp_log_joint_grad_engine.restype = i32
     lib.arp_hmc_num_transitions.argtypes = [C.POINTER(HmcConfig)]
     lib.arp_hmc_num_transitions.restype = i64
     lib.arp_hmc_run.argtypes = [vp, C.POINTER(HmcConfig), vp, vp, i64, C.POINTER(HmcBuffers), i32, vp]

@@ -1,0 +1,263 @@
+// Effective sample size through a shared-memory FFT: the autocovariance of EVERY lag in O(N log N) per series.
+//
+// Restates [TFP 0.7] tfp.mcmc.effective_sample_size(states, filter_threshold=0) (reference inference.py:240,327)
+// the way TFP computes it -- zero-pad the centred series to N >= 2S, power spectrum, inverse transform:
+//   c_k = sum_t x_t x_{t+k},  rho_k = (c_k / (S - k)) / (c_0 / S),  every lag from the first rho_k < 0 on is dropped,
+//   ESS = S / (-1 + 2 sum_k (S - k)/S rho_k).
+// The direct method of arp_ess.cuh costs S K multiply-adds per series (K = first negative lag, ~400 on slowly mixing
+// chains: 23 ms for 836k series x 1000 samples, 7 x the algorithmic HBM traffic).  Here:
+//   * a CTA owns ARP_FFT_G adjacent series of the [S][C*D] sample array and reads them straight from it, row by row
+//     (ARP_FFT_G floats = whole 32-byte sectors per row): the samples cross HBM exactly once and no transposed copy
+//     exists;
+//   * two REAL series ride in one COMPLEX transform (z = x1 + i x2; X1 = (Z_k + conj Z_{N-k}) / 2, X2 = (Z_k - conj
+//     Z_{N-k}) / 2i), their power spectra are packed again as P1 + i P2, and because a power spectrum is real and even
+//     its inverse transform equals its forward transform: ONE routine, c1 = Re, c2 = Im of the second pass;
+//   * N = 2048 = 16 x 16 x 8: three Stockham autosort passes, one radix-16 / radix-8 butterfly per thread per pass,
+//     data in shared memory between passes (padded against bank conflicts), 128 threads per transform.
+// S <= 1024 only (N = 2048 covers every lag of the linear autocovariance); longer series take the direct kernel.
+#pragma once
+#include "arp_common.cuh"
+
+namespace arp {
+
+#define ARP_FFT_N 2048
+#define ARP_FFT_MAXS 1024
+#define ARP_FFT_G 8                       // series per CTA (4 complex transforms)
+#define ARP_FFT_TPF 128                   // threads per transform
+#define ARP_FFT_THREADS (ARP_FFT_TPF * ARP_FFT_G / 2)
+#ifndef ARP_FFT_MINB
+#define ARP_FFT_MINB 2                    // resident CTAs per SM the register allocation aims at
+#endif
+#define ARP_FFT_PAD(i) ((i) + ((i) >> 4)) // one padding element per 16: the stride-16 stores of the first pass spread over all banks
+#define ARP_FFT_BUF (ARP_FFT_N + ARP_FFT_N / 16 + 4)   // + 4: the four transforms of a CTA start 8 banks apart
+
+template <typename T> struct cplx { T x, y; };
+template <typename T> __host__ __device__ __forceinline__ cplx<T> cmul(cplx<T> a, cplx<T> b) {
+  return cplx<T>{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T> __host__ __device__ __forceinline__ cplx<T> cadd(cplx<T> a, cplx<T> b) { return cplx<T>{a.x + b.x, a.y + b.y}; }
+template <typename T> __host__ __device__ __forceinline__ cplx<T> csub(cplx<T> a, cplx<T> b) { return cplx<T>{a.x - b.x, a.y - b.y}; }
+// multiplication by -i (forward transform: e^{-i pi/2})
+template <typename T> __host__ __device__ __forceinline__ cplx<T> cmul_mi(cplx<T> a) { return cplx<T>{a.y, -a.x}; }
+
+// exp(-2 pi i num / den)
+template <typename T> __host__ __device__ __forceinline__ cplx<T> twiddle(int num, int den) {
+#ifdef __CUDA_ARCH__
+  T s, c;
+  if constexpr (sizeof(T) == 8) sincospi((T)(-2.0) * (T)num / (T)den, &s, &c);
+  else sincospif((T)(-2.0f) * (T)num / (T)den, &s, &c);
+  return cplx<T>{c, s};
+#else
+  const double ang = -2.0 * 3.14159265358979323846 * (double)num / (double)den;
+  return cplx<T>{(T)cos(ang), (T)sin(ang)};
+#endif
+}
+
+// in-place 4-point DFT (forward), natural order out
+template <typename T> __host__ __device__ __forceinline__ void dft4(cplx<T>& a0, cplx<T>& a1, cplx<T>& a2, cplx<T>& a3) {
+  const cplx<T> s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = cmul_mi(csub(a1, a3));
+  a0 = cadd(s02, s13); a2 = csub(s02, s13);
+  a1 = cadd(d02, d13); a3 = csub(d02, d13);
+}
+template <typename T> __host__ __device__ __forceinline__ void dft2(cplx<T>& a0, cplx<T>& a1) {
+  const cplx<T> s = cadd(a0, a1), d = csub(a0, a1);
+  a0 = s; a1 = d;
+}
+
+// R-point DFT of v[0..R), natural order in and out; R = 16 (4 x 4) or 8 (2 x 4).
+// n = R1 n2 + n1 (n1 < R1), k = k1 R2' ... written out for the two radices to keep everything in registers.
+template <typename T> __host__ __device__ __forceinline__ void dft16(cplx<T>* v) {
+  // step 1: four 4-point DFTs over n2 (stride 4) for each n1
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1) dft4(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
+  // v[n1 + 4 k2] now holds the k2-th output of column n1; twiddle by W16^(n1 k2)
+  const T c1 = (T)0.92387953251128673848, s1 = (T)0.38268343236508978178, h = (T)0.70710678118654752440;
+  const cplx<T> w1{c1, -s1}, w2{h, -h}, w3{s1, -c1}, w6{-h, -h}, w9{-c1, s1};
+  v[1 + 4] = cmul(v[1 + 4], w1);  v[1 + 8] = cmul(v[1 + 8], w2);  v[1 + 12] = cmul(v[1 + 12], w3);
+  v[2 + 4] = cmul(v[2 + 4], w2);  v[2 + 8] = cmul_mi(v[2 + 8]);   v[2 + 12] = cmul(v[2 + 12], w6);
+  v[3 + 4] = cmul(v[3 + 4], w3);  v[3 + 8] = cmul(v[3 + 8], w6);  v[3 + 12] = cmul(v[3 + 12], w9);
+  // step 2: four 4-point DFTs over n1 for each k2: output k = k2 + 4 k1 lands in v[4 k2 + k1]
+#pragma unroll
+  for (int k2 = 0; k2 < 4; ++k2) dft4(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
+  // v[4 k2 + k1] = X[k2 + 4 k1]: transpose to natural order
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = i + 1; j < 4; ++j) { const cplx<T> t = v[4 * i + j]; v[4 * i + j] = v[4 * j + i]; v[4 * j + i] = t; }
+}
+
+template <typename T> __host__ __device__ __forceinline__ void dft8(cplx<T>* v) {
+  // n = 2 n2 + n1 (n1 < 2, n2 < 4): 4-point DFTs over n2 for each n1
+  dft4(v[0], v[2], v[4], v[6]);
+  dft4(v[1], v[3], v[5], v[7]);
+  // v[n1 + 2 k2]; twiddle the n1 = 1 column by W8^k2
+  const T h = (T)0.70710678118654752440;
+  v[3] = cmul(v[3], cplx<T>{h, -h});
+  v[5] = cmul_mi(v[5]);
+  v[7] = cmul(v[7], cplx<T>{-h, -h});
+  // 2-point DFTs over n1: X[k2 + 4 k1]
+  dft2(v[0], v[1]); dft2(v[2], v[3]); dft2(v[4], v[5]); dft2(v[6], v[7]);
+  // v[2 k2 + k1] = X[k2 + 4 k1] -> natural order
+  const cplx<T> x0 = v[0], x4 = v[1], x1 = v[2], x5 = v[3], x2 = v[4], x6 = v[5], x3 = v[6], x7 = v[7];
+  v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
+}
+
+// One Stockham autosort pass of radix R over a length-N transform held in buf (padded indexing): butterfly j of N / R.
+// Ns = product of the radices of the earlier passes.  load: v[r] = x[j + r N/R] w^r, w = exp(-2 pi i (j mod Ns) / (Ns R));
+// store: y[(j / Ns) Ns R + (j mod Ns) + r Ns] = DFT_R(v)[r].   (Govindaraju et al., "High performance discrete Fourier
+// transforms on graphics processors", SC'08 -- the published algorithm; all reads of a pass precede its writes.)
+template <typename T, int R>
+__host__ __device__ __forceinline__ void stockham_load(const cplx<T>* buf, int j, int Ns, cplx<T>* v) {
+  const int k = j % Ns;
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = buf[ARP_FFT_PAD(j + r * (ARP_FFT_N / R))];
+  if (Ns > 1) {
+    const cplx<T> w = twiddle<T>(k, Ns * R);
+    cplx<T> wr = w;
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+      v[r] = cmul(v[r], wr);
+      wr = cmul(wr, w);
+    }
+  }
+}
+template <typename T, int R>
+__host__ __device__ __forceinline__ void stockham_store(cplx<T>* buf, int j, int Ns, const cplx<T>* v) {
+  const int k = j % Ns, base = (j / Ns) * Ns * R + k;
+#pragma unroll
+  for (int r = 0; r < R; ++r) buf[ARP_FFT_PAD(base + r * Ns)] = v[r];
+}
+
+#ifdef __CUDACC__
+// named barrier among the ARP_FFT_TPF threads of one transform (ids 1 .. G/2)
+__device__ __forceinline__ void fft_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ARP_FFT_TPF) : "memory"); }
+
+// forward transform of buf (length ARP_FFT_N, padded indexing) by the 128 threads of one group, in place
+template <typename T>
+__device__ __forceinline__ void fft2048(cplx<T>* buf, int t, int bar_id) {
+  cplx<T> v[16];
+  // pass 1: radix 16, Ns = 1 (no twiddles)
+  stockham_load<T, 16>(buf, t, 1, v);
+  dft16(v);
+  fft_bar(bar_id);
+  stockham_store<T, 16>(buf, t, 1, v);
+  fft_bar(bar_id);
+  // pass 2: radix 16, Ns = 16
+  stockham_load<T, 16>(buf, t, 16, v);
+  dft16(v);
+  fft_bar(bar_id);
+  stockham_store<T, 16>(buf, t, 16, v);
+  fft_bar(bar_id);
+  // pass 3: radix 8, Ns = 256: 256 butterflies, two per thread
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    stockham_load<T, 8>(buf, t + h * ARP_FFT_TPF, 256, v + 8 * h);
+    dft8(v + 8 * h);
+  }
+  fft_bar(bar_id);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) stockham_store<T, 8>(buf, t + h * ARP_FFT_TPF, 256, v + 8 * h);
+  fft_bar(bar_id);
+}
+
+// x: [S][n] samples (n = C * D series); ess / mean / var: [n].
+template <typename T>
+__global__ void __launch_bounds__(ARP_FFT_THREADS, ARP_FFT_MINB)
+k_ess_fft(const T* __restrict__ x, int S, long long n, T* __restrict__ ess, T* __restrict__ mean_out, T* __restrict__ var_out) {
+  extern __shared__ __align__(16) unsigned char ess_smem[];
+  cplx<T>* bufs = reinterpret_cast<cplx<T>*>(ess_smem);                                   // [G/2][ARP_FFT_BUF]
+  double* red = reinterpret_cast<double*>(ess_smem + sizeof(cplx<T>) * (ARP_FFT_G / 2) * ARP_FFT_BUF);   // [THREADS / 32][G] partial sums
+  __shared__ double mean_s[ARP_FFT_G];
+  __shared__ int kneg_s[ARP_FFT_G];
+  __shared__ double sum_s[ARP_FFT_G];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long i0 = (long long)blockIdx.x * ARP_FFT_G;
+  // ---- load: thread tid reads column j = tid % G of rows tid / G, tid / G + THREADS / G, ...
+  {
+    const int j = tid % ARP_FFT_G;
+    const bool col_ok = i0 + j < n;
+    T* dst = reinterpret_cast<T*>(bufs + (size_t)(j >> 1) * ARP_FFT_BUF) + (j & 1);
+    double part = 0;
+    for (int t = tid / ARP_FFT_G; t < ARP_FFT_N; t += ARP_FFT_THREADS / ARP_FFT_G) {
+      T v = 0;
+      if (t < S && col_ok) v = x[(size_t)t * n + i0 + j];
+      part += (double)v;
+      dst[2 * ARP_FFT_PAD(t)] = v;
+    }
+    // lanes with the same j: lane, lane ^ 8, ^ 16 (G = 8 divides 32)
+    part += __shfl_xor_sync(0xffffffffu, part, 8);
+    part += __shfl_xor_sync(0xffffffffu, part, 16);
+    if (lane < ARP_FFT_G) red[warp * ARP_FFT_G + lane] = part;
+  }
+  __syncthreads();
+  if (tid < ARP_FFT_G) {
+    double s = 0;
+    for (int w = 0; w < ARP_FFT_THREADS / 32; ++w) s += red[w * ARP_FFT_G + tid];
+    mean_s[tid] = s / S;
+    kneg_s[tid] = S;     // first lag with a negative autocorrelation (S = none)
+    sum_s[tid] = 0;
+    if (mean_out && i0 + tid < n) mean_out[i0 + tid] = (T)(s / S);
+  }
+  __syncthreads();
+  // ---- centre (only the S real samples; the padding stays 0)
+  {
+    const int j = tid % ARP_FFT_G;
+    T* dst = reinterpret_cast<T*>(bufs + (size_t)(j >> 1) * ARP_FFT_BUF) + (j & 1);
+    const double m = mean_s[j];
+    const T mh = (T)m, ml = (T)(m - (double)mh);
+    for (int t = tid / ARP_FFT_G; t < S; t += ARP_FFT_THREADS / ARP_FFT_G) {
+      T& r = dst[2 * ARP_FFT_PAD(t)];
+      r = (r - mh) - ml;
+    }
+  }
+  __syncthreads();
+  // ---- per pair of series: forward transform, power spectra, forward transform again
+  const int grp = tid / ARP_FFT_TPF, t = tid % ARP_FFT_TPF;
+  cplx<T>* buf = bufs + (size_t)grp * ARP_FFT_BUF;
+  fft2048<T>(buf, t, 1 + grp);
+  // W_k = |X1_k|^2 + i |X2_k|^2 with X1 = (Z_k + conj Z_{N-k}) / 2, X2 = (Z_k - conj Z_{N-k}) / (2 i); W_{N-k} = W_k
+  for (int k = t; k <= ARP_FFT_N / 2; k += ARP_FFT_TPF) {
+    const int km = (ARP_FFT_N - k) & (ARP_FFT_N - 1);
+    const cplx<T> zk = buf[ARP_FFT_PAD(k)], zm = buf[ARP_FFT_PAD(km)];
+    const T ar = (T)0.5 * (zk.x + zm.x), ai = (T)0.5 * (zk.y - zm.y);    // X1
+    const T br = (T)0.5 * (zk.y + zm.y), bi = (T)0.5 * (zm.x - zk.x);    // X2 = (Z_k - conj Z_m) / (2 i)
+    const cplx<T> w{ar * ar + ai * ai, br * br + bi * bi};
+    buf[ARP_FFT_PAD(k)] = w;
+    buf[ARP_FFT_PAD(km)] = w;
+  }
+  fft_bar(1 + grp);
+  fft2048<T>(buf, t, 1 + grp);
+  // buf[k] = N (c1_k + i c2_k) for k < S (the factor N cancels in rho)
+  // ---- ESS per series: 64 threads each
+  {
+    const int sidx = 2 * grp + (t >> 6);          // series within the CTA
+    const int u = t & 63;
+    const T* c = reinterpret_cast<const T*>(buf) + (t >> 6);
+    const double c0 = (double)c[0];
+    const double inv0 = (double)S / c0;
+    int kneg = S;
+    for (int k = u; k < S; k += 64) {
+      const double rho = (double)c[2 * ARP_FFT_PAD(k)] / (double)(S - k) * inv0;
+      if (rho < 0.0) { kneg = k; break; }          // k increases: the first negative lag this thread sees
+    }
+    if (c0 > 0.0) atomicMin(&kneg_s[sidx], kneg);
+    fft_bar(1 + grp);
+    const int kn = kneg_s[sidx];
+    double part = 0;
+    for (int k = u; k < kn; k += 64)
+      part += (double)(S - k) / S * ((double)c[2 * ARP_FFT_PAD(k)] / (double)(S - k) * inv0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((u & 31) == 0) atomicAdd(&sum_s[sidx], part);
+    fft_bar(1 + grp);
+    if (u == 0 && i0 + sidx < n) {
+      const double acov0 = c0 / ARP_FFT_N / S;
+      if (var_out) var_out[i0 + sidx] = (T)acov0;
+      // constant (or non-finite) series: TFP yields NaN
+      ess[i0 + sidx] = (c0 > 0.0) ? (T)((double)S / (-1.0 + 2.0 * sum_s[sidx])) : (T)NAN;
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace arp

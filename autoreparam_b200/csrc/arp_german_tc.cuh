@@ -1,34 +1,18 @@
-// tcgen05 engine: persistent HMC kernel for german_credit_lognormalcentered with
-// the design-matrix contractions on the 5th-generation tensor cores.
+// tcgen05 primitives shared by the German-credit tensor-core engine (arp_german_tcs.cuh): PTX wrappers
+// (mbarrier, tcgen05.mma / ld / st / commit, shared-memory matrix descriptors), the fp16 head / tail
+// split, MUFU-based site math and Box-Muller.
 //
 //   eta = X beta   (reference models.py:903 einsum)  ->  GEMM1  H[chain, obs] = B[chain, f] X[obs, f]^T
 //   gbeta = X^T r  (autodiff of :903-904)            ->  GEMM2  G[chain, f]  = R[chain, obs] X[obs, f]
 //
-// One CTA owns 128 chains (= the 128 TMEM lanes).  X stays resident in shared
-// memory for the whole run as ONE canonical no-swizzle core-matrix image that
-// serves GEMM1 as a K-major B operand and GEMM2 as an MN-major B operand.  The
-// residual R = y - sigmoid(H) never leaves the SM: the epilogue warps read H from
-// TMEM (tcgen05.ld), compute R and write it back to TMEM (tcgen05.st) as the
-// A operand of GEMM2 (tcgen05.mma with A in TMEM).
+// Precision: fp32 operands are split into an fp16 head and tail (x = x1 + x2, 22 significant bits) and
+// each contraction is three kind::f16 MMAs with fp32 accumulation (x1 b1 + x2 b1 + x1 b2) -- the
+// split-precision scheme of 3xTF32, done in fp16 because the f16 MMA rate is twice the tf32 rate and
+// the images are half the size.  Error per product ~2^-22, which holds the 1e-5 fp32 tolerance of the
+// log-joint gradient (tests/test_gpu_tc.py).
 //
-// Precision: fp32 operands are split into an fp16 head and tail (x = x1 + x2,
-// 22 significant bits) and each contraction is three kind::f16 MMAs with fp32
-// accumulation (x1 b1 + x2 b1 + x1 b2) -- the split-precision scheme of 3xTF32,
-// done in fp16 because (a) both X parts then fit in shared memory (128 KiB) and
-// (b) the f16 MMA rate is twice the tf32 rate.  Error per product ~2^-22, which
-// holds the 1e-5 fp32 tolerance of the log-joint gradient (tests/test_gpu_tc.py).
-//
-// Warp roles (544 threads): 16 worker warps in four "quarters" that all map
-// thread -> chain (TMEM lane = tid & 127): quarter w owns features [8w, 8w+8)
-// (their log-scale and coefficient coordinates: momentum in registers, proposal
-// in a private shared-memory column) and observation columns [32w, 32w+32) of
-// every 128-observation chunk; four warps per SM sub-partition hide the MUFU /
-// TMEM latencies of each other.  Warp 16 issues every tcgen05.mma /
-// tcgen05.commit from one elected lane.
-//
-// Everything else (Philox momenta, two half-kicks per leapfrog step, Metropolis
-// accept, per-chain dual averaging, thinning, centred-sample store) follows
-// arp_hmc.cuh / SURVEY.md appendix D.
+// (Round 1 also had a kernel with X resident in shared memory and a dual-tile M = 64 variant; both were
+// superseded by the streaming kernel -- 2 % / 9 % slower -- and were removed; see git history.)
 #pragma once
 #include <atomic>
 #include <cuda_fp16.h>
@@ -46,41 +30,11 @@ namespace arp {
 #define TC_NEWTON_MIX 0   // 1: odd likelihood elements take their reciprocal on the FMA pipe (measured 3.6 % slower: issue-bound)
 #endif
 #define TC_CHAINS 128
-#define TC_NF 32          // padded feature count (K of GEMM1, N of GEMM2)
-#define TC_NOBS 1024      // padded observation count
 #define TC_CHUNK 128      // observations per GEMM1 tile
-#define TC_NCHUNK (TC_NOBS / TC_CHUNK)
 #define TC_NQ 4            // worker threads per chain
 #define TC_WORKERS (TC_NQ * TC_CHAINS)   // 512
-#define TC_THREADS (TC_WORKERS + 32)     // + the MMA issuer warp
-#define TC_MMA_WARP (TC_WORKERS / 32)
-// canonical no-swizzle image: block (g = row/8, c = col/8) is 8 rows x 16 B, contiguous 128 B
-#define TC_SF 128u        // bytes between feature chunks (8 features) of one row group
-#define TC_SG 512u        // bytes between row groups (8 rows): TC_NF/8 * 128
-#define TC_XIMG_BYTES (TC_NOBS / 8 * TC_SG)      // 65536 per part
-#define TC_AIMG_BYTES (TC_CHAINS / 8 * TC_SG)    // 8192 per part
-// TMEM columns
-#define TC_COL_H 0        // 2 x 128 fp32 accumulator columns (GEMM1 output, then R head in place)
-#define TC_COL_G 256      // 32 fp32 accumulator columns (GEMM2 output)
-#define TC_COL_R2 288     // 2 x 64 columns: packed fp16 tail of R
 #define TC_TMEM_COLS 512
 
-#define TC_NLOC 17        // coordinates a worker thread owns: overall_log_scale (replicated) + 8 log-scales + 8 betas
-
-struct TcSmem {
-  static constexpr uint32_t X1 = 0;
-  static constexpr uint32_t X2 = X1 + TC_XIMG_BYTES;
-  static constexpr uint32_t A1 = X2 + TC_XIMG_BYTES;
-  static constexpr uint32_t A2 = A1 + TC_AIMG_BYTES;
-  static constexpr uint32_t Y = A2 + TC_AIMG_BYTES;              // float[1024]
-  static constexpr uint32_t XCH = Y + TC_NOBS * 4;               // float[4][TC_NQ][128]
-  static constexpr uint32_t XS = XCH + 4 * TC_NQ * TC_CHAINS * 4; // float[TC_NLOC][512]: thread-private proposal x
-  static constexpr uint32_t PAR = XS + TC_NLOC * TC_WORKERS * 4;        // float[3][2*TC_NF+4]: a, b, eps0 per coordinate
-  static constexpr uint32_t BAR = PAR + 3 * (2 * TC_NF + 4) * 4; // 6 mbarriers
-  static constexpr uint32_t TMEM_PTR = BAR + 8 * 8;
-  static constexpr uint32_t BYTES = TMEM_PTR + 16;
-};
-static_assert(TcSmem::BYTES <= 232448, "shared memory budget");
 
 // ---------------------------------------------------------------- PTX wrappers ---
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,9 +67,6 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
          ((uint64_t)1 << 46);
 }
-// instruction descriptors: f16 x f16 -> f32, M = 128
-#define TC_IDESC_G1 ((1u << 4) | ((uint32_t)(TC_CHUNK >> 3) << 17) | ((128u >> 4) << 24))               // B K-major,  N = 128
-#define TC_IDESC_G2 ((1u << 4) | (1u << 16) | ((uint32_t)(TC_NF >> 3) << 17) | ((128u >> 4) << 24))     // B MN-major, N = 32
 
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -244,406 +195,6 @@ __device__ __forceinline__ void philox_normal4_fast(uint64_t seed, uint32_t chai
   out[0] = -rad0 * c0; out[1] = -rad0 * s0; out[2] = -rad1 * c1; out[3] = -rad1 * s1;
 }
 
-struct TcParams {
-  const uint8_t* ximg;  // X1 image followed by X2 image
-  const float* ypad;    // [TC_NOBS]
-  int N, F;
-};
-
-// ------------------------------------------------------------------------ kernel ---
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_german_tc_hmc(TcParams tp, HmcWs ws, HmcArgs p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_a = sbase + TcSmem::BAR, bar_h0 = bar_a + 8, bar_r0 = bar_a + 24, bar_g = bar_a + 40;
-  float* sy = reinterpret_cast<float*>(smem + TcSmem::Y);
-  float* xch = reinterpret_cast<float*>(smem + TcSmem::XCH);
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + TcSmem::TMEM_PTR);
-
-  // ---- one-time set-up: X image and y into shared memory, barriers, TMEM
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(tp.ximg);
-    uint4* dst = reinterpret_cast<uint4*>(smem + TcSmem::X1);
-    for (int i = tid; i < 2 * TC_XIMG_BYTES / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
-    for (int i = tid; i < TC_NOBS; i += TC_THREADS) sy[i] = __ldg(tp.ypad + i);
-    float* par = reinterpret_cast<float*>(smem + TcSmem::PAR);
-    for (int i = tid; i < p.D; i += TC_THREADS) {
-      par[i] = p.a[i];
-      par[(2 * TC_NF + 4) + i] = p.b[i];
-      par[2 * (2 * TC_NF + 4) + i] = p.eps0[i];
-    }
-  }
-  if (warp == TC_MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)),
-                 "r"((uint32_t)TC_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-    mbar_init(bar_a, TC_WORKERS);
-    mbar_init(bar_h0, 1); mbar_init(bar_h0 + 8, 1);
-    mbar_init(bar_r0, TC_WORKERS); mbar_init(bar_r0 + 8, TC_WORKERS);
-    mbar_init(bar_g, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_s;
-  const int n_lf = p.T * p.L;  // leapfrog steps = gradient evaluations per chain
-
-  if (warp == TC_MMA_WARP) {
-    // =========================== MMA issuer ===========================
-    uint32_t pa = 0, pr[2] = {0, 0};
-    const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform copy for the uniform datapath
-    const uint32_t sX[2] = {sbase + TcSmem::X1, sbase + TcSmem::X2};
-    const uint32_t sA[2] = {sbase + TcSmem::A1, sbase + TcSmem::A2};
-    // the three split products (head x head, tail x head, head x tail)
-    const int pa_sel[3] = {0, 0, 1}, pb_sel[3] = {0, 1, 0};
-    auto issue_g1 = [&](int c) {
-      const uint32_t d = tmu + TC_COL_H + (uint32_t)(c & 1) * TC_CHUNK;
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-#pragma unroll
-        for (int ks = 0; ks < TC_NF / 16; ++ks) {
-          const uint64_t ad = tc_desc(sA[pa_sel[q]] + ks * 2 * TC_SF, TC_SF, TC_SG);
-          const uint64_t bd = tc_desc(sX[pb_sel[q]] + (uint32_t)c * (TC_CHUNK / 8) * TC_SG + ks * 2 * TC_SF, TC_SF, TC_SG);
-          mma_ss_if(1u, d, ad, bd, TC_IDESC_G1, (q | ks) ? 1u : 0u);
-        }
-    };
-    auto issue_g2 = [&](int c) {
-      const uint32_t b = (uint32_t)(c & 1);
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-#pragma unroll
-        for (int w = 0; w < TC_NQ; ++w)
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            // A: 16 observations = 8 packed columns; head in place of H, tail in its own buffer
-            const uint32_t a_t = pa_sel[q] == 0 ? tmu + TC_COL_H + b * TC_CHUNK + 32 * w + 8 * kk
-                                                : tmu + TC_COL_R2 + b * 64 + 16 * w + 8 * kk;
-            const uint32_t og = (uint32_t)c * (TC_CHUNK / 8) + 4 * w + 2 * kk;  // first 8-observation group
-            // MN-major B: N = features (chunks of 8 at TC_SF), K = observations (groups of 8 at TC_SG)
-            const uint64_t bd = tc_desc(sX[pb_sel[q]] + og * TC_SG, TC_SG, TC_SF);
-            mma_ts_if(1u, tmu + TC_COL_G, a_t, bd, TC_IDESC_G2, (c | q | w | kk) ? 1u : 0u);
-          }
-    };
-    // The whole warp runs the issue loop convergently (waits included); each MMA / commit is issued by the
-    // elected lane.  (With `if (lane == 0)` around single MMAs the other 31 lanes ran ahead into the next
-    // mbarrier.try_wait and could suspend the warp while lane 0 still had MMAs to issue.)
-    {
-      for (int s = 0; s < n_lf; ++s) {
-        mbar_wait(bar_a, pa); pa ^= 1;
-        tc_fence_after();
-        issue_g1(0); tc_commit_if(1u, bar_h0);
-        issue_g1(1); tc_commit_if(1u, bar_h0 + 8);
-        for (int c = 0; c < TC_NCHUNK; ++c) {
-          const int b = c & 1;
-          mbar_wait(bar_r0 + 8 * b, pr[b]); pr[b] ^= 1;
-          tc_fence_after();
-          issue_g2(c);
-          if (c + 2 < TC_NCHUNK) { issue_g1(c + 2); tc_commit_if(1u, bar_h0 + 8 * b); }
-          if (c == TC_NCHUNK - 1) tc_commit_if(1u, bar_g);
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ====================== chain workers (4 per chain) ======================
-    // Worker (chain r, quarter w) owns features f = 8w + k (k < 8, f < F): local coordinate 1 + k is the
-    // log-scale d = 1 + f, local 9 + k is the coefficient d = 1 + F + f; local 0 (overall_log_scale, d = 0)
-    // is replicated in all quarters.  It also owns observation columns [32w, 32w + 32) of every chunk.
-    // Momentum lives in registers, the proposal x in a private shared-memory column.
-    const int w = tid >> 7;                 // quarter
-    const int r = tid & 127;                // chain within the CTA = TMEM lane
-    const int chain = blockIdx.x * TC_CHAINS + r;
-    const bool valid = chain < p.C;
-    const int D = p.D, F = tp.F;
-    const int nf = max(0, min(8, F - 8 * w));   // features owned
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const size_t co = (size_t)chain * ws.sc;
-    Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
-    float* xs = reinterpret_cast<float*>(smem + TcSmem::XS) + tid;           // xs[i * TC_WORKERS]
-    const float* pa_s = reinterpret_cast<const float*>(smem + TcSmem::PAR);  // a[d]
-    const float* pb_s = pa_s + (2 * TC_NF + 4);                              // b[d]
-    const float* pe_s = pb_s + (2 * TC_NF + 4);                              // eps0[d]
-    float lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
-    int nacc = ws.nacc[chain];
-    const unsigned int gchain = p.chain_offset + (unsigned int)chain;
-    uint32_t ph[2] = {0, 0}, pg = 0;
-    const float a0 = pa_s[0], b0 = pb_s[0];
-    uint8_t* a_row1 = smem + TcSmem::A1 + (r >> 3) * TC_SG + (r & 7) * 16 + w * TC_SF;
-    uint8_t* a_row2 = smem + TcSmem::A2 + (r >> 3) * TC_SG + (r & 7) * 16 + w * TC_SF;
-    const float NLOG2E = -1.4426950408889634f;
-    // global coordinate of local coordinate i, and whether this worker really owns it
-    auto dof = [&](int i) { return i == 0 ? 0 : (i <= 8 ? 8 * w + i : F + 8 * w + i - 8); };
-    auto owned = [&](int i) { return i == 0 || (i <= 8 ? (i - 1) < nf : (i - 9) < nf); };
-    auto xch_at = [&](int slot, int q) -> float& { return xch[(slot * TC_NQ + q) * TC_CHAINS + r]; };
-
-    for (int t = 0; t < p.T; ++t) {
-      const int tg = p.t_begin + t;
-      // ---- momenta: stage the normals of my coordinates in my xs column, then kick + drift
-      if (p.ext_momenta) {
-        const float* mom = p.ext_momenta + ((size_t)tg * p.C + (valid ? chain : 0)) * D;
-#pragma unroll
-        for (int i = 0; i < TC_NLOC; ++i)
-          if (owned(i)) xs[i * TC_WORKERS] = mom[dof(i)];
-      } else {
-        // Philox block j holds coordinates 4j .. 4j+3; my ranges are d = 0, [1+8w, 1+8w+nf), [1+F+8w, ..+nf)
-        for (int seg = 0; seg < 3; ++seg) {
-          const int d_lo = seg == 0 ? 0 : (seg == 1 ? 1 + 8 * w : 1 + F + 8 * w);
-          const int d_hi = seg == 0 ? 1 : d_lo + nf;
-          const int i_lo = seg == 0 ? 0 : (seg == 1 ? 1 : 9);
-          for (int j = d_lo >> 2; 4 * j < d_hi; ++j) {
-            float n4[4];
-            philox_normal4_fast(p.seed, gchain, (unsigned int)tg, (unsigned int)j, n4);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int d = 4 * j + q;
-              if (d >= d_lo && d < d_hi) xs[(i_lo + d - d_lo) * TC_WORKERS] = n4[q];
-            }
-          }
-        }
-      }
-      float v[TC_NLOC];
-      float ke0 = 0.f, ke1 = 0.f;   // coordinate 0 is counted by quarter 0 only
-#pragma unroll
-      for (int i = 0; i < TC_NLOC; ++i) {
-        v[i] = 0.f;
-        if (owned(i)) {
-          const int d = dof(i);
-          v[i] = xs[i * TC_WORKERS];
-          if (i > 0 || w == 0) ke0 = fmaf(v[i], v[i], ke0);
-          const float e = pe_s[d] * mult;
-          v[i] = v[i] + 0.5f * e * G(d);
-          xs[i * TC_WORKERS] = Z(d) + e * v[i];
-        }
-      }
-      float lpx = 0.f;
-      float glast[TC_NLOC], xclast[TC_NLOC];
-#pragma unroll
-      for (int i = 0; i < TC_NLOC; ++i) { glast[i] = 0.f; xclast[i] = 0.f; }
-      for (int l = 0; l < p.L; ++l) {
-        const bool last = (l == p.L - 1);
-        // ---- site forward: centred log-scales and coefficients of my 8 features -> A operand (head, tail)
-        float lp_top = 0.f;
-        const Site s0 = site_fwd_fast(xs[0], 0.f, ARP_LOG_10, a0, b0, lp_top);
-        {
-          float be[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            be[k] = 0.f;
-            if (k < nf) {
-              const int f = 8 * w + k;
-              float dummy = 0.f;
-              const Site ss = site_fwd_unit(xs[(1 + k) * TC_WORKERS], s0.x, pa_s[1 + f], dummy);
-              const Site sb = site_fwd_fast(xs[(9 + k) * TC_WORKERS], 0.f, ss.x, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
-              be[k] = sb.x;
-            }
-          }
-          uint4 hi, lo;
-          split_pack(be[0], be[1], hi.x, lo.x);
-          split_pack(be[2], be[3], hi.y, lo.y);
-          split_pack(be[4], be[5], hi.z, lo.z);
-          split_pack(be[6], be[7], hi.w, lo.w);
-          *reinterpret_cast<uint4*>(a_row1) = hi;
-          *reinterpret_cast<uint4*>(a_row2) = lo;
-        }
-        fence_async_smem();
-        tc_fence_before();  // orders last step's tcgen05.ld of G before the issuer's next MMAs
-        mbar_arrive(bar_a);
-        // ---- likelihood epilogue: H -> R = y - sigmoid(H), 8 chunks of 128 observations, 32 columns each
-        float lik = 0.f;
-        for (int c = 0; c < TC_NCHUNK; ++c) {
-          const int b = c & 1;
-          mbar_wait(bar_h0 + 8 * b, ph[b]); ph[b] ^= 1;
-          tc_fence_after();
-          uint32_t hv[32];
-          TC_LD32(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 32 * w, hv);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int n0 = c * TC_CHUNK + 32 * w;
-          uint32_t r1[16], r2[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 y4 = *reinterpret_cast<const float4*>(sy + n0 + i);
-            const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
-            float rr[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float eta = __uint_as_float(hv[i + q]);
-              // odd elements: reciprocal on the FMA pipe (Newton) instead of MUFU.RCP
-#if TC_NEWTON_MIX
-              const float sg = (q & 1) ? rcp_newton(1.0f + ex2_approx(fminf(eta * NLOG2E, 60.f)))
-                                       : rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
-#else
-              const float sg = rcp_approx(1.0f + ex2_approx(eta * NLOG2E));
-#endif
-              rr[q] = yy[q] - sg;
-              if (last) {
-                // y eta - softplus(eta), softplus(eta) = max(eta,0) - log(sigmoid(|eta|))
-                const float m = fmaxf(sg, 1.0f - sg);
-                const float term = fmaf(lg2_approx(m), 0.69314718055994531f, yy[q] * eta - fmaxf(eta, 0.f));
-                lik += (n0 + i + q < tp.N) ? term : 0.f;
-              }
-            }
-            split_pack(rr[0], rr[1], r1[i / 2], r2[i / 2]);
-            split_pack(rr[2], rr[3], r1[i / 2 + 1], r2[i / 2 + 1]);
-          }
-          TC_ST16(tmem + lane_off + TC_COL_H + b * TC_CHUNK + 32 * w, r1);
-          TC_ST16(tmem + lane_off + TC_COL_R2 + b * 64 + 16 * w, r2);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          mbar_arrive(bar_r0 + 8 * b);
-        }
-        // ---- gradient wrt beta from TMEM; reverse through my sites, kicks and drift fused in
-        mbar_wait(bar_g, pg); pg ^= 1;
-        tc_fence_after();
-        uint32_t gv[8];
-        TC_LD8(tmem + lane_off + TC_COL_G + 8 * w, gv);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float acc0 = 0.f, lps = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (k < nf) {
-            const int f = 8 * w + k;
-            const float af = pa_s[1 + f], ab_ = pa_s[1 + F + f], bb_ = pb_s[1 + F + f];
-            const float xs_s = xs[(1 + k) * TC_WORKERS], xs_b = xs[(9 + k) * TC_WORKERS];
-            const Site ss = site_fwd_unit(xs_s, s0.x, af, lps);
-            const Site sb = site_fwd_fast(xs_b, 0.f, ss.x, ab_, bb_, lps);
-            float gb, mb, lb, ab;
-            site_rev(sb, __uint_as_float(gv[k]), 0.f, ab_, bb_, gb, mb, lb, ab);
-            float gs, mb2, lb2, ab2;
-            site_rev(ss, lb, s0.x, af, 1.f, gs, mb2, lb2, ab2);
-            acc0 += mb2;
-            // second half kick of this step, then (unless last) first half kick + drift of the next
-            const float es = pe_s[1 + f] * mult, eb = pe_s[1 + F + f] * mult;
-            v[1 + k] = v[1 + k] + 0.5f * es * gs;
-            v[9 + k] = v[9 + k] + 0.5f * eb * gb;
-            if (last) {
-              ke1 = fmaf(v[1 + k], v[1 + k], ke1);
-              ke1 = fmaf(v[9 + k], v[9 + k], ke1);
-              glast[1 + k] = gs; glast[9 + k] = gb;       // proposal gradient and centred values stay in
-              xclast[1 + k] = ss.x; xclast[9 + k] = sb.x;  // registers until the accept decision
-            } else {
-              v[1 + k] = v[1 + k] + 0.5f * es * gs;
-              v[9 + k] = v[9 + k] + 0.5f * eb * gb;
-              xs[(1 + k) * TC_WORKERS] = xs_s + es * v[1 + k];
-              xs[(9 + k) * TC_WORKERS] = xs_b + eb * v[9 + k];
-            }
-          }
-        }
-        xch_at(0, w) = acc0;
-        xch_at(1, w) = lik + lps;
-        epi_bar();
-        const float acc0_t = (xch_at(0, 0) + xch_at(0, 1)) + (xch_at(0, 2) + xch_at(0, 3));
-        lpx = (xch_at(1, 0) + xch_at(1, 1)) + (xch_at(1, 2) + xch_at(1, 3)) + lp_top;
-        {
-          float g0, mb, lb, ab;
-          site_rev(s0, acc0_t, 0.f, a0, b0, g0, mb, lb, ab);
-          const float e = pe_s[0] * mult;
-          v[0] = v[0] + 0.5f * e * g0;
-          if (last) {
-            if (w == 0) ke1 = fmaf(v[0], v[0], ke1);
-            glast[0] = g0; xclast[0] = s0.x;
-          } else {
-            v[0] = v[0] + 0.5f * e * g0;
-            xs[0] = xs[0] + e * v[0];
-          }
-        }
-        epi_bar();  // xch is rewritten by the next step
-      }
-      // ---- Metropolis-Hastings (all quarters compute the same decision)
-      xch_at(2, w) = ke0;
-      xch_at(3, w) = ke1;
-      epi_bar();
-      ke0 = (xch_at(2, 0) + xch_at(2, 1)) + (xch_at(2, 2) + xch_at(2, 3));
-      ke1 = (xch_at(3, 0) + xch_at(3, 1)) + (xch_at(3, 2) + xch_at(3, 3));
-      float log_alpha = lpx - lp_cur + 0.5f * ke0 - 0.5f * ke1;
-      if (!(log_alpha == log_alpha) || log_alpha == -INFINITY) log_alpha = -INFINITY;
-      float log_u;
-      if (p.ext_log_u) log_u = p.ext_log_u[(size_t)tg * p.C + (valid ? chain : 0)];
-      else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
-      const bool acc = log_u < log_alpha;
-      if (acc) {
-#pragma unroll
-        for (int i = 0; i < TC_NLOC; ++i)
-          if (owned(i) && (i > 0 || w == 0)) {
-            const int d = dof(i);
-            Z(d) = xs[i * TC_WORKERS]; G(d) = glast[i]; XC(d) = xclast[i];
-          }
-        lp_cur = lpx;
-        ++nacc;
-      }
-      const int t1 = tg + 1;
-      if (t1 <= p.num_adapt) {
-        const float ft = (float)t1;
-        Hc += p.target_accept - expf(log_alpha < 0.f ? log_alpha : 0.f);
-        const float log_step = ARP_LOG_10 - Hc * sqrtf(ft) / ((ft + 10.f) * 0.05f);
-        const float eta = powf(ft, -0.75f);
-        lavg = eta * log_step + (1.f - eta) * lavg;
-        mult = (t1 < p.num_adapt) ? expf(log_step) : expf(lavg);
-      }
-      const int since = tg - p.num_burnin;
-      if (since >= 0 && (since % p.stride) == 0 && valid) {
-        const int s = since / p.stride;
-        if (s < p.S) {
-          const size_t o = ((size_t)s * p.C + chain) * D;
-#pragma unroll
-          for (int i = 0; i < TC_NLOC; ++i)
-            if (owned(i) && (i > 0 || w == 0)) {
-              const int d = dof(i);
-              if (p.samples) p.samples[o + d] = XC(d);
-              if (p.samples_orig) p.samples_orig[o + d] = Z(d);
-            }
-          if (p.is_accepted && w == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
-        }
-      }
-      epi_bar();
-    }
-    if (w == 0) {
-      ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == TC_MMA_WARP) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS) : "memory");
-  }
-}
-
-// --------------------------------------------------------------------------- host ---
-struct GermanTc {
-  DevBuf ximg, ypad;
-  int N = 0, F = 0;
-  bool ok = false;
-
-  // X [N, F] fp32 row-major -> fp16 head/tail canonical images (zero padded to 1024 x 32)
-  bool build(const float* X, const float* y, int n, int f, std::string* err) {
-    ok = false;
-    if (n > TC_NOBS || f > TC_NF) return true;  // not an error: the SIMT engine handles it
-    std::vector<__half> img((size_t)2 * TC_XIMG_BYTES / 2, __float2half(0.f));
-    for (int i = 0; i < n; ++i)
-      for (int j = 0; j < f; ++j) {
-        const float x = X[(size_t)i * f + j];
-        if (!(fabsf(x) < 60000.f)) return true;  // outside fp16 range: SIMT engine only
-        const __half h1 = __float2half_rn(x);
-        const __half h2 = __float2half_rn(x - __half2float(h1));
-        const size_t off = ((size_t)(i / 8) * TC_SG + (size_t)(j / 8) * TC_SF + (size_t)(i % 8) * 16) / 2 + (j % 8);
-        img[off] = h1;
-        img[TC_XIMG_BYTES / 2 + off] = h2;
-      }
-    std::vector<float> yp(TC_NOBS, 0.f);
-    for (int i = 0; i < n; ++i) yp[i] = y[i];
-    cudaError_t e = upload(ximg, img);
-    if (e == cudaSuccess) e = upload(ypad, yp);
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return false; }
-    N = n; F = f; ok = true;
-    return true;
-  }
-  bool ready() const { return ok; }
-};
-
 static inline bool german_tc_auto(long long C) { return C >= 2 * TC_CHAINS; }
 
 __global__ void k_gather_ws_tc(const real* ws, int sd, int sc, int C, int D, real* out) {
@@ -651,49 +202,6 @@ __global__ void k_gather_ws_tc(const real* ws, int sd, int sc, int C, int D, rea
   if (i >= (long long)C * D) return;
   const int c = (int)(i / D), d = (int)(i % D);
   out[i] = ws[(size_t)d * sd + (size_t)c * sc];
-}
-
-// Runs the whole HMC job on the tcgen05 engine.  wsbuf / scal / nacc keep the
-// workspace alive for the caller (final state, step multipliers, accept counts).
-static inline int german_tc_hmc(GermanTc& tc, const DevModel& dm, const HmcArgs& p, const real* z0, cudaStream_t st,
-                                bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
-                                std::atomic<long long>* launches, std::string* err) {
-#define TC_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(_e); return 1; } } while (0)
-  const long long C = p.C;
-  const long long Cpad = (C + TC_CHAINS - 1) / TC_CHAINS * TC_CHAINS;
-  const long long Dpad = (p.D + 7) / 8 * 8;
-  const size_t vec = (size_t)Cpad * Dpad;
-  TC_CUDA(wsbuf->alloc(7 * vec * sizeof(real)));
-  TC_CUDA(cudaMemsetAsync(wsbuf->p, 0, 7 * vec * sizeof(real), st));
-  TC_CUDA(scal->alloc(4 * Cpad * sizeof(real)));
-  TC_CUDA(nacc->alloc(Cpad * sizeof(int)));
-  HmcWs ws{};
-  real* base = wsbuf->as<real>();
-  ws.z = base; ws.g = base + vec; ws.xc = base + 2 * vec; ws.x = base + 3 * vec;
-  ws.gx = base + 4 * vec; ws.xcx = base + 5 * vec; ws.v = base + 6 * vec;
-  real* sb = scal->as<real>();
-  ws.mult = sb; ws.lp = sb + Cpad; ws.H = sb + 2 * Cpad; ws.lavg = sb + 3 * Cpad;
-  ws.nacc = nacc->as<int>();
-  ws.sd = (int)Cpad; ws.sc = 1;  // [d][chain]: one thread per chain, coalesced
-  const dim3 grid((unsigned)(Cpad / TC_CHAINS));
-  // bootstrap (log-prob, gradient, centred values of the initial state) on the SIMT kernel
-  k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 32><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
-  launches->fetch_add(1);
-  TC_CUDA(cudaGetLastError());
-  TcParams tp{tc.ximg.as<uint8_t>(), tc.ypad.as<float>(), tc.N, tc.F};
-  TC_CUDA(cudaFuncSetAttribute(k_german_tc_hmc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem::BYTES));
-  k_german_tc_hmc<<<grid, TC_THREADS, TcSmem::BYTES, st>>>(tp, ws, p);
-  launches->fetch_add(1);
-  TC_CUDA(cudaGetLastError());
-  if (want_final) {
-    TC_CUDA(dfz->alloc((size_t)C * p.D * sizeof(real)));
-    const long long n = C * p.D;
-    k_gather_ws_tc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.z, ws.sd, ws.sc, (int)C, p.D, dfz->as<real>());
-    launches->fetch_add(1);
-    TC_CUDA(cudaGetLastError());
-  }
-#undef TC_CUDA
-  return 0;
 }
 
 }  // namespace arp

@@ -1,5 +1,5 @@
-// tcgen05 engine, STREAMING variant: same algorithm as arp_german_tc.cuh, but the design matrix is
-// not resident in shared memory.  X (fp16 head + tail, plus y) is cut into 128-observation chunk
+// tcgen05 engine for German credit (the only dense contraction of the hot path; primitives in arp_german_tc.cuh).
+// One CTA owns 128 chains (= the 128 TMEM lanes).  X (fp16 head + tail of the label-scaled rows) is cut into 128-observation chunk
 // images that a producer warp ring-buffers from L2 into shared memory with bulk asynchronous copies
 // (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP); each chunk image feeds GEMM1 (K-major B) and,
 // one epilogue later, GEMM2 (MN-major B) before its stage is released by tcgen05.commit.  This lifts
@@ -68,7 +68,7 @@ struct Tcs {
 struct TcsParams {
   const uint8_t* img;   // nchunk stage images
   int N, F, nchunk;
-  int skew;             // dual-tile kernel: clocks by which tile 1 starts late
+  int bias;             // 1: K-slot NF - 1 of every image row holds 1.0 and the A operand puts -31 there (see tcs_epilogue32)
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -112,19 +112,34 @@ __device__ __forceinline__ void split_pack_trunc(float x0, float x1, uint32_t& h
 #define TCS_SPLIT split_pack
 #endif
 
-template <bool SHARE, bool LAST>
+// BIAS: the clamp is folded into the GEMM and an add.  A spare K-slot (F < NF) carries the constant -31: the image rows
+// hold 1.0 there and the A operand -31, so GEMM1 yields h' = h - 31 and with e' = 2^h' = 2^-31 2^h
+//   ds = sat(e' + 2^-31) = 2^-31 (1 + 2^h) clamped at 1      (one FADD.SAT instead of the half-rate FMNMX + FADD),
+//   q  = 2^-31 / ds  (clamped at h = 31, q < 5e-10),  prod of four ds >= 2^-124: no under- / overflow;
+// last step: min(h, 31) + log2 q = min(h', 0) - log2 ds, i.e. per group  sum min(h', 0) + log2(1 / prod ds).
+#define TCS_2M31 4.656612873077392578125e-10f
+template <bool SHARE, bool LAST, bool BIAS>
 __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1, uint32_t* r2, float& lik) {
   float m[8][4], e[8][4], p01[8], p23[8], inv[8];
   auto stage_a = [&](int g) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      m[g][q] = fminf(__uint_as_float(hv[4 * g + q]), 30.f);
-      e[g][q] = ex2_approx(m[g][q]);
+      if constexpr (BIAS) {
+        const float hp = __uint_as_float(hv[4 * g + q]);
+        if (LAST) m[g][q] = fminf(hp, 0.f);
+        e[g][q] = ex2_approx(hp);
+      } else {
+        m[g][q] = fminf(__uint_as_float(hv[4 * g + q]), 30.f);
+        e[g][q] = ex2_approx(m[g][q]);
+      }
     }
   };
   auto stage_b = [&](int g) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) e[g][q] += 1.0f;
+    for (int q = 0; q < 4; ++q) {
+      if constexpr (BIAS) e[g][q] = __saturatef(e[g][q] + TCS_2M31);
+      else e[g][q] += 1.0f;
+    }
     if constexpr (SHARE) {
       p01[g] = e[g][0] * e[g][1];
       p23[g] = e[g][2] * e[g][3];
@@ -137,11 +152,12 @@ __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1,
   auto stage_c = [&](int g) {
     float qv[4];
     if constexpr (SHARE) {
-      const float i01 = inv[g] * p23[g], i23 = inv[g] * p01[g];
+      const float is = BIAS ? inv[g] * TCS_2M31 : inv[g];
+      const float i01 = is * p23[g], i23 = is * p01[g];
       qv[0] = i01 * e[g][1]; qv[1] = i01 * e[g][0]; qv[2] = i23 * e[g][3]; qv[3] = i23 * e[g][2];
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) qv[q] = e[g][q];
+      for (int q = 0; q < 4; ++q) qv[q] = BIAS ? e[g][q] * TCS_2M31 : e[g][q];
     }
     if (LAST) {
       // ln sigmoid(t eta) / ln2 = h + log2 q.  The two terms cancel for well-predicted observations, so the
@@ -150,8 +166,9 @@ __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1,
       if constexpr (SHARE) {
         lik += ((m[g][0] + m[g][1]) + (m[g][2] + m[g][3])) + lg2_approx(inv[g]);
       } else {
-        const float t0 = m[g][0] + lg2_approx(qv[0]), t1 = m[g][1] + lg2_approx(qv[1]);
-        const float t2 = m[g][2] + lg2_approx(qv[2]), t3 = m[g][3] + lg2_approx(qv[3]);
+        // BIAS: e[][] holds 1 / ds here and min(h', 0) - log2 ds is the term; else qv = q and min(h, 30) + log2 q
+        const float t0 = m[g][0] + lg2_approx(BIAS ? e[g][0] : qv[0]), t1 = m[g][1] + lg2_approx(BIAS ? e[g][1] : qv[1]);
+        const float t2 = m[g][2] + lg2_approx(BIAS ? e[g][2] : qv[2]), t3 = m[g][3] + lg2_approx(BIAS ? e[g][3] : qv[3]);
         lik += (t0 + t1) + (t2 + t3);
       }
     }
@@ -345,6 +362,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const int chain = blockIdx.x * TC_CHAINS + r;
     const bool valid = chain < p.C;
     const int D = p.D, F = tp.F;
+    const bool bias = tp.bias != 0;
     // features are dealt to the four workers of a chain in contiguous, balanced ranges (25 -> 7, 6, 6, 6); worker w
     // owns K-slots [FPW w, FPW w + nf) of the A operand / X images and the matching columns of G
     const int nf = F / TC_NQ + (w < F % TC_NQ ? 1 : 0);
@@ -466,6 +484,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               const Site sb = site_fwd_fast(xs[(1 + FPW + k) * TC_WORKERS], 0.f, ls, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
               be[k8] = sb.x * LOG2E;   // GEMM1 then yields log2(e) t eta: one FMUL less per likelihood element
               ovf |= !(fabsf(be[k8]) < 60000.f);   // outside the fp16 range of the A operand (or NaN)
+            } else if (bias && w == TC_NQ - 1 && k == FPW - 1) {
+              be[k8] = -31.f;   // the bias slot (K-slot NF - 1; free because F < NF)
             }
           }
           uint4 hi, lo;
@@ -499,8 +519,13 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           TC_LD32(h_addr, hv);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           TCS_TICK(3)
-          if (last) tcs_epilogue32<K::RCP_SHARE, true>(hv, r1, r2, lik);
-          else tcs_epilogue32<K::RCP_SHARE, false>(hv, r1, r2, lik);
+          if (bias) {
+            if (last) tcs_epilogue32<K::RCP_SHARE, true, true>(hv, r1, r2, lik);
+            else tcs_epilogue32<K::RCP_SHARE, false, true>(hv, r1, r2, lik);
+          } else {
+            if (last) tcs_epilogue32<K::RCP_SHARE, true, false>(hv, r1, r2, lik);
+            else tcs_epilogue32<K::RCP_SHARE, false, false>(hv, r1, r2, lik);
+          }
           TCS_TICK(14)
           TC_ST16(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, r1);
           TC_ST16(tmem + lane_off + K::COL_R2 + b * 64 + 16 * w, r2);
@@ -665,6 +690,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         if (owned(i) && (i > 0 || w == 0)) { const int d = dof(i); const float gv_ = Gc(d), xv_ = XCc(d); G(d) = gv_; XC(d) = xv_; }
     }
     if (w == 0) {
+      G(0) = g0_cur;   // coordinate 0 lives in registers during the run
       ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
     }
   }
@@ -679,7 +705,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
 struct GermanTcs {
   DevBuf img;
   int N = 0, F = 0, nf_pad = 0, nchunk = 0;
-  bool ok = false;
+  bool ok = false, bias = false;
 
   // X [N, F] fp32 row-major, y [N] in {0, 1} -> per-chunk stage images (head | tail) of the rows t_n X_n,
   // t_n = 2 y_n - 1, zero padded
@@ -713,6 +739,22 @@ struct GermanTcs {
         memcpy(st + XCHUNK + off, &h2, 2);
       }
     }
+    // bias slot (K-slot nf_pad - 1, unused when f < nf_pad): 1.0 in the head image of EVERY row, padded rows included,
+    // so that a padded row still behaves as h = 0 (q = 1/2, zero contribution to X^T q) -- see tcs_epilogue32
+#ifndef TCS_NO_BIAS
+    bias = f < nf_pad;
+#else
+    bias = false;
+#endif
+    if (bias) {
+      const int sl = nf_pad - 1;
+      const __half one = __float2half_rn(1.f);
+      for (int i = 0; i < nchunk * TC_CHUNK; ++i) {
+        const int c = i / TC_CHUNK, rloc = i % TC_CHUNK;
+        const size_t off = (size_t)(rloc / 8) * SG + (size_t)(sl / 8) * 128 + (size_t)(rloc % 8) * 16 + (size_t)(sl % 8) * 2;
+        memcpy(buf.data() + (size_t)c * STAGE + off, &one, 2);
+      }
+    }
     cudaError_t e = upload(img, buf);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return false; }
     N = n; F = f; ok = true;
@@ -736,17 +778,8 @@ static inline cudaError_t tcs_launch(int nf_pad, dim3 grid, cudaStream_t st, con
   return cudaGetLastError();
 }
 
-static inline int tcd_skew() {
-  static const int v = [] { const char* e = getenv("ARP_TCD_SKEW"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
-template <bool GAMMA>
-static inline cudaError_t tcd_launch(dim3 grid, cudaStream_t st, const TcsParams& tp, const HmcWs& ws, const HmcArgs& p);
-
-// dual = true: the dual-tile kernel of arp_german_tcd.cuh (F <= 32 only)
 static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt, const HmcArgs& p, const real* z0,
-                                 cudaStream_t st, bool dual, bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
+                                 cudaStream_t st, bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
                                  std::atomic<long long>* launches, std::string* err) {
 #define TCS_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(_e); return 1; } } while (0)
   const long long C = p.C;
@@ -777,9 +810,8 @@ static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt,
   }
   launches->fetch_add(1);
   TCS_CUDA(cudaGetLastError());
-  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk, tcd_skew()};
-  if (dual && tc.nf_pad == 32) TCS_CUDA(gamma ? tcd_launch<true>(grid, st, tp, ws, p) : tcd_launch<false>(grid, st, tp, ws, p));
-  else TCS_CUDA(gamma ? tcs_launch<true>(tc.nf_pad, grid, st, tp, ws, p) : tcs_launch<false>(tc.nf_pad, grid, st, tp, ws, p));
+  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk, tc.bias ? 1 : 0};
+  TCS_CUDA(gamma ? tcs_launch<true>(tc.nf_pad, grid, st, tp, ws, p) : tcs_launch<false>(tc.nf_pad, grid, st, tp, ws, p));
   launches->fetch_add(1);
   if (want_final) {
     TCS_CUDA(dfz->alloc((size_t)C * p.D * sizeof(real)));

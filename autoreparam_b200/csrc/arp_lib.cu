@@ -15,11 +15,10 @@
 #include "arp_host.cuh"
 #include "arp_hmc.cuh"
 #include "arp_ess.cuh"
+#include "arp_ess_fft.cuh"
 #include "arp_vi.cuh"
 #ifndef ARP_FP64
-#include "arp_german_tc.cuh"
 #include "arp_german_tcs.cuh"
-#include "arp_german_tcd.cuh"
 #endif
 
 using namespace arp;
@@ -58,8 +57,7 @@ struct arp_model {
   DevBuf X, y, x1, x2, w, u, offs, gidx, pidx;
   int fp = 32;  // german: register-resident padded feature count of the SIMT engine
 #ifndef ARP_FP64
-  GermanTc tc;    // german: operands of the tcgen05 engine (X resident in shared memory: F <= 32, N <= 1024)
-  GermanTcs tcs;  // german: operands of the streaming tcgen05 engine (F <= 64, any N)
+  GermanTcs tcs;  // german: operands of the tcgen05 engine (chunk images of X streamed from L2; F <= 64, any N)
 #endif
 };
 
@@ -97,9 +95,7 @@ extern "C" int arp_model_create(const char* model_name, const arp_model_data* d,
 #ifndef ARP_FP64
     {
       std::string err;
-      if (dm.kind == MODEL_GERMAN_LOGNORMAL && !m->tc.build(d->X, d->y, dm.N, dm.F, &err))
-        return bail("tcgen05 operand build: " + err);
-      if (!m->tcs.build(d->X, d->y, dm.N, dm.F, &err)) return bail("tcgen05 streaming operand build: " + err);
+      if (!m->tcs.build(d->X, d->y, dm.N, dm.F, &err)) return bail("tcgen05 operand build: " + err);
     }
 #endif
   } else if (name == "radon" || name == "radon_stddvs") {
@@ -294,6 +290,84 @@ extern "C" int arp_log_joint_grad(arp_model* m, const arp_real* a, const arp_rea
   return 0;
 }
 
+// Same contract, chosen engine.  engine 0 / 1: the SIMT kernel above.  engine 2 / 3: the gradient as the tcgen05 HMC
+// engine computes it (german_credit models): one transition of one leapfrog step with step size 0, momentum 0 and
+// log u = -inf is run through k_german_tcs_hmc, so the proposal IS the input state, it is always accepted, and the
+// kernel's own epilogue / GEMM2 / site-reverse code leaves (log-joint, gradient, centred values) in the workspace.
+// A chain whose coefficients leave the fp16 range of the A operand is rejected by that engine: lp = -inf, grad = NaN.
+#ifndef ARP_FP64
+__global__ void k_tc_grad_out(HmcWs ws, int C, int D, real* lp, real* grad, real* centered) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)C * D) return;
+  const int c = (int)(i / D), d = (int)(i % D);
+  const bool ok = ws.nacc[c] == 1;
+  if (d == 0 && lp) lp[c] = ok ? ws.lp[c] : -INFINITY;
+  if (grad) grad[i] = ok ? ws.g[(size_t)d * ws.sd + c] : NAN;
+  if (centered) centered[i] = ok ? ws.xc[(size_t)d * ws.sd + c] : NAN;
+}
+#endif
+
+extern "C" int arp_log_joint_grad_engine(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
+                                         arp_real* lp, arp_real* grad, arp_real* centered, int engine, int mem,
+                                         void* stream) {
+  if (engine == 0 || engine == 1) return arp_log_joint_grad(m, a, b, z, C, lp, grad, centered, nullptr, mem, stream);
+#ifdef ARP_FP64
+  return fail("arp_log_joint_grad_engine: the fp64 check build has no tcgen05 engine");
+#else
+  if (!m || !a || !b || !z || C <= 0) return fail("arp_log_joint_grad_engine: bad argument");
+  if (engine != 2 && engine != 3) return fail("arp_log_joint_grad_engine: unknown engine");
+  if (!((m->dev.kind == MODEL_GERMAN_LOGNORMAL || m->dev.kind == MODEL_GERMAN_GAMMA) && m->tcs.ready()))
+    return fail("arp_log_joint_grad_engine: the tcgen05 engine needs a german_credit model with 0/1 outcomes and at most 64 features");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->dev.D;
+  const bool host = mem == ARP_MEM_HOST;
+  DevBuf da, db, dz, deps, dmom, dlu, dout;
+  if (stage_in(da, a, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  if (stage_in(db, b, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  const real* zdev = z;
+  if (host) {
+    if (stage_in(dz, z, (size_t)C * D * sizeof(real), mem, st)) return 1;
+    zdev = dz.as<real>();
+  }
+  ARP_CUDA(deps.alloc(D * sizeof(real)));
+  ARP_CUDA(cudaMemsetAsync(deps.p, 0, D * sizeof(real), st));
+  ARP_CUDA(dmom.alloc((size_t)C * D * sizeof(real)));
+  ARP_CUDA(cudaMemsetAsync(dmom.p, 0, (size_t)C * D * sizeof(real), st));
+  {
+    std::vector<real> neg((size_t)C, -INFINITY);
+    if (stage_in(dlu, neg.data(), (size_t)C * sizeof(real), ARP_MEM_HOST, st)) return 1;
+    ARP_CUDA(cudaStreamSynchronize(st));   // `neg` dies at the end of this scope
+  }
+  HmcArgs p{};
+  p.C = (int)C; p.D = D; p.L = 1; p.T = 1; p.t_begin = 0; p.num_adapt = 0; p.num_burnin = 0; p.stride = 2; p.S = 1;
+  p.seed = 0; p.chain_offset = 0; p.target_accept = (real)0.75;
+  p.eps0 = deps.as<real>(); p.a = da.as<real>(); p.b = db.as<real>();
+  p.ext_momenta = dmom.as<real>(); p.ext_log_u = dlu.as<real>();
+  DevBuf wsbuf, dfz, scal, nacc;
+  if (german_tcs_hmc(m->tcs, m->dev, m->fp, p, zdev, st, false, &wsbuf, &dfz, &scal, &nacc, &g_launches, &g_last_error)) return 1;
+  const long long Cpad = round_up(C, TC_CHAINS), Dpad = round_up(D, 8);
+  const size_t vec = (size_t)Cpad * Dpad;
+  HmcWs ws{};
+  ws.g = wsbuf.as<real>() + vec; ws.xc = wsbuf.as<real>() + 2 * vec;
+  ws.lp = scal.as<real>() + Cpad; ws.nacc = nacc.as<int>(); ws.sd = (int)Cpad; ws.sc = 1;
+  real *olp = lp, *og = grad, *oxc = centered;
+  const size_t n = (size_t)C * D;
+  if (host) {
+    ARP_CUDA(dout.alloc((2 * n + (size_t)C) * sizeof(real)));
+    og = dout.as<real>(); oxc = og + n; olp = oxc + n;
+  }
+  k_tc_grad_out<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, (int)C, D, olp, og, oxc);
+  ARP_LAUNCH_CHECK();
+  if (host) {
+    if (lp) ARP_CUDA(cudaMemcpyAsync(lp, olp, C * sizeof(real), cudaMemcpyDeviceToHost, st));
+    if (grad) ARP_CUDA(cudaMemcpyAsync(grad, og, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+    if (centered) ARP_CUDA(cudaMemcpyAsync(centered, oxc, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+  }
+  ARP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+#endif
+}
+
 // ------------------------------------------------------------------------ HMC ---
 extern "C" int64_t arp_hmc_num_transitions(const arp_hmc_config* cfg) {
   if (!cfg || cfg->num_results <= 0) return 0;
@@ -321,18 +395,11 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
   const bool host = mem == ARP_MEM_HOST;
 
 #ifndef ARP_FP64
-  const bool tc_res = m->dev.kind == MODEL_GERMAN_LOGNORMAL && m->tc.ready();   // resident-X kernel
-  const bool tc_str = (m->dev.kind == MODEL_GERMAN_LOGNORMAL || m->dev.kind == MODEL_GERMAN_GAMMA) && m->tcs.ready();
-  const bool tc_ok = tc_res || tc_str;
-  if ((cfg->engine == 2 || cfg->engine == 3 || cfg->engine == 4) && !tc_ok)
-    return fail("arp_hmc_run: the tcgen05 engine needs a german_credit model with at most 64 features");
-  if ((cfg->engine == 3 || cfg->engine == 4) && !tc_str)
-    return fail("arp_hmc_run: streaming tcgen05 engine not available for this model");
-  if (cfg->engine == 4 && m->tcs.nf_pad != 32) return fail("arp_hmc_run: the dual-tile tcgen05 engine needs at most 32 features");
+  const bool tc_ok = (m->dev.kind == MODEL_GERMAN_LOGNORMAL || m->dev.kind == MODEL_GERMAN_GAMMA) && m->tcs.ready();
+  if (cfg->engine < 0 || cfg->engine > 3) return fail("arp_hmc_run: unknown engine");
+  if (cfg->engine >= 2 && !tc_ok)
+    return fail("arp_hmc_run: the tcgen05 engine needs a german_credit model with 0/1 outcomes and at most 64 features");
   const bool use_tc = tc_ok && (cfg->engine >= 2 || (cfg->engine == 0 && german_tc_auto(C)));
-  const bool use_dual = cfg->engine == 4;
-  // auto prefers the streaming kernel: it measures ~2 % faster than the resident one and has no size limits
-  const bool use_stream = use_tc && tc_str && (cfg->engine != 2 || !tc_res);
 #else
   if (cfg->engine >= 2) return fail("arp_hmc_run: the fp64 check build has no tcgen05 engine");
   const bool use_tc = false;
@@ -374,11 +441,8 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
 
 #ifndef ARP_FP64
   if (use_tc) {
-    int rc = use_stream
-                 ? german_tcs_hmc(m->tcs, m->dev, m->fp, p, z0, st, use_dual, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc,
-                                  &g_launches, &g_last_error)
-                 : german_tc_hmc(m->tc, m->dev, p, z0, st, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc, &g_launches,
-                                 &g_last_error);
+    int rc = german_tcs_hmc(m->tcs, m->dev, m->fp, p, z0, st, buf->final_z != nullptr, &wsbuf, &dfz, &scal, &nacc,
+                            &g_launches, &g_last_error);
     if (rc) return rc;
     final_z_dev = dfz.as<real>();
     out_mult_dev = scal.as<real>();
@@ -517,6 +581,12 @@ extern "C" int arp_hmc_interleaved_run(arp_model* m, const arp_ilv_config* cfg, 
 }
 
 // ------------------------------------------------------------------------ ESS ---
+// ARP_ESS_DIRECT=1 forces the direct-summation kernels for every S (A/B measurements, cross-check tests)
+static bool ess_force_direct() {
+  const char* e = getenv("ARP_ESS_DIRECT");
+  return e && e[0] == '1';
+}
+
 extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* ess, arp_real* mean,
                        arp_real* var, int mem, void* stream) {
   if (!samples || !ess || S < 2 || C <= 0 || D <= 0) return fail("arp_ess: bad argument");
@@ -532,13 +602,20 @@ extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D,
     omean = mean ? out + n : nullptr; ovar = var ? out + 2 * n : nullptr;
   }
   DevBuf dxt;
-  ARP_CUDA(dxt.alloc((size_t)S * n * sizeof(real)));
-  {
-    const dim3 tb(32, 8), tg((unsigned)((n + 31) / 32), (unsigned)std::min<long long>((S + 31) / 32, 64));
-    k_ess_transpose<<<tg, tb, 0, st>>>(in, (int)S, (long long)n, dxt.as<real>());
-    ARP_LAUNCH_CHECK();
-  }
-  {
+  if (S <= ARP_FFT_MAXS && !ess_force_direct()) {
+    // shared-memory FFT (arp_ess_fft.cuh): every lag at once, the samples cross HBM once, no transposed copy
+    const size_t smem = sizeof(cplx<real>) * (ARP_FFT_G / 2) * ARP_FFT_BUF + sizeof(double) * (ARP_FFT_THREADS / 32) * ARP_FFT_G;
+    ARP_CUDA(cudaFuncSetAttribute(k_ess_fft<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned fg = (unsigned)((n + ARP_FFT_G - 1) / ARP_FFT_G);
+    k_ess_fft<real><<<fg, ARP_FFT_THREADS, smem, st>>>(in, (int)S, (long long)n, out, omean, ovar);
+  } else {
+    // longer series: direct summation up to the first negative lag on a series-major copy (arp_ess.cuh)
+    ARP_CUDA(dxt.alloc((size_t)S * n * sizeof(real)));
+    {
+      const dim3 tb(32, 8), tg((unsigned)((n + 31) / 32), (unsigned)std::min<long long>((S + 31) / 32, 64));
+      k_ess_transpose<<<tg, tb, 0, st>>>(in, (int)S, (long long)n, dxt.as<real>());
+      ARP_LAUNCH_CHECK();
+    }
     const unsigned eg = (unsigned)((n + ARP_ESS_BLOCK - 1) / ARP_ESS_BLOCK);
     if (!ARP_REAL_IS_DOUBLE && S % 4 == 0)
       k_ess<true><<<eg, ARP_ESS_BLOCK, 0, st>>>(dxt.as<real>(), (int)S, (int)C, (int)D, out, omean, ovar);
@@ -546,7 +623,7 @@ extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D,
       k_ess<false><<<eg, ARP_ESS_BLOCK, 0, st>>>(dxt.as<real>(), (int)S, (int)C, (int)D, out, omean, ovar);
   }
   ARP_LAUNCH_CHECK();
-  ARP_CUDA(cudaStreamSynchronize(st));  // the transposed copy is freed on return
+  if (dxt.p) ARP_CUDA(cudaStreamSynchronize(st));  // the transposed copy is freed on return
   if (mem == ARP_MEM_HOST) {
     ARP_CUDA(cudaMemcpyAsync(ess, out, n * sizeof(real), cudaMemcpyDeviceToHost, st));
     if (mean) ARP_CUDA(cudaMemcpyAsync(mean, omean, n * sizeof(real), cudaMemcpyDeviceToHost, st));

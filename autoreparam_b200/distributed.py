@@ -105,6 +105,40 @@ def sum_scalar(x, device=None):
     return float(t.item())
 
 
+def is_multi():
+    dist = _dist()
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def rhat_stats(chain_mean, chain_var):
+    """Per-chain moments [C_local, D] (torch tensors, any device) -> packed sufficient statistics [3 D + 1] fp64:
+    (sum_c mean, sum_c mean^2, sum_c var, n_chains).  Sums over chains, so shards add."""
+    import torch
+    m, v = chain_mean.double(), chain_var.double()
+    n = torch.full((1,), float(m.shape[0]), dtype=torch.float64, device=m.device)
+    return torch.cat([m.sum(0), (m * m).sum(0), v.sum(0), n])
+
+
+def rhat_from_stats(packed, num_samples):
+    """Packed statistics (after the all-reduce) -> R-hat [D] (torch, fp64)."""
+    import torch
+    D = (packed.numel() - 1) // 3
+    s1, s2, sv, n = packed[:D], packed[D:2 * D], packed[2 * D:3 * D], packed[-1]
+    s = float(num_samples)
+    w = sv / n * s / (s - 1.0)
+    b_over_n = (s2 - s1 * s1 / n) / (n - 1.0)
+    return torch.sqrt(((s - 1.0) / s * w + b_over_n) / w)
+
+
+def allreduce_sum_(t):
+    """In-place sum over ranks of a tensor living on this rank's device (NCCL over NVLink on GPUs, gloo on CPU);
+    a no-op without a process group."""
+    if is_multi():
+        dist = _dist()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def rhat_allreduce(chain_mean, chain_var, num_samples, device=None):
     """R-hat from per-chain moments held shard-wise: all_reduce(sum) of
     (sum_c mean, sum_c mean^2, sum_c var, n_chains) per coordinate -- 3D+1 numbers."""

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib
 
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_STREAM, ENGINE_TCGEN05_DUAL = 0, 1, 2, 3, 4
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05, ENGINE_TCGEN05_STREAM = 0, 1, 2, 3   # include/autoreparam_b200.h: ARP_ENGINE_*
 
 
 def _is_torch(x):
@@ -37,8 +37,9 @@ def _torch_dtype(precision):
     return torch.float32 if precision == "f32" else torch.float64
 
 
-def log_joint_grad(model, z, a, b, precision="f32", want_abar=False):
-    """``z`` [C, D] -> (lp [C], grad [C, D], centered [C, D][, abar [C, D]])."""
+def log_joint_grad(model, z, a, b, precision="f32", want_abar=False, engine=ENGINE_AUTO):
+    """``z`` [C, D] -> (lp [C], grad [C, D], centered [C, D][, abar [C, D]]).
+    ``engine=ENGINE_TCGEN05``: the values as the tensor-core HMC engine computes them (``arp_log_joint_grad_engine``)."""
     lib = _lib.load(precision)
     dt = _lib.np_dtype(precision)
     a_h, b_h = _np(a, dt), _np(b, dt)
@@ -61,6 +62,12 @@ def log_joint_grad(model, z, a, b, precision="f32", want_abar=False):
         ab = np.empty_like(z) if want_abar else None
         mem, st = _lib.ARP_MEM_HOST, None
     assert z.shape == (Cn, D)
+    if engine in (ENGINE_TCGEN05, ENGINE_TCGEN05_STREAM):
+        assert not want_abar, "the tcgen05 engine does not produce d/da"
+        rc = lib.arp_log_joint_grad_engine(model.handle(precision), _p(a_h), _p(b_h), _p(z), Cn, _p(lp), _p(g), _p(xc),
+                                           engine, mem, st)
+        _lib.check(lib, rc, "arp_log_joint_grad_engine")
+        return lp, g, xc
     rc = lib.arp_log_joint_grad(model.handle(precision), _p(a_h), _p(b_h), _p(z), Cn, _p(lp), _p(g), _p(xc), _p(ab),
                                 mem, st)
     _lib.check(lib, rc, "arp_log_joint_grad")

@@ -14,14 +14,15 @@ import collections
 
 import numpy as np
 
-from . import engine, util
+from . import distributed, engine, util
 
 
 class HmcResult(collections.namedtuple(
-        "HmcResult", "ess is_accepted samples rhat step_mult accept_count num_transitions ess_flat")):
+        "HmcResult", "ess is_accepted samples rhat step_mult accept_count num_transitions ess_flat accept_stats")):
     """ess: list of [C, *site] (un-normalised, as tfp.mcmc.effective_sample_size);
     is_accepted [S, C] bool; samples: list of [S, n_save, *site] centred traces
-    (None unless chains were requested); rhat [D] per coordinate."""
+    (None unless chains were requested); rhat [D] per coordinate over the chains of ALL ranks;
+    accept_stats = (accepted kept transitions, accepted transitions, chains) summed over ALL ranks."""
 
 
 _PINNED = {}
@@ -77,21 +78,24 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
                          num_adaptation_steps=num_adaptation_steps, seed=seed, chain_offset=chain_offset,
                          want_final=False, engine=engine_kind, precision=precision)
     ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
-    # R-hat from the per-chain moments, reduced on the device ([C, D] -> [D], fp64): util.rhat_from_moments
-    rhat_dev = None
-    if C > 1:
-        s_ = float(num_samples)
-        w_ = var_dev.double().mul_(s_ / (s_ - 1.0)).mean(dim=0)
-        b_over_n = mean_dev.double().var(dim=0, unbiased=True)
-        rhat_dev = torch.sqrt(((s_ - 1.0) / s_ * w_ + b_over_n) / w_)
+    # R-hat from the per-chain moments: [C, D] -> packed sums [3 D + 1] on the device, summed over the ranks (one small
+    # NCCL all-reduce when the chains are sharded over several GPUs), -> [D].  Accept counters ride in a second
+    # 3-element all-reduce.  These are the only collectives of an HMC run.
+    stats = distributed.rhat_stats(mean_dev, var_dev)
+    acc = torch.stack([out["is_accepted"].sum(dtype=torch.float64), out["accept_count"].sum(dtype=torch.float64),
+                       torch.tensor(float(C), dtype=torch.float64, device=dev)])
+    distributed.allreduce_sum_(stats)
+    distributed.allreduce_sum_(acc)
+    rhat_dev = distributed.rhat_from_stats(stats, num_samples) if (C > 1 or distributed.is_multi()) else None
     # device -> host through pinned buffers, one synchronisation: only what the caller consumes
-    dev_out = [ess_dev, out["is_accepted"], out["step_mult"], out["accept_count"]] + ([rhat_dev] if C > 1 else [])
+    dev_out = [ess_dev, out["is_accepted"], out["step_mult"], out["accept_count"], acc] + \
+        ([rhat_dev] if rhat_dev is not None else [])
     host = [_pinned_like(t, tag) for tag, t in enumerate(dev_out)]
     for h, t in zip(host, dev_out):
         h.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    ess_flat, is_acc_u8, step_mult, accept_count = [h.numpy().copy() for h in host[:4]]
-    rhat = host[4].numpy().copy() if C > 1 else None
+    ess_flat, is_acc_u8, step_mult, accept_count, acc_host = [h.numpy().copy() for h in host[:5]]
+    rhat = host[5].numpy().copy() if rhat_dev is not None else None
     is_acc = is_acc_u8.view(np.bool_)
     samples = None
     if num_chains_to_save > 0:
@@ -99,7 +103,8 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
     res = HmcResult(ess=mc.split(ess_flat), is_accepted=is_acc, samples=samples,
                     rhat=rhat,
                     step_mult=step_mult, accept_count=accept_count,
-                    num_transitions=out["num_transitions"], ess_flat=ess_flat)
+                    num_transitions=out["num_transitions"], ess_flat=ess_flat,
+                    accept_stats=tuple(float(v) for v in acc_host))
     if keep_on_device:
         return res, out
     return res
@@ -186,11 +191,13 @@ def hmc_interleaved(model_config, target_cp, target_ncp, num_leapfrog_steps_cp, 
                                      seed=seed, chain_offset=chain_offset, precision=precision)
     ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
     ess_flat = ess_dev.cpu().numpy()
+    stats = distributed.allreduce_sum_(distributed.rhat_stats(mean_dev, var_dev))   # R-hat over the chains of all ranks
+    rhat = distributed.rhat_from_stats(stats, num_samples).cpu().numpy() if (C > 1 or distributed.is_multi()) else None
     samples = None
     if num_chains_to_save > 0:
         samples = mc.split(out["samples"][:, :num_chains_to_save].cpu().numpy())
     return InterleavedResult(
         ess=mc.split(ess_flat), is_accepted_cp=out["is_accepted_a"].cpu().numpy().astype(bool),
         is_accepted_ncp=out["is_accepted_b"].cpu().numpy().astype(bool), samples=samples,
-        rhat=util.rhat_from_moments(mean_dev.cpu().numpy(), var_dev.cpu().numpy(), num_samples) if C > 1 else None,
+        rhat=rhat,
         ess_flat=ess_flat, num_transitions=out["num_transitions"])

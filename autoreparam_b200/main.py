@@ -195,19 +195,23 @@ def run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False):
         FLAGS.num_adaptation_steps = int(FLAGS.num_adaptation_steps / float(FLAGS.num_leapfrog_steps))
 
     target, actual_reparam = create_target_graph(FLAGS, model_config, results_dir)
+    _check_sharding(FLAGS, world)
     lo, hi = distributed.shard_range(FLAGS.num_chains, rank, world)
     z0 = model_config.join(initial_states)[lo:hi]
     device = distributed.local_device()
     start_time = time.time()
     # traces are only kept for the first --num_chains_to_save chains (main.py:578-585): they live on rank 0
     n_save = min(FLAGS.num_chains_to_save, hi - lo) if rank == 0 else 0
+    if rank == 0 and n_save < FLAGS.num_chains_to_save:
+        util.print("note: --num_chains_to_save={} exceeds rank 0's shard of {} chains; saving {}".format(
+            FLAGS.num_chains_to_save, hi - lo, n_save))
     res = inference.hmc(target, model_config, initial_step_size, z0, reparam=actual_reparam,
                         num_leapfrog_steps=FLAGS.num_leapfrog_steps, num_samples=FLAGS.num_samples,
                         num_burnin_steps=FLAGS.num_burnin_steps, num_adaptation_steps=FLAGS.num_adaptation_steps,
                         num_chains_to_save=n_save, seed=FLAGS.seed, chain_offset=lo, device=device,
                         precision=FLAGS.precision)
     ess_flat = distributed.gather_chains(res.ess_flat, device)            # [C, D] over all ranks
-    n_accepted = distributed.sum_scalar(float(res.is_accepted.sum()), device)
+    n_accepted = res.accept_stats[0]     # accepted kept transitions of ALL ranks (all-reduced inside inference.hmc)
     samples = res.samples
     mcmc_time = time.time() - start_time
     if rank != 0:
@@ -225,7 +229,7 @@ def run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False):
             "num_burnin_steps": FLAGS.num_burnin_steps})
     else:
         # superset of main.py:375-391: analyze.py:44-50 reads num_leapfrog_steps; ESS per second (un-normalised minimum
-        # ESS summed over chains / wall time) and the largest R-hat of this rank's chains are new
+        # ESS summed over chains / wall time) and the largest R-hat over the chains of ALL ranks are new
         min_ess_raw = np.nan_to_num(ess_flat).min(axis=1)
         save_hmc_results(file_path=file_path, ess_min=float(ess_min), sem_min=float(sem_min),
                          acceptance_rate=float(acceptance_rate), mcmc_time_sec=mcmc_time,
@@ -234,6 +238,14 @@ def run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False):
                          rhat_max=None if res.rhat is None else float(np.nanmax(res.rhat)))
         save_ess(file_path_base=file_path[:-5], samples=samples, param_names=param_names,
                  normalized_ess_final=normalized_ess_final, num_chains_to_save=FLAGS.num_chains_to_save)
+
+
+def _check_sharding(FLAGS, world):
+    """Every rank must own at least one chain: an empty shard would fail its kernel launch and leave the other
+    ranks waiting in the collectives.  Raised on ALL ranks, before any work."""
+    if FLAGS.num_chains < world:
+        raise ValueError("--num_chains={} is smaller than the number of ranks ({}): run with fewer GPUs".format(
+            FLAGS.num_chains, world))
 
 
 def _first_existing(results_dir, names):
@@ -267,6 +279,7 @@ def run_interleaved_hmc(FLAGS, model_config, results_dir, file_path):
         learned_variational_params_cp, param_names=param_names, num_inits=FLAGS.num_chains, rng=rng).values())
     (target_cp, target_ncp), _ = create_target_graph(FLAGS, model_config, results_dir)
     rank, world = distributed.rank_world()
+    _check_sharding(FLAGS, world)
     lo, hi = distributed.shard_range(FLAGS.num_chains, rank, world)
     device = distributed.local_device()
     x0 = model_config.join(initial_states_cp)[lo:hi]

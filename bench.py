@@ -43,7 +43,9 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--chains", type=int, default=16384, help="chains per GPU (weak scaling)")
+    p.add_argument("--chains", type=int, default=16384, help="chains per GPU (weak scaling) / in total (strong scaling)")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="weak: --chains per GPU; strong: --chains in total, sharded over the GPUs")
     p.add_argument("--method", default="NCP", choices=["CP", "NCP", "cVIP"])
     p.add_argument("--features", type=int, default=25, help="25 = BASELINE synthetic shape")
     p.add_argument("--num_leapfrog_steps", type=int, default=4)
@@ -207,17 +209,27 @@ def main():
         torch.cuda.synchronize()
 
     mc = models.from_data("german_credit_lognormalcentered", raw)
-    C, L, S = args.chains, args.num_leapfrog_steps, args.num_samples
+    L, S = args.num_leapfrog_steps, args.num_samples
+    if args.scaling == "strong":
+        from autoreparam_b200 import distributed
+        lo, hi = distributed.shard_range(args.chains, rank, world)
+        C, chain_lo = hi - lo, lo
+        assert C > 0, "more ranks than chains"
+    else:
+        C, chain_lo = args.chains, rank * args.chains
+    config["scaling"] = args.scaling
+    config["chains_total"] = args.chains if args.scaling == "strong" else args.chains * world
     z0, sigma_q = init_states(D, C, rank)
     eps0 = sigma_q / (L / 4.0) ** 2
     T = engine.hmc_num_transitions(S, args.num_burnin_steps)
-    evals_per_step = C * L * T
+    evals_per_step = C * L * T            # this rank
+    evals_all = config["chains_total"] * L * T   # all ranks
     z_dev = torch.as_tensor(z0, device=dev)
     bufs = {"samples": torch.empty((S, C, D), dtype=torch.float32, device=dev),
             "is_accepted": torch.empty((S, C), dtype=torch.uint8, device=dev)}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     kw = dict(num_leapfrog_steps=L, num_results=S, num_burnin_steps=args.num_burnin_steps,
-              num_adaptation_steps=args.num_adaptation_steps, chain_offset=rank * C, want_final=False,
+              num_adaptation_steps=args.num_adaptation_steps, chain_offset=chain_lo, want_final=False,
               engine=args.engine)
 
     def step(i):
@@ -246,8 +258,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
-    value = world * evals_per_step * args.steps / (ms * 1e-3)
-    acc_rate = float(out["is_accepted"].float().mean().item())
+    value = evals_all * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public API with host buffers
     target = graphs.TargetGraph(mc, args.method, a, b, False)
@@ -256,20 +267,20 @@ def main():
     d2h = C * D * 4 + S * C + C * 8 + D * 8   # ESS [C, D], is_accepted [S, C] u8, step_mult + accept_count [C], R-hat [D] f64
     inference.hmc(target, mc, step_sizes, z0, num_leapfrog_steps=L, num_samples=S,
                   num_burnin_steps=args.num_burnin_steps, num_adaptation_steps=args.num_adaptation_steps,
-                  seed=1, chain_offset=rank * C, device=dev, engine_kind=args.engine)
+                  seed=1, chain_offset=chain_lo, device=dev, engine_kind=args.engine)
     barrier()
     e0 = time.perf_counter()
     for i in range(args.steps):
         res = inference.hmc(target, mc, step_sizes, z0, num_leapfrog_steps=L, num_samples=S,
                             num_burnin_steps=args.num_burnin_steps, num_adaptation_steps=args.num_adaptation_steps,
-                            seed=2000 + i, chain_offset=rank * C, device=dev, engine_kind=args.engine)
+                            seed=2000 + i, chain_offset=chain_lo, device=dev, engine_kind=args.engine)
     barrier()
     e2e_s = time.perf_counter() - e0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e.item())
-    e2e_value = world * evals_per_step * args.steps / e2e_s
+    e2e_value = evals_all * args.steps / e2e_s
     # ESS / R-hat: per-chain min ESS gathered over ranks (NCCL), as util.get_min_ess consumes it
     min_ess = torch.as_tensor(np.nan_to_num(res.ess_flat).min(axis=1), device=dev)
     if world > 1:
@@ -289,12 +300,12 @@ def main():
         # 16 results / clk / SM (profiles/micro/pipes.cu), on the SMs the 128-chain tiles occupy
         n_pad = (1000 + 127) // 128 * 128
         mufu_per_obs = (1.0 + 0.25 + 0.25 / L) if args.features <= 32 else (2.0 + 1.0 / L)
-        sms_used = min(148, (C + 127) // 128)
+        sms_used = min(148, (C + 127) // 128)   # rank 0's tiles
         f_clk = 1e6 * (clocks.get("sm_mhz") or pk.get("sm_max_mhz", 1965.0))
         xu_roof = sms_used * f_clk / (n_pad * mufu_per_obs / 16.0)
         line = {
             "metric": metric, "value": value, "unit": "grad_evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "grad_evals/s", "h2d_bytes_per_step": int(h2d),
@@ -307,13 +318,18 @@ def main():
                          "note": "algorithmic fp32 flop (%.3g per grad eval) / measured dense bf16 cuBLAS peak (%s, "
                                  "sustained); per GPU" % (flop, pk_src),
                          "binding_pipe": {"pipe": "xu (MUFU), co-limited by instruction dispatch",
-                                          "achieved": value / world, "peak": xu_roof, "unit": "grad_evals/s per GPU",
-                                          "frac": value / world / xu_roof,
+                                          "achieved": evals_per_step * args.steps / (ms * 1e-3), "peak": xu_roof,
+                                          "unit": "grad_evals/s per GPU",
+                                          "frac": evals_per_step * args.steps / (ms * 1e-3) / xu_roof,
                                           "note": "%.4g MUFU ops per observation x %d padded observations, 16 MUFU "
                                                   "results/clk/SM (measured), %d SMs occupied by the 128-chain tiles, "
                                                   "SM clock sampled under load" % (mufu_per_obs, n_pad, sms_used)}},
+            # acceptance rate and R-hat are over the chains of ALL ranks: inference.hmc all-reduces the per-chain
+            # moments / accept counters (NCCL) inside the e2e timed region
             "ess": {"ess_per_sec": ess_per_sec, "ess_per_1000_grads_mean": ess_per_1000,
-                    "acceptance_rate": acc_rate, "rhat_max": None if res.rhat is None else float(np.nanmax(res.rhat))},
+                    "acceptance_rate": res.accept_stats[1] / (res.accept_stats[2] * T),
+                    "chains_reduced": int(res.accept_stats[2]),
+                    "rhat_max": None if res.rhat is None else float(np.nanmax(res.rhat))},
             "wall_s_timed_region": wall,
         }
         if world == 1 and not args.no_cpu_baseline:

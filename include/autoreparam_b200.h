@@ -90,6 +90,18 @@ int arp_model_num_coords(const arp_model* m);
 int arp_log_joint_grad(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
                        arp_real* lp, arp_real* grad, arp_real* centered, arp_real* abar, int mem, void* stream);
 
+/* Same contract (lp, grad, centered; no abar) through a chosen engine: ARP_ENGINE_AUTO / ARP_ENGINE_SIMT = the call
+ * above; ARP_ENGINE_TCGEN05 = the log-joint and gradient exactly as the tensor-core HMC engine computes them
+ * (german_credit models, fp32 build only) -- the elementwise parity hook for that engine.  A chain whose coefficients
+ * leave the fp16 range of the tensor-core operands is rejected by that engine: lp = -inf, grad = centered = NaN. */
+int arp_log_joint_grad_engine(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
+                              arp_real* lp, arp_real* grad, arp_real* centered, int engine, int mem, void* stream);
+
+#define ARP_ENGINE_AUTO 0     /* tcgen05 for german_credit with >= 256 chains, SIMT otherwise */
+#define ARP_ENGINE_SIMT 1     /* generic FP32 / FP64 SIMT kernels (every model) */
+#define ARP_ENGINE_TCGEN05 2  /* tcgen05 tensor-core engine (german_credit, 0/1 outcomes, <= 64 features, any N) */
+#define ARP_ENGINE_TCGEN05_STREAM 3  /* alias of 2 (round 1 had a second, shared-memory-resident tcgen05 kernel) */
+
 /* HMC configuration: inference.hmc (inference.py:198-242) + main.py flags. */
 typedef struct arp_hmc_config {
   int32_t num_leapfrog_steps;   /* --num_leapfrog_steps */
@@ -101,9 +113,7 @@ typedef struct arp_hmc_config {
   int64_t chain_offset;         /* global id of chain 0 (multi-GPU sharding: RNG is keyed by global id) */
   double target_accept_prob;    /* 0.75 [TFP default] */
   int32_t lanes_per_chain;      /* 0 = auto; 1,8,32 = force */
-  int32_t engine;               /* 0 = auto, 1 = generic FP32 SIMT kernels, 2 = tcgen05 (german credit), 3 = tcgen05 with
-                                   the design matrix streamed from L2 (up to 64 features, any N), 4 = streamed, two 64-chain
-                                   tiles per CTA out of phase (up to 32 features) */
+  int32_t engine;               /* ARP_ENGINE_* */
 } arp_hmc_config;
 
 /* Buffers of one HMC run.  `mem` applies to every non-NULL pointer here.
