@@ -50,16 +50,17 @@ class IlvBuffers(C.Structure):
 
 class ViConfig(C.Structure):
     _fields_ = [("num_mc_samples", C.c_int32), ("num_optimization_steps", C.c_int32), ("num_runs", C.c_int32),
-                ("learning_rates", C.c_double * ARP_VI_MAX_RUNS), ("seed", C.c_uint64), ("learn_a", C.c_int32)]
+                ("learning_rates", C.c_double * ARP_VI_MAX_RUNS), ("seed", C.c_uint64), ("num_params", C.c_int32),
+                ("discrete_prior", C.c_int32)]
 
 
 class ViBuffers(C.Structure):
-    _fields_ = [("loc", C.c_void_p), ("rho", C.c_void_p), ("a_logit", C.c_void_p), ("ext_eps", C.c_void_p),
-                ("elbo", C.c_void_p)]
+    _fields_ = [("loc", C.c_void_p), ("rho", C.c_void_p), ("u", C.c_void_p), ("a_index", C.c_void_p),
+                ("b_index", C.c_void_p), ("ext_eps", C.c_void_p), ("elbo", C.c_void_p), ("prior_logp", C.c_void_p)]
 
 
 # every symbol include/autoreparam_b200.h declares
-EXPORTS = ["arp_model_create", "arp_model_destroy", "arp_model_num_coords", "arp_log_joint_grad", "arp_log_joint_grad_engine",
+EXPORTS = ["arp_model_create", "arp_model_destroy", "arp_model_num_coords", "arp_log_joint_grad", "arp_log_joint_grad_engine", "arp_log_joint_param_grad",
            "arp_hmc_num_transitions", "arp_hmc_run", "arp_hmc_interleaved_run", "arp_ess", "arp_vi_run", "arp_kernel_launch_count",
            "arp_last_error", "arp_precision", "arp_release_cached_memory"]
 
@@ -112,6 +113,8 @@ def load(precision="f32"):
     lib.arp_log_joint_grad.restype = i32
     lib.arp_log_joint_grad_engine.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, i32, i32, vp]
     lib.arp_log_joint_grad_engine.restype = i32
+    lib.arp_log_joint_param_grad.argtypes = [vp, vp, vp, vp, i64, vp, vp, i32, vp]
+    lib.arp_log_joint_param_grad.restype = i32
     lib.arp_hmc_num_transitions.argtypes = [C.POINTER(HmcConfig)]
     lib.arp_hmc_num_transitions.restype = i64
     lib.arp_hmc_run.argtypes = [vp, C.POINTER(HmcConfig), vp, vp, i64, C.POINTER(HmcBuffers), i32, vp]

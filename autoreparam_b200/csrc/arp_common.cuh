@@ -123,6 +123,12 @@ __device__ __forceinline__ void site_rev(const Site& s, real xbar, real mu, real
   abar = mu * (s.usb - xbar * s.r);
 }
 
+// d log_joint / d b of one site: ln(sigma) [(u^2 - 1) - xbar (z - a mu) sigma^(1-b)].
+// Needed only when b is learned (untied VIP, or the paper's tied b = a): program_transformations.py:512-523.
+__device__ __forceinline__ real site_bbar(const Site& s, real xbar, real ls) {
+  return ls * ((s.usb * s.dz - (real)1) - xbar * s.dz * s.r);
+}
+
 // --------------------------------------------------------------- Philox ---
 #define ARP_STREAM_MOMENTUM 0u
 #define ARP_STREAM_ACCEPT 1u

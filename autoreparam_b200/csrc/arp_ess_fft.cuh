@@ -132,12 +132,28 @@ __host__ __device__ __forceinline__ void stockham_store(cplx<T>* buf, int j, int
 // named barrier among the ARP_FFT_TPF threads of one transform (ids 1 .. G/2)
 __device__ __forceinline__ void fft_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(ARP_FFT_TPF) : "memory"); }
 
-// forward transform of buf (length ARP_FFT_N, padded indexing) by the 128 threads of one group, in place
-template <typename T>
-__device__ __forceinline__ void fft2048(cplx<T>* buf, int t, int bar_id) {
+// forward transform of buf (length ARP_FFT_N, padded indexing) by the 128 threads of one group, in place.
+// FIRST: the input is the raw pair of series (x1 + i x2), S <= N / 2 samples; centring (mean m1 / m2, split hi + lo),
+// scaling to unit variance (s1 / s2) and the zero padding are applied while the first pass loads its operands, so the
+// padding never exists in shared memory and only the first 8 of the 16 operands are read at all.
+// HALF_OUT: only outputs k < N / 2 are stored by the last pass (the lags 0 .. S - 1 of the second transform).
+template <typename T, bool FIRST, bool HALF_OUT>
+__device__ __forceinline__ void fft2048(cplx<T>* buf, int t, int bar_id, int S, T m1h, T m1l, T s1, T m2h, T m2l, T s2) {
   cplx<T> v[16];
   // pass 1: radix 16, Ns = 1 (no twiddles)
-  stockham_load<T, 16>(buf, t, 1, v);
+  if constexpr (FIRST) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int idx = t + r * (ARP_FFT_N / 16);
+      v[r] = cplx<T>{0, 0};
+      if (r < 8 && idx < S) {                       // S <= N / 2: operands 8 .. 15 are padding
+        const cplx<T> raw = buf[ARP_FFT_PAD(idx)];
+        v[r] = cplx<T>{((raw.x - m1h) - m1l) * s1, ((raw.y - m2h) - m2l) * s2};
+      }
+    }
+  } else {
+    stockham_load<T, 16>(buf, t, 1, v);
+  }
   dft16(v);
   fft_bar(bar_id);
   stockham_store<T, 16>(buf, t, 1, v);
@@ -156,7 +172,11 @@ __device__ __forceinline__ void fft2048(cplx<T>* buf, int t, int bar_id) {
   }
   fft_bar(bar_id);
 #pragma unroll
-  for (int h = 0; h < 2; ++h) stockham_store<T, 8>(buf, t + h * ARP_FFT_TPF, 256, v + 8 * h);
+  for (int h = 0; h < 2; ++h) {
+    const int j = t + h * ARP_FFT_TPF;               // Ns = 256 = N / 8: output index j + 256 r
+#pragma unroll
+    for (int r = 0; r < (HALF_OUT ? 4 : 8); ++r) buf[ARP_FFT_PAD(j + r * 256)] = v[8 * h + r];
+  }
   fft_bar(bar_id);
 }
 
@@ -166,55 +186,65 @@ __global__ void __launch_bounds__(ARP_FFT_THREADS, ARP_FFT_MINB)
 k_ess_fft(const T* __restrict__ x, int S, long long n, T* __restrict__ ess, T* __restrict__ mean_out, T* __restrict__ var_out) {
   extern __shared__ __align__(16) unsigned char ess_smem[];
   cplx<T>* bufs = reinterpret_cast<cplx<T>*>(ess_smem);                                   // [G/2][ARP_FFT_BUF]
-  double* red = reinterpret_cast<double*>(ess_smem + sizeof(cplx<T>) * (ARP_FFT_G / 2) * ARP_FFT_BUF);   // [THREADS / 32][G] partial sums
-  __shared__ double mean_s[ARP_FFT_G];
+  double* red = reinterpret_cast<double*>(ess_smem + sizeof(cplx<T>) * (ARP_FFT_G / 2) * ARP_FFT_BUF);   // [2][THREADS / 32][G] partial sums
+  __shared__ double mean_s[ARP_FFT_G], var_s[ARP_FFT_G], sum_s[ARP_FFT_G];
   __shared__ int kneg_s[ARP_FFT_G];
-  __shared__ double sum_s[ARP_FFT_G];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = ARP_FFT_THREADS / 32;
   const long long i0 = (long long)blockIdx.x * ARP_FFT_G;
-  // ---- load: thread tid reads column j = tid % G of rows tid / G, tid / G + THREADS / G, ...
+  // ---- load: thread tid reads column j = tid % G of rows tid / G, tid / G + THREADS / G, ... (whole 32-byte sectors per
+  // row); raw values go to shared memory, sum and sum of squares accumulate in double
   {
     const int j = tid % ARP_FFT_G;
     const bool col_ok = i0 + j < n;
     T* dst = reinterpret_cast<T*>(bufs + (size_t)(j >> 1) * ARP_FFT_BUF) + (j & 1);
-    double part = 0;
-    for (int t = tid / ARP_FFT_G; t < ARP_FFT_N; t += ARP_FFT_THREADS / ARP_FFT_G) {
-      T v = 0;
-      if (t < S && col_ok) v = x[(size_t)t * n + i0 + j];
-      part += (double)v;
+    double p1 = 0, p2 = 0;
+    for (int t = tid / ARP_FFT_G; t < S; t += ARP_FFT_THREADS / ARP_FFT_G) {
+      const T v = col_ok ? x[(size_t)t * n + i0 + j] : (T)0;
+      p1 += (double)v;
+      p2 += (double)v * (double)v;
       dst[2 * ARP_FFT_PAD(t)] = v;
     }
     // lanes with the same j: lane, lane ^ 8, ^ 16 (G = 8 divides 32)
-    part += __shfl_xor_sync(0xffffffffu, part, 8);
-    part += __shfl_xor_sync(0xffffffffu, part, 16);
-    if (lane < ARP_FFT_G) red[warp * ARP_FFT_G + lane] = part;
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 8);  p2 += __shfl_xor_sync(0xffffffffu, p2, 8);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, 16); p2 += __shfl_xor_sync(0xffffffffu, p2, 16);
+    if (lane < ARP_FFT_G) { red[warp * ARP_FFT_G + lane] = p1; red[(NW + warp) * ARP_FFT_G + lane] = p2; }
   }
   __syncthreads();
   if (tid < ARP_FFT_G) {
-    double s = 0;
-    for (int w = 0; w < ARP_FFT_THREADS / 32; ++w) s += red[w * ARP_FFT_G + tid];
-    mean_s[tid] = s / S;
+    double s1 = 0, s2 = 0;
+    for (int w = 0; w < NW; ++w) { s1 += red[w * ARP_FFT_G + tid]; s2 += red[(NW + w) * ARP_FFT_G + tid]; }
+    const double m = s1 / S;
+    double v = s2 / S - m * m;                       // biased variance (= lag-0 autocovariance), one pass in double
+    if (v < 0.0) v = 0.0;
+    // a constant series has s2 / S == m * m up to double rounding: treat anything below 1e-24 of the second moment as
+    // zero (an fp32 series cannot carry a relative variance that small)
+    if (v <= 1e-24 * (s2 / S)) v = 0.0;
+    mean_s[tid] = m;
+    var_s[tid] = v;
     kneg_s[tid] = S;     // first lag with a negative autocorrelation (S = none)
     sum_s[tid] = 0;
-    if (mean_out && i0 + tid < n) mean_out[i0 + tid] = (T)(s / S);
-  }
-  __syncthreads();
-  // ---- centre (only the S real samples; the padding stays 0)
-  {
-    const int j = tid % ARP_FFT_G;
-    T* dst = reinterpret_cast<T*>(bufs + (size_t)(j >> 1) * ARP_FFT_BUF) + (j & 1);
-    const double m = mean_s[j];
-    const T mh = (T)m, ml = (T)(m - (double)mh);
-    for (int t = tid / ARP_FFT_G; t < S; t += ARP_FFT_THREADS / ARP_FFT_G) {
-      T& r = dst[2 * ARP_FFT_PAD(t)];
-      r = (r - mh) - ml;
+    if (i0 + tid < n) {
+      if (mean_out) mean_out[i0 + tid] = (T)m;
+      if (var_out) var_out[i0 + tid] = (T)v;
     }
   }
   __syncthreads();
   // ---- per pair of series: forward transform, power spectra, forward transform again
   const int grp = tid / ARP_FFT_TPF, t = tid % ARP_FFT_TPF;
   cplx<T>* buf = bufs + (size_t)grp * ARP_FFT_BUF;
-  fft2048<T>(buf, t, 1 + grp);
+  {
+    // centring with a two-term mean (hi + lo); scaling to unit variance: ESS does not depend on the scale of a series,
+    // but the two series that share one complex transform see each other's rounding noise -- without the scaling a
+    // series 1e4 x smaller than its partner would inherit a relative error of 1e4 x 2^-24.  A constant or non-finite
+    // series is zeroed so that it cannot contaminate its partner.
+    const double ma = mean_s[2 * grp], mb = mean_s[2 * grp + 1], va = var_s[2 * grp], vb = var_s[2 * grp + 1];
+    const bool oka = va > 0.0 && va < (double)INFINITY, okb = vb > 0.0 && vb < (double)INFINITY;
+    const T mah = oka ? (T)ma : (T)0, mbh = okb ? (T)mb : (T)0;
+    const T mal = oka ? (T)(ma - (double)mah) : (T)0, mbl = okb ? (T)(mb - (double)mbh) : (T)0;
+    const T sa = oka ? (T)(1.0 / sqrt(va)) : (T)0, sb = okb ? (T)(1.0 / sqrt(vb)) : (T)0;
+    fft2048<T, true, false>(buf, t, 1 + grp, S, mah, mal, sa, mbh, mbl, sb);
+  }
   // W_k = |X1_k|^2 + i |X2_k|^2 with X1 = (Z_k + conj Z_{N-k}) / 2, X2 = (Z_k - conj Z_{N-k}) / (2 i); W_{N-k} = W_k
   for (int k = t; k <= ARP_FFT_N / 2; k += ARP_FFT_TPF) {
     const int km = (ARP_FFT_N - k) & (ARP_FFT_N - 1);
@@ -226,8 +256,8 @@ k_ess_fft(const T* __restrict__ x, int S, long long n, T* __restrict__ ess, T* _
     buf[ARP_FFT_PAD(km)] = w;
   }
   fft_bar(1 + grp);
-  fft2048<T>(buf, t, 1 + grp);
-  // buf[k] = N (c1_k + i c2_k) for k < S (the factor N cancels in rho)
+  fft2048<T, false, true>(buf, t, 1 + grp, S, 0, 0, 0, 0, 0, 0);
+  // buf[k] = N (c1_k + i c2_k) for k < N / 2 (the factor N cancels in rho)
   // ---- ESS per series: 64 threads each
   {
     const int sidx = 2 * grp + (t >> 6);          // series within the CTA
@@ -235,12 +265,13 @@ k_ess_fft(const T* __restrict__ x, int S, long long n, T* __restrict__ ess, T* _
     const T* c = reinterpret_cast<const T*>(buf) + (t >> 6);
     const double c0 = (double)c[0];
     const double inv0 = (double)S / c0;
+    const bool live = var_s[sidx] > 0.0 && var_s[sidx] < (double)INFINITY && c0 > 0.0;   // constant / non-finite series: NaN, as TFP
     int kneg = S;
     for (int k = u; k < S; k += 64) {
       const double rho = (double)c[2 * ARP_FFT_PAD(k)] / (double)(S - k) * inv0;
       if (rho < 0.0) { kneg = k; break; }          // k increases: the first negative lag this thread sees
     }
-    if (c0 > 0.0) atomicMin(&kneg_s[sidx], kneg);
+    if (live) atomicMin(&kneg_s[sidx], kneg);
     fft_bar(1 + grp);
     const int kn = kneg_s[sidx];
     double part = 0;
@@ -250,12 +281,8 @@ k_ess_fft(const T* __restrict__ x, int S, long long n, T* __restrict__ ess, T* _
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if ((u & 31) == 0) atomicAdd(&sum_s[sidx], part);
     fft_bar(1 + grp);
-    if (u == 0 && i0 + sidx < n) {
-      const double acov0 = c0 / ARP_FFT_N / S;
-      if (var_out) var_out[i0 + sidx] = (T)acov0;
-      // constant (or non-finite) series: TFP yields NaN
-      ess[i0 + sidx] = (c0 > 0.0) ? (T)((double)S / (-1.0 + 2.0 * sum_s[sidx])) : (T)NAN;
-    }
+    if (u == 0 && i0 + sidx < n)
+      ess[i0 + sidx] = live ? (T)((double)S / (-1.0 + 2.0 * sum_s[sidx])) : (T)NAN;
   }
 }
 #endif  // __CUDACC__

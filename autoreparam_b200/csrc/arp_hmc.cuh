@@ -45,7 +45,8 @@ struct HmcArgs {
 template <int KIND, int LPC, bool WITH_A, int FP>
 __global__ void __launch_bounds__(ARP_BLOCK)
 k_log_joint_grad(DevModel m, const real* __restrict__ a, const real* __restrict__ b,
-                 const real* z, int C, real* lp_out, real* g_scratch, real* xc_scratch, real* abar_scratch) {
+                 const real* z, int C, real* lp_out, real* g_scratch, real* xc_scratch, real* abar_scratch,
+                 real* bbar_scratch) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int chain = gtid / LPC;
   const int sub = gtid % LPC;
@@ -54,8 +55,8 @@ k_log_joint_grad(DevModel m, const real* __restrict__ a, const real* __restrict_
   const int zc = chain < C ? chain : C - 1;
   Vec vz{const_cast<real*>(z) + (size_t)zc * m.D, 1};
   Vec vg_{g_scratch + off, 1}, vxc{xc_scratch + off, 1};
-  Vec vab{abar_scratch ? abar_scratch + off : nullptr, 1};
-  real lp = vg<KIND, LPC, WITH_A, FP>(m, a, b, vz, vg_, vxc, vab, sub, true);
+  Vec vab{abar_scratch ? abar_scratch + off : nullptr, 1}, vbb{bbar_scratch ? bbar_scratch + off : nullptr, 1};
+  real lp = vg<KIND, LPC, WITH_A, FP>(m, a, b, vz, vg_, vxc, vab, vbb, sub, true);
   if (chain < C && sub == 0 && lp_out) lp_out[chain] = lp;
 }
 
@@ -70,7 +71,7 @@ k_hmc_init(DevModel m, HmcWs ws, HmcArgs p, const real* z0) {
   Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
   for (int d = sub; d < p.D; d += LPC) Z(d) = valid ? z0[(size_t)chain * p.D + d] : (real)0;
   __syncwarp();
-  real lp = vg<KIND, LPC, false, FP>(m, p.a, p.b, Z, G, XC, Vec{nullptr, 1}, sub, true);
+  real lp = vg<KIND, LPC, false, FP>(m, p.a, p.b, Z, G, XC, Vec{nullptr, 1}, Vec{nullptr, 1}, sub, true);
   if (sub == 0) {
     ws.lp[chain] = lp;
     ws.H[chain] = 0;
@@ -140,7 +141,7 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
       }
       __syncwarp();
       const bool last = (l == p.L - 1);
-      lpx = vg<KIND, LPC, false, FP>(m, p.a, p.b, X, GX, XCX, Vec{nullptr, 1}, sub, last);
+      lpx = vg<KIND, LPC, false, FP>(m, p.a, p.b, X, GX, XCX, Vec{nullptr, 1}, Vec{nullptr, 1}, sub, last);
       __syncwarp();
       for (int d = sub; d < D; d += LPC) {
         const real e = ldg(eps0 + d) * mult;
@@ -249,7 +250,7 @@ k_hmc_interleaved(DevModel m, HmcWs ws, HmcArgs p, IlvArgs q, const real* x0) {
       // ---- centred -> rule coordinates, re-bootstrap
       to_rule<KIND, LPC>(m, a, b, XC, Z, sub);
       __syncwarp();
-      real lp_cur = vg<KIND, LPC, false, FP>(m, a, b, Z, G, XC, Vec{nullptr, 1}, sub, true);
+      real lp_cur = vg<KIND, LPC, false, FP>(m, a, b, Z, G, XC, Vec{nullptr, 1}, Vec{nullptr, 1}, sub, true);
       __syncwarp();
       // ---- one HMC step (same op order as k_hmc_run)
       real ke0 = 0;
@@ -281,7 +282,7 @@ k_hmc_interleaved(DevModel m, HmcWs ws, HmcArgs p, IlvArgs q, const real* x0) {
         }
         __syncwarp();
         const bool last = (l == L - 1);
-        lpx = vg<KIND, LPC, false, FP>(m, a, b, X, GX, XCX, Vec{nullptr, 1}, sub, last);
+        lpx = vg<KIND, LPC, false, FP>(m, a, b, X, GX, XCX, Vec{nullptr, 1}, Vec{nullptr, 1}, sub, last);
         __syncwarp();
         for (int d = sub; d < D; d += LPC) {
           const real e = ldg(eps0 + d) * mult[r];

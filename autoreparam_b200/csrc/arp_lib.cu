@@ -248,16 +248,16 @@ static int stage_in(DevBuf& buf, const void* src, size_t bytes, int mem, cudaStr
 }
 
 // -------------------------------------------------------- log joint + gradient ---
-extern "C" int arp_log_joint_grad(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
-                                  arp_real* lp, arp_real* grad, arp_real* centered, arp_real* abar, int mem,
-                                  void* stream) {
+static int log_joint_grad_impl(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
+                               arp_real* lp, arp_real* grad, arp_real* centered, arp_real* abar, arp_real* bbar, int mem,
+                               void* stream) {
   if (!m || !a || !b || !z || C <= 0) return fail("arp_log_joint_grad: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int D = m->dev.D;
   const int lpc = pick_lpc(m, C, 0);
   const int cpb = ARP_BLOCK / lpc;
   const long long Cpad = round_up(C, cpb);
-  DevBuf da, db, dz, dlp, dg, dxc, dab;
+  DevBuf da, db, dz, dlp, dg, dxc, dab, dbb;
   if (stage_in(da, a, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
   if (stage_in(db, b, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
   const real* zdev = z;
@@ -265,19 +265,22 @@ extern "C" int arp_log_joint_grad(arp_model* m, const arp_real* a, const arp_rea
     if (stage_in(dz, z, (size_t)C * D * sizeof(real), mem, st)) return 1;
     zdev = dz.as<real>();
   }
+  const bool with_a = abar != nullptr || bbar != nullptr;
   ARP_CUDA(dlp.alloc(Cpad * sizeof(real)));
   ARP_CUDA(dg.alloc((size_t)Cpad * D * sizeof(real)));
   ARP_CUDA(dxc.alloc((size_t)Cpad * D * sizeof(real)));
-  if (abar) ARP_CUDA(dab.alloc((size_t)Cpad * D * sizeof(real)));
+  if (with_a) {
+    ARP_CUDA(dab.alloc((size_t)Cpad * D * sizeof(real)));
+    ARP_CUDA(dbb.alloc((size_t)Cpad * D * sizeof(real)));
+  }
   const dim3 grid((unsigned)(Cpad / cpb)), block(ARP_BLOCK);
   const DevModel dm = m->dev;
   const int fp = m->fp;
-  const bool with_a = abar != nullptr;
 #define BODY(KIND, LPC, FP)                                                                              \
   if (with_a) k_log_joint_grad<KIND, LPC, true, FP><<<grid, block, 0, st>>>(                              \
-      dm, da.as<real>(), db.as<real>(), zdev, (int)C, dlp.as<real>(), dg.as<real>(), dxc.as<real>(), dab.as<real>()); \
+      dm, da.as<real>(), db.as<real>(), zdev, (int)C, dlp.as<real>(), dg.as<real>(), dxc.as<real>(), dab.as<real>(), dbb.as<real>()); \
   else k_log_joint_grad<KIND, LPC, false, FP><<<grid, block, 0, st>>>(                                    \
-      dm, da.as<real>(), db.as<real>(), zdev, (int)C, dlp.as<real>(), dg.as<real>(), dxc.as<real>(), nullptr);
+      dm, da.as<real>(), db.as<real>(), zdev, (int)C, dlp.as<real>(), dg.as<real>(), dxc.as<real>(), nullptr, nullptr);
   ARP_DISPATCH(dm.kind, lpc, fp, BODY)
 #undef BODY
   ARP_LAUNCH_CHECK();
@@ -286,8 +289,20 @@ extern "C" int arp_log_joint_grad(arp_model* m, const arp_real* a, const arp_rea
   if (grad) ARP_CUDA(cudaMemcpyAsync(grad, dg.p, (size_t)C * D * sizeof(real), kd, st));
   if (centered) ARP_CUDA(cudaMemcpyAsync(centered, dxc.p, (size_t)C * D * sizeof(real), kd, st));
   if (abar) ARP_CUDA(cudaMemcpyAsync(abar, dab.p, (size_t)C * D * sizeof(real), kd, st));
+  if (bbar) ARP_CUDA(cudaMemcpyAsync(bbar, dbb.p, (size_t)C * D * sizeof(real), kd, st));
   ARP_CUDA(cudaStreamSynchronize(st));  // temporaries are freed on return
   return 0;
+}
+
+extern "C" int arp_log_joint_grad(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
+                                  arp_real* lp, arp_real* grad, arp_real* centered, arp_real* abar, int mem,
+                                  void* stream) {
+  return log_joint_grad_impl(m, a, b, z, C, lp, grad, centered, abar, nullptr, mem, stream);
+}
+
+extern "C" int arp_log_joint_param_grad(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
+                                        arp_real* abar, arp_real* bbar, int mem, void* stream) {
+  return log_joint_grad_impl(m, a, b, z, C, nullptr, nullptr, nullptr, abar, bbar, mem, stream);
 }
 
 // Same contract, chosen engine.  engine 0 / 1: the SIMT kernel above.  engine 2 / 3: the gradient as the tcgen05 HMC
@@ -604,7 +619,7 @@ extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D,
   DevBuf dxt;
   if (S <= ARP_FFT_MAXS && !ess_force_direct()) {
     // shared-memory FFT (arp_ess_fft.cuh): every lag at once, the samples cross HBM once, no transposed copy
-    const size_t smem = sizeof(cplx<real>) * (ARP_FFT_G / 2) * ARP_FFT_BUF + sizeof(double) * (ARP_FFT_THREADS / 32) * ARP_FFT_G;
+    const size_t smem = sizeof(cplx<real>) * (ARP_FFT_G / 2) * ARP_FFT_BUF + sizeof(double) * 2 * (ARP_FFT_THREADS / 32) * ARP_FFT_G;
     ARP_CUDA(cudaFuncSetAttribute(k_ess_fft<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned fg = (unsigned)((n + ARP_FFT_G - 1) / ARP_FFT_G);
     k_ess_fft<real><<<fg, ARP_FFT_THREADS, smem, st>>>(in, (int)S, (long long)n, out, omean, ovar);
@@ -637,7 +652,9 @@ extern "C" int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D,
 extern "C" int arp_vi_run(arp_model* m, const arp_vi_config* cfg, const arp_real* a, const arp_real* b,
                           const arp_vi_buffers* buf, int mem, void* stream) {
   if (!m || !cfg || !a || !b || !buf || !buf->loc || !buf->rho || !buf->elbo) return fail("arp_vi_run: bad argument");
-  if (cfg->learn_a && !buf->a_logit) return fail("arp_vi_run: learn_a needs a_logit");
+  const int P = cfg->num_params;
+  if (P < 0 || P > 2 * m->dev.D) return fail("arp_vi_run: num_params out of range");
+  if (P > 0 && (!buf->u || !buf->a_index || !buf->b_index)) return fail("arp_vi_run: num_params > 0 needs u, a_index and b_index");
   if (cfg->num_mc_samples < 1 || cfg->num_mc_samples > ARP_VI_MAX_S || cfg->num_optimization_steps < 1)
     return fail("arp_vi_run: num_mc_samples must be in [1, " + std::to_string(ARP_VI_MAX_S) + "]");
   if (cfg->num_runs < 1 || cfg->num_runs > ARP_VI_MAX_RUNS) return fail("arp_vi_run: num_runs out of range");
@@ -645,33 +662,44 @@ extern "C" int arp_vi_run(arp_model* m, const arp_vi_config* cfg, const arp_real
   const int D = m->dev.D, R = cfg->num_runs;
   const int S = cfg->num_mc_samples, steps = cfg->num_optimization_steps;
   const bool host = mem == ARP_MEM_HOST;
-  DevBuf da, db, dloc, drho, dal, deps, delbo, dws;
+  if (P > 0)
+    for (int d = 0; d < D; ++d)
+      if (buf->a_index[d] < -1 || buf->a_index[d] >= P || buf->b_index[d] < -1 || buf->b_index[d] >= P)
+        return fail("arp_vi_run: a_index / b_index entry out of range");
+  DevBuf da, db, dloc, drho, du, dia, dib, deps, delbo, dplp, dws;
   if (stage_in(da, a, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
   if (stage_in(db, b, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
-  real *loc = buf->loc, *rho = buf->rho, *al = buf->a_logit, *elbo = buf->elbo;
+  if (P > 0) {
+    if (stage_in(dia, buf->a_index, D * sizeof(int), ARP_MEM_HOST, st)) return 1;
+    if (stage_in(dib, buf->b_index, D * sizeof(int), ARP_MEM_HOST, st)) return 1;
+  }
+  real *loc = buf->loc, *rho = buf->rho, *u = buf->u, *elbo = buf->elbo, *plp = buf->prior_logp;
   const real* eps = buf->ext_eps;
-  const size_t pbytes = (size_t)R * D * sizeof(real);
+  const size_t pbytes = (size_t)R * D * sizeof(real), ubytes = (size_t)R * P * sizeof(real);
   if (host) {
     if (stage_in(dloc, loc, pbytes, mem, st)) return 1;
     if (stage_in(drho, rho, pbytes, mem, st)) return 1;
     loc = dloc.as<real>(); rho = drho.as<real>();
-    if (cfg->learn_a) { if (stage_in(dal, al, pbytes, mem, st)) return 1; al = dal.as<real>(); }
+    if (P > 0) { if (stage_in(du, u, ubytes, mem, st)) return 1; u = du.as<real>(); }
     if (eps) { if (stage_in(deps, eps, (size_t)steps * S * D * sizeof(real), mem, st)) return 1; eps = deps.as<real>(); }
     ARP_CUDA(delbo.alloc((size_t)R * steps * sizeof(real)));
     elbo = delbo.as<real>();
+    if (plp) { ARP_CUDA(dplp.alloc((size_t)R * steps * sizeof(real))); plp = dplp.as<real>(); }
   }
   ViArgs v{};
-  v.D = D; v.S = S; v.steps = steps; v.R = R; v.seed = cfg->seed; v.learn_a = cfg->learn_a;
+  v.D = D; v.S = S; v.steps = steps; v.R = R; v.P = P; v.discrete_prior = cfg->discrete_prior; v.seed = cfg->seed;
   for (int r = 0; r < R; ++r) v.lrs[r] = (real)cfg->learning_rates[r];
-  v.loc = loc; v.rho = rho; v.a_logit = al; v.ext_eps = eps; v.elbo = elbo;
+  v.loc = loc; v.rho = rho; v.u = u; v.ia = dia.as<int>(); v.ib = dib.as<int>(); v.ext_eps = eps; v.elbo = elbo;
+  v.prior_logp = plp;
   v.a_in = da.as<real>(); v.b_in = db.as<real>();
   int rc = vi_launch(m->dev, m->fp, v, st, &dws, &g_launches, &g_last_error);
   if (rc) return rc;
   if (host) {
     ARP_CUDA(cudaMemcpyAsync(buf->loc, loc, pbytes, cudaMemcpyDeviceToHost, st));
     ARP_CUDA(cudaMemcpyAsync(buf->rho, rho, pbytes, cudaMemcpyDeviceToHost, st));
-    if (cfg->learn_a) ARP_CUDA(cudaMemcpyAsync(buf->a_logit, al, pbytes, cudaMemcpyDeviceToHost, st));
+    if (P > 0) ARP_CUDA(cudaMemcpyAsync(buf->u, u, ubytes, cudaMemcpyDeviceToHost, st));
     ARP_CUDA(cudaMemcpyAsync(buf->elbo, elbo, (size_t)R * steps * sizeof(real), cudaMemcpyDeviceToHost, st));
+    if (buf->prior_logp) ARP_CUDA(cudaMemcpyAsync(buf->prior_logp, plp, (size_t)R * steps * sizeof(real), cudaMemcpyDeviceToHost, st));
   }
   ARP_CUDA(cudaStreamSynchronize(st));
   return 0;

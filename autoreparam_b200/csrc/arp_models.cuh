@@ -6,12 +6,13 @@
 // with bit-identical scalars), and the state vectors live in (L1/L2-cached)
 // global memory behind a strided accessor.
 //
-//   lp = vg<KIND, LPC, WITH_A, FP>(m, a, b, z, g, xc, abar, sub, want_lp)
+//   lp = vg<KIND, LPC, WITH_A, FP>(m, a, b, z, g, xc, abar, bbar, sub, want_lp)
 //     z     in   state coordinates (trace order)
 //     g     out  d log_joint / d z
 //     xc    out  centred value of every coordinate (= make_to_centered(z),
 //                reference models.py:59-81); also used as scratch between lanes
 //     abar  out  d log_joint / d a per coordinate (only if WITH_A; cVIP VI)
+//     bbar  out  d log_joint / d b per coordinate (only if WITH_A; VI with a learned b)
 //     returns log_joint (valid only if want_lp; the gradient never needs it)
 //
 // Model bodies follow reference models.py (line ranges per function) with the
@@ -61,7 +62,7 @@ __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
 // reference models.py:139-147.  z = [mu, log_tau, theta[8]]
 template <int LPC, bool WITH_A>
 __device__ real vg_8schools(const DevModel& m, const real* a, const real* b,
-                            Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+                            Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
   real lp_top = 0;
   const real a0 = (*(a + 0)), b0 = (*(b + 0)), a1 = (*(a + 1)), b1 = (*(b + 1));
   Site smu = site_fwd(z(0), (real)0, ARP_LOG_5, a0, b0, lp_top);
@@ -78,7 +79,7 @@ __device__ real vg_8schools(const DevModel& m, const real* a, const real* b,
     site_rev(st, e / sig, mu, ai, bi, zb, mb, lb, ab);
     g(2 + i) = zb;
     xc(2 + i) = st.x;
-    if (WITH_A) abar(2 + i) = ab;
+    if (WITH_A) { abar(2 + i) = ab; bbar(2 + i) = site_bbar(st, e / sig, lt); }
     acc_mu += mb;
     acc_lt += lb;
   }
@@ -93,7 +94,10 @@ __device__ real vg_8schools(const DevModel& m, const real* a, const real* b,
     site_rev(slt, acc_lt, (real)0, a1, b1, zb, mb, lb, ab);
     g(1) = zb;
     xc(1) = lt;
-    if (WITH_A) { abar(0) = 0; abar(1) = 0; }
+    if (WITH_A) {
+      abar(0) = 0; abar(1) = 0;
+      bbar(0) = site_bbar(smu, acc_mu, ARP_LOG_5); bbar(1) = site_bbar(slt, acc_lt, ARP_LOG_5);
+    }
   }
   return lp;
 }
@@ -157,7 +161,7 @@ __device__ real german_likelihood(const DevModel& m, Vec xc, Vec g, int beta_off
 // z = [overall_log_scale, beta_log_scales[F], beta[F]]
 template <int LPC, bool WITH_A, int FP, bool GAMMA>
 __device__ real vg_german(const DevModel& m, const real* a, const real* b,
-                          Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+                          Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
   const int F = m.F;
   real lp_top = 0;
   const real a0 = (*a), b0 = (*b);
@@ -191,9 +195,10 @@ __device__ real vg_german(const DevModel& m, const real* a, const real* b,
       const real v = z(1 + f);
       const real ls = s0x + v;
       Site sb = site_fwd(z(1 + F + f), (real)0, ls, ab_, bb_, lp_sites);
-      site_rev(sb, g(1 + F + f), (real)0, ab_, bb_, zb, mb, lb, ab);
+      const real xb = g(1 + F + f);
+      site_rev(sb, xb, (real)0, ab_, bb_, zb, mb, lb, ab);
       g(1 + F + f) = zb;
-      if (WITH_A) { abar(1 + F + f) = 0; abar(1 + f) = 0; }
+      if (WITH_A) { abar(1 + F + f) = 0; abar(1 + f) = 0; bbar(1 + F + f) = site_bbar(sb, xb, ls); bbar(1 + f) = 0; }
       // log Gamma(1/2, 1/2) density of v: 0.5 v - 0.5 e^v + 0.5 log 0.5 - lgamma(0.5)
       const real ev = r_exp(v);
       lp_sites += (real)0.5 * v - (real)0.5 * ev + (real)(-0.34657359027997264 - 0.57236494292470008);
@@ -202,13 +207,14 @@ __device__ real vg_german(const DevModel& m, const real* a, const real* b,
     } else {
       Site ss = site_fwd_unit(z(1 + f), s0x, af, lp_sites);
       Site sb = site_fwd(z(1 + F + f), (real)0, ss.x, ab_, bb_, lp_sites);
-      site_rev(sb, g(1 + F + f), (real)0, ab_, bb_, zb, mb, lb, ab);
+      const real xb = g(1 + F + f);
+      site_rev(sb, xb, (real)0, ab_, bb_, zb, mb, lb, ab);
       g(1 + F + f) = zb;
-      if (WITH_A) abar(1 + F + f) = 0;
+      if (WITH_A) { abar(1 + F + f) = 0; bbar(1 + F + f) = site_bbar(sb, xb, ss.x); }
       real zb2, mb2, lb2, ab2;
       site_rev(ss, lb, s0x, af, (real)1, zb2, mb2, lb2, ab2);
       g(1 + f) = zb2;
-      if (WITH_A) abar(1 + f) = ab2;
+      if (WITH_A) { abar(1 + f) = ab2; bbar(1 + f) = 0; }   // unit prior scale: no dependence on b
       acc0 += mb2;
     }
   }
@@ -219,7 +225,7 @@ __device__ real vg_german(const DevModel& m, const real* a, const real* b,
     site_rev(s0, acc0, (real)0, a0, b0, zb, mb, lb, ab);
     g(0) = zb;
     xc(0) = s0x;
-    if (WITH_A) abar(0) = 0;
+    if (WITH_A) { abar(0) = 0; bbar(0) = site_bbar(s0, acc0, ARP_LOG_10); }
   }
   return lp;
 }
@@ -229,7 +235,7 @@ __device__ real vg_german(const DevModel& m, const real* a, const real* b,
 // z = [mua, b1, b2, m[J]] (+ log_m_stddv[J]); observations sorted by county, CSR.
 template <int LPC, bool WITH_A, bool STDDVS>
 __device__ real vg_radon(const DevModel& m, const real* a, const real* b,
-                         Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+                         Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
   const int J = m.J;
   real lp_top = 0;
   const real a0 = (*a), a1 = (*(a + 1)), a2 = (*(a + 2));
@@ -270,14 +276,14 @@ __device__ real vg_radon(const DevModel& m, const real* a, const real* b,
     site_rev(sm, se * inv2, mu_j, aj, (real)1, zb, mb, lb, ab);
     g(3 + j) = zb;
     xc(3 + j) = mj;
-    if (WITH_A) abar(3 + j) = ab;
+    if (WITH_A) { abar(3 + j) = ab; bbar(3 + j) = 0; }
     acc_mua += mb;
     acc_b1 += uj * mb;
     if (STDDVS) {
       site_rev(sl, see * inv2 - cnt, (real)0, (real)0, (real)1, zb, mb, lb, ab);
       g(3 + J + j) = zb;
       xc(3 + J + j) = lsj;
-      if (WITH_A) abar(3 + J + j) = 0;
+      if (WITH_A) { abar(3 + J + j) = 0; bbar(3 + J + j) = 0; }
     }
   }
   acc_mua = group_sum<LPC>(acc_mua);
@@ -292,7 +298,7 @@ __device__ real vg_radon(const DevModel& m, const real* a, const real* b,
     g(1) = zb; xc(1) = b1;
     site_rev(sb2, acc_b2, (real)0, a2, (real)1, zb, mb, lb, ab);
     g(2) = zb; xc(2) = b2;
-    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(2) = 0; }
+    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(2) = 0; bbar(0) = 0; bbar(1) = 0; bbar(2) = 0; }
   }
   return lp;
 }
@@ -305,7 +311,7 @@ __device__ real vg_radon(const DevModel& m, const real* a, const real* b,
 // (w = count, y = sum of y): sum over equal-eta observations, exact.
 template <int LPC, bool WITH_A>
 __device__ real vg_election(const DevModel& m, const real* a, const real* b,
-                            Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+                            Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
   const int K = m.K;
   real lp_top = 0;
   const real a0 = (*a), b0 = (*b), a1 = (*(a + 1)), bb1 = (*(b + 1));
@@ -341,7 +347,7 @@ __device__ real vg_election(const DevModel& m, const real* a, const real* b,
       site_rev(sa, abar_k, mua, aa, ba, zb, mb, lb, ab);
       g(2 + k) = zb;
       xc(2 + k) = ak;
-      if (WITH_A) abar(2 + k) = ab;
+      if (WITH_A) { abar(2 + k) = ab; bbar(2 + k) = site_bbar(sa, abar_k, lsa); }
       acc_mua += mb;
       acc_lsa += lb;
     }
@@ -361,7 +367,11 @@ __device__ real vg_election(const DevModel& m, const real* a, const real* b,
     g(2 + K) = zb; xc(2 + K) = b1;
     site_rev(sb2, acc_b2, (real)0, a4, b4, zb, mb, lb, ab);
     g(3 + K) = zb; xc(3 + K) = b2;
-    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(2 + K) = 0; abar(3 + K) = 0; }
+    if (WITH_A) {
+      abar(0) = 0; abar(1) = 0; abar(2 + K) = 0; abar(3 + K) = 0;
+      bbar(0) = site_bbar(smua, acc_mua, ARP_LOG_100); bbar(1) = site_bbar(slsa, acc_lsa, ARP_LOG_10);
+      bbar(2 + K) = site_bbar(sb1, acc_b1, ARP_LOG_100); bbar(3 + K) = site_bbar(sb2, acc_b2, ARP_LOG_100);
+    }
   }
   return lp;
 }
@@ -372,7 +382,7 @@ __device__ real vg_election(const DevModel& m, const real* a, const real* b,
 // grade_pair indices are -1 where the reference's one-hot row is all zero.
 template <int LPC, bool WITH_A>
 __device__ real vg_electric(const DevModel& m, const real* a, const real* b,
-                            Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+                            Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
   const int K = m.K;
   const int oB = 8 + K;
   real lp_top = 0;
@@ -420,7 +430,7 @@ __device__ real vg_electric(const DevModel& m, const real* a, const real* b,
       site_rev(sa, abar_p, mu_p, ap_a, (real)1, zb, mb, lb, ab);
       g(8 + p) = zb;
       xc(8 + p) = ap;
-      if (WITH_A) abar(8 + p) = ab;
+      if (WITH_A) { abar(8 + p) = ab; bbar(8 + p) = 0; }
 #pragma unroll
       for (int q = 0; q < 4; ++q) if (gp == q) acc_mua[q] += (real)100 * mb;
     }
@@ -442,7 +452,10 @@ __device__ real vg_electric(const DevModel& m, const real* a, const real* b,
       g(4 + q) = zb; xc(4 + q) = sy[q];
       site_rev(s_b[q], acc_b[q], (real)0, (*(a + oB + q)), (*(b + oB + q)), zb, mb, lb, ab);
       g(oB + q) = zb; xc(oB + q) = bx[q];
-      if (WITH_A) { abar(q) = 0; abar(4 + q) = 0; abar(oB + q) = 0; }
+      if (WITH_A) {
+        abar(q) = 0; abar(4 + q) = 0; abar(oB + q) = 0;
+        bbar(q) = 0; bbar(4 + q) = 0; bbar(oB + q) = site_bbar(s_b[q], acc_b[q], ARP_LOG_100);
+      }
     }
   }
   return lp;
@@ -456,7 +469,7 @@ __device__ real vg_electric(const DevModel& m, const real* a, const real* b,
 // writes.
 template <int LPC, bool WITH_A>
 __device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
-                               Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
+                               Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
   const int T = m.K;
   const int oBeta = 2 + 2 * T;
   const bool wr = (sub == 0);
@@ -499,11 +512,11 @@ __device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
     acc_be = fma(lik, xt, acc_be);
     real zb, mb_al, lb, ab;
     site_rev(s_al, lik + carry_al, alp + mup, aa, ba, zb, mb_al, lb, ab);
-    if (wr) { g(ia) = zb; if (WITH_A) abar(ia) = ab; }
+    if (wr) { g(ia) = zb; if (WITH_A) { abar(ia) = ab; bbar(ia) = site_bbar(s_al, lik + carry_al, lsa); } }
     acc_lsa += lb;
     real mb_mu;
     site_rev(s_mu, carry_mu, mup, am, bm, zb, mb_mu, lb, ab);
-    if (wr) { g(im) = zb; if (WITH_A) abar(im) = ab; }
+    if (wr) { g(im) = zb; if (WITH_A) { abar(im) = ab; bbar(im) = site_bbar(s_mu, carry_mu, lsm); } }
     acc_lsm += lb;
     carry_al = mb_al;
     carry_mu = mb_al + mb_mu;
@@ -519,7 +532,7 @@ __device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
     g(1) = zb; xc(1) = sm;
     site_rev(s_be, acc_be, (real)0, (*(a + oBeta)), (real)1, zb, mb, lb, ab);
     g(oBeta) = zb; xc(oBeta) = be;
-    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(oBeta) = 0; }
+    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(oBeta) = 0; bbar(0) = 0; bbar(1) = 0; bbar(oBeta) = 0; }
   }
   return lp;
 }
@@ -597,15 +610,15 @@ __device__ void to_rule(const DevModel& m, const real* a, const real* b, Vec x, 
 // --------------------------------------------------------------- dispatch ---
 template <int KIND, int LPC, bool WITH_A, int FP>
 __device__ __forceinline__ real vg(const DevModel& m, const real* a, const real* b,
-                                   Vec z, Vec g, Vec xc, Vec abar, int sub, bool want_lp) {
-  if (KIND == MODEL_8SCHOOLS) return vg_8schools<LPC, WITH_A>(m, a, b, z, g, xc, abar, sub, want_lp);
-  if (KIND == MODEL_GERMAN_LOGNORMAL) return vg_german<LPC, WITH_A, FP, false>(m, a, b, z, g, xc, abar, sub, want_lp);
-  if (KIND == MODEL_GERMAN_GAMMA) return vg_german<LPC, WITH_A, FP, true>(m, a, b, z, g, xc, abar, sub, want_lp);
-  if (KIND == MODEL_RADON) return vg_radon<LPC, WITH_A, false>(m, a, b, z, g, xc, abar, sub, want_lp);
-  if (KIND == MODEL_RADON_STDDVS) return vg_radon<LPC, WITH_A, true>(m, a, b, z, g, xc, abar, sub, want_lp);
-  if (KIND == MODEL_ELECTION) return vg_election<LPC, WITH_A>(m, a, b, z, g, xc, abar, sub, want_lp);
-  if (KIND == MODEL_ELECTRIC) return vg_electric<LPC, WITH_A>(m, a, b, z, g, xc, abar, sub, want_lp);
-  return vg_time_series<LPC, WITH_A>(m, a, b, z, g, xc, abar, sub, want_lp);
+                                   Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
+  if (KIND == MODEL_8SCHOOLS) return vg_8schools<LPC, WITH_A>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
+  if (KIND == MODEL_GERMAN_LOGNORMAL) return vg_german<LPC, WITH_A, FP, false>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
+  if (KIND == MODEL_GERMAN_GAMMA) return vg_german<LPC, WITH_A, FP, true>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
+  if (KIND == MODEL_RADON) return vg_radon<LPC, WITH_A, false>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
+  if (KIND == MODEL_RADON_STDDVS) return vg_radon<LPC, WITH_A, true>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
+  if (KIND == MODEL_ELECTION) return vg_election<LPC, WITH_A>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
+  if (KIND == MODEL_ELECTRIC) return vg_electric<LPC, WITH_A>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
+  return vg_time_series<LPC, WITH_A>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
 }
 
 }  // namespace arp

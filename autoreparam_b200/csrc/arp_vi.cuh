@@ -13,7 +13,13 @@
 // ELBO = mean_s [ log_joint(z_s) + sum_d (eps^2/2 + log scale_d + log(2 pi)/2) ],
 // z_s = loc + scale * eps_s; gradients of -ELBO:
 //   d loc = -mean_s g_s          d scale = -mean_s g_s eps_s - 1/scale
-//   d rho = d scale * sigmoid(rho)   d a_logit = -mean_s abar_s * a (1 - a)
+//   d rho = d scale * sigmoid(rho)
+// Learnable reparameterisation (cVIP, program_transformations.py:486-533): P unconstrained parameters u_p, value
+// sigmoid(u_p); coordinate d reads its `a` from slot ia[d] and its `b` from slot ib[d] (-1 = fixed).  This covers
+//   tied as written   ia[d] = d, ib = -1 (b = 1)              [the reference's default, SURVEY.md section 0 item 3]
+//   tied, b = a       ia[d] = ib[d] = d                        [the paper's intent]
+//   untied            ia = slot by loc shape, ib = slot by scale shape (a scalar loc / scale shares one slot per site)
+//   d u_p = -[ mean_s (sum_{ia[d]=p} abar_{s,d} + sum_{ib[d]=p} bbar_{s,d}) + d log prior / d p ] * p (1 - p)
 #pragma once
 #include <atomic>
 #include <string>
@@ -30,14 +36,18 @@ namespace arp {
 
 struct ViArgs {
   int D, S, steps, R;
-  int learn_a;
+  int P;                // learnable reparameterisation parameters (0 = fixed (a, b): CP / NCP / dVIP)
+  int discrete_prior;   // 1: mixture-of-Laplace prior on the learnable parameters (main.py:244-253)
   real lrs[ARP_VI_MAX_RUNS];
   unsigned long long seed;
   real* loc;            // [R, D] in/out
   real* rho;            // [R, D] in/out
-  real* a_logit;        // [R, D] in/out (learn_a)
+  real* u;              // [R, P] in/out  unconstrained parameters, value = sigmoid(u) (program_transformations.py:507-523)
+  const int* ia;        // [D] parameter slot that coordinate d's `a` reads (-1: a_in[d] is used, not learned)
+  const int* ib;        // [D] same for `b`
   const real* ext_eps;  // [steps, S, D] or null (shared by all runs)
-  real* elbo;           // [R, steps]
+  real* elbo;           // [R, steps]  ELBO (+ prior log-prob of the parameters when discrete_prior)
+  real* prior_logp;     // [R, steps] or null
   const real* a_in;     // [D]
   const real* b_in;     // [D]
 };
@@ -49,34 +59,60 @@ __device__ __forceinline__ void adam_update(real& theta, real grad, real& m1, re
   theta -= lr_t * m1 / (r_sqrt(m2) + (real)1e-8);
 }
 
-template <int KIND, bool LEARN_A, int FP>
+// log density and its derivative of the reference's prior on a learnable parameter p in (0, 1) (main.py:244-253):
+// Mixture(Categorical(logits = [0, 5, 0]), [Laplace(0, 0.1), Uniform(0, 1), Laplace(1, 0.1)]).
+__device__ __forceinline__ real discrete_prior_logp(real p, real& dlogp) {
+  const real e5 = (real)148.41315910257660342;           // exp(5)
+  const real w0 = (real)1 / ((real)2 + e5), w1 = e5 * w0;
+  const real l0 = (real)5 * r_exp((real)-10 * p), l2 = (real)5 * r_exp((real)-10 * ((real)1 - p));
+  const real mix = w0 * l0 + w1 + w0 * l2;
+  dlogp = (real)10 * w0 * (l2 - l0) / mix;
+  return r_log(mix);
+}
+
+template <int KIND, bool LEARN, int FP>
 __global__ void __launch_bounds__(ARP_VI_BLOCK)
 k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
   extern __shared__ unsigned char smem_raw[];
   real* sm = reinterpret_cast<real*>(smem_raw);
-  const int D = v.D, S = v.S, nthr = blockDim.x;  // Spad = samples rounded up to a multiple of nthr
+  const int D = v.D, S = v.S, P = v.P, nthr = blockDim.x;  // Spad = samples rounded up to a multiple of nthr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   const int run = blockIdx.x;
-  real* loc = sm;          real* rho = loc + D;    real* ul = rho + D;
-  real* scale = ul + D;    real* a_s = scale + D;  real* b_s = a_s + D;
-  real* gl = b_s + D;      real* gs = gl + D;      real* ga = gs + D;
-  real* mom = ga + D;      // [6][D] Adam first/second moments of loc, rho, a_logit
-  real* red = mom + 6 * D; // [32] block-reduction scratch
-  real* ws = ws_all + (size_t)run * 5 * D * Spad;
+  real* loc = sm;          real* rho = loc + D;    real* scale = rho + D;
+  real* a_s = scale + D;   real* b_s = a_s + D;
+  real* gl = b_s + D;      real* gs = gl + D;      real* ga = gs + D;   real* gb = ga + D;
+  real* mom = gb + D;      // [4][D] Adam first/second moments of loc, rho
+  real* up = mom + 4 * D;  // [P] unconstrained parameters; pv [P] values; gu [P] gradient sums; pm [2][P] Adam moments
+  real* pv = up + P;       real* gu = pv + P;      real* pm = gu + P;
+  real* red = pm + 2 * P;  // [32] block-reduction scratch
+  int* ia = reinterpret_cast<int*>(red + 32);
+  int* ib = ia + D;
+  real* ws = ws_all + (size_t)run * 6 * D * Spad;
   for (int d = tid; d < D; d += nthr) {
     loc[d] = v.loc[(size_t)run * D + d];
     rho[d] = v.rho[(size_t)run * D + d];
-    ul[d] = LEARN_A ? v.a_logit[(size_t)run * D + d] : (real)0;
+    a_s[d] = v.a_in[d];
     b_s[d] = v.b_in[d];
+    ia[d] = LEARN ? v.ia[d] : -1;
+    ib[d] = LEARN ? v.ib[d] : -1;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) mom[q * D + d] = 0;
+    for (int q = 0; q < 4; ++q) mom[q * D + d] = 0;
   }
+  if (LEARN)
+    for (int p = tid; p < P; p += nthr) { up[p] = v.u[(size_t)run * P + p]; pm[p] = 0; pm[P + p] = 0; }
   const real base_lr = v.lrs[run];
   __syncthreads();
   for (int step = 0; step < v.steps; ++step) {
+    if (LEARN) {
+      for (int p = tid; p < P; p += nthr) pv[p] = (real)1 / ((real)1 + r_exp(-up[p]));
+      __syncthreads();
+    }
     for (int d = tid; d < D; d += nthr) {
       scale[d] = r_softplus(rho[d]);
-      a_s[d] = LEARN_A ? (real)1 / ((real)1 + r_exp(-ul[d])) : v.a_in[d];
+      if (LEARN) {
+        if (ia[d] >= 0) a_s[d] = pv[ia[d]];
+        if (ib[d] >= 0) b_s[d] = pv[ib[d]];
+      }
     }
     __syncthreads();
     // ---- reparameterised samples: thread tid owns samples tid, tid + nthr, ...
@@ -85,6 +121,7 @@ k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
       const bool live = smp < S;
       Vec Z{ws + smp, Spad}, G{ws + (size_t)D * Spad + smp, Spad}, XC{ws + (size_t)2 * D * Spad + smp, Spad};
       Vec AB{ws + (size_t)3 * D * Spad + smp, Spad}, E{ws + (size_t)4 * D * Spad + smp, Spad};
+      Vec BB{ws + (size_t)5 * D * Spad + smp, Spad};
       real ent = 0;
       if (v.ext_eps) {
         const real* e = v.ext_eps + ((size_t)step * S + (live ? smp : 0)) * D;
@@ -110,36 +147,56 @@ k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
           }
         }
       }
-      const real lp = vg<KIND, 1, LEARN_A, FP>(m, a_s, b_s, Z, G, XC, AB, 0, true);
+      const real lp = vg<KIND, 1, LEARN, FP>(m, a_s, b_s, Z, G, XC, AB, BB, 0, true);
       if (live) el += lp + ent;
     }
     // ---- ELBO: block sum
     el = group_sum<32>(el);
     if (lane == 0) red[warp] = el;
-    __syncthreads();  // also publishes G / E / AB of every sample to the block
+    __syncthreads();  // also publishes G / E / AB / BB of every sample to the block
     if (tid == 0) {
       real tot = 0;
       for (int w = 0; w < nwarp; ++w) tot += red[w];
-      v.elbo[(size_t)run * v.steps + step] = tot / (real)S;
+      real plp = 0;
+      if (LEARN && v.discrete_prior)
+        for (int p = 0; p < P; ++p) { real dl; plp += discrete_prior_logp(pv[p], dl); }
+      v.elbo[(size_t)run * v.steps + step] = tot / (real)S + plp;   // elbo_with_prior (inference.py:54)
+      if (v.prior_logp) v.prior_logp[(size_t)run * v.steps + step] = plp;
     }
     // ---- gradient sums over the S samples: one warp per coordinate
     for (int d = warp; d < D; d += nwarp) {
       const real* gd = ws + (size_t)D * Spad + (size_t)d * Spad;
       const real* ed = ws + (size_t)4 * D * Spad + (size_t)d * Spad;
       const real* ad = ws + (size_t)3 * D * Spad + (size_t)d * Spad;
-      real s_l = 0, s_s = 0, s_a = 0;
+      const real* bd = ws + (size_t)5 * D * Spad + (size_t)d * Spad;
+      const bool la = LEARN && ia[d] >= 0, lb = LEARN && ib[d] >= 0;
+      real s_l = 0, s_s = 0, s_a = 0, s_b = 0;
       for (int s = lane; s < S; s += 32) {
         const real gg = gd[s];
         s_l += gg;
         s_s = fma(gg, ed[s], s_s);
-        if (LEARN_A) s_a += ad[s];
+        if (la) s_a += ad[s];
+        if (lb) s_b += bd[s];
       }
       s_l = group_sum<32>(s_l);
       s_s = group_sum<32>(s_s);
-      if (LEARN_A) s_a = group_sum<32>(s_a);
-      if (lane == 0) { gl[d] = s_l; gs[d] = s_s; ga[d] = s_a; }
+      if (LEARN) { s_a = group_sum<32>(s_a); s_b = group_sum<32>(s_b); }
+      if (lane == 0) { gl[d] = s_l; gs[d] = s_s; ga[d] = s_a; gb[d] = s_b; }
     }
     __syncthreads();
+    if (LEARN) {
+      // a parameter may be shared by several coordinates (untied: `a` has the shape of the site's loc, `b` of its
+      // scale) and by a and b (tied b = a): sum the coordinate adjoints per slot, in coordinate order (deterministic)
+      for (int p = tid; p < P; p += nthr) {
+        real acc = 0;
+        for (int d = 0; d < D; ++d) {
+          if (ia[d] == p) acc += ga[d];
+          if (ib[d] == p) acc += gb[d];
+        }
+        gu[p] = acc;
+      }
+      __syncthreads();
+    }
     // ---- Adam (TF1 formulation, inference.py:47) with the reference's lr schedule (:69-75)
     real lr = base_lr;
     if (3LL * step > 2LL * v.steps) lr = base_lr / (real)20;
@@ -153,33 +210,37 @@ k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
       const real sig_rho = (real)1 / ((real)1 + r_exp(-rho[d]));
       adam_update(loc[d], g_loc, mom[d], mom[D + d], lr_t);
       adam_update(rho[d], g_scale * sig_rho, mom[2 * D + d], mom[3 * D + d], lr_t);
-      if (LEARN_A) {
-        const real aa = a_s[d];
-        adam_update(ul[d], -ga[d] * inv_S * aa * ((real)1 - aa), mom[4 * D + d], mom[5 * D + d], lr_t);
-      }
     }
+    if (LEARN)
+      for (int p = tid; p < P; p += nthr) {
+        const real pp = pv[p];
+        real dl = 0;
+        if (v.discrete_prior) discrete_prior_logp(pp, dl);
+        adam_update(up[p], -(gu[p] * inv_S + dl) * pp * ((real)1 - pp), pm[p], pm[P + p], lr_t);
+      }
     __syncthreads();
   }
   for (int d = tid; d < D; d += nthr) {
     v.loc[(size_t)run * D + d] = loc[d];
     v.rho[(size_t)run * D + d] = rho[d];
-    if (LEARN_A) v.a_logit[(size_t)run * D + d] = ul[d];
   }
+  if (LEARN)
+    for (int p = tid; p < P; p += nthr) v.u[(size_t)run * P + p] = up[p];
 }
 
 static inline int vi_launch(const DevModel& dm, int fp, const ViArgs& v, cudaStream_t st, DevBuf* ws,
                             std::atomic<long long>* launches, std::string* err) {
   const int nthr = v.S >= ARP_VI_BLOCK ? ARP_VI_BLOCK : (v.S + 31) / 32 * 32;
   const int Spad = (v.S + nthr - 1) / nthr * nthr;
-  const size_t ws_bytes = (size_t)v.R * 5 * v.D * Spad * sizeof(real);
+  const size_t ws_bytes = (size_t)v.R * 6 * v.D * Spad * sizeof(real);
   cudaError_t e = ws->alloc(ws_bytes);
   if (e != cudaSuccess) { *err = std::string("vi workspace: ") + cudaGetErrorString(e); return 1; }
   cudaMemsetAsync(ws->p, 0, ws_bytes, st);
-  const size_t smem = (size_t)(15 * v.D + 32) * sizeof(real);
+  const size_t smem = (size_t)(13 * v.D + 5 * v.P + 32) * sizeof(real) + (size_t)2 * v.D * sizeof(int);
   if (smem > 200 * 1024) { *err = "vi: model too large for the shared-memory parameter block"; return 1; }
 #define ARP_VI_GO(KIND, FP)                                                                              \
   do {                                                                                                   \
-    if (v.learn_a) {                                                                                     \
+    if (v.P > 0) {                                                                                       \
       cudaFuncSetAttribute(k_vi<KIND, true, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       k_vi<KIND, true, FP><<<v.R, nthr, smem, st>>>(dm, v, ws->as<real>(), Spad);                              \
     } else {                                                                                             \

@@ -216,34 +216,56 @@ def ess(samples, precision="f32", want_moments=False):
     return (out, mean, var) if want_moments else out
 
 
-def vi_run(model, a, b, loc, rho, learning_rates, *, num_mc_samples, num_optimization_steps, a_logit=None,
-           seed=0, ext_eps=None, precision="f32"):
+def log_joint_param_grad(model, z, a, b, precision="f32"):
+    """``z`` [C, D] (numpy) -> (abar, bbar) [C, D]: d log_joint / d a and / d b per coordinate
+    (``arp_log_joint_param_grad``), the adjoints the cVIP objective differentiates."""
+    lib = _lib.load(precision)
+    dt = _lib.np_dtype(precision)
+    a_h, b_h, z = _np(a, dt), _np(b, dt), _np(z, dt)
+    ab, bb = np.empty_like(z), np.empty_like(z)
+    rc = lib.arp_log_joint_param_grad(model.handle(precision), _p(a_h), _p(b_h), _p(z), z.shape[0], _p(ab), _p(bb),
+                                      _lib.ARP_MEM_HOST, None)
+    _lib.check(lib, rc, "arp_log_joint_param_grad")
+    return ab, bb
+
+
+def vi_run(model, a, b, loc, rho, learning_rates, *, num_mc_samples, num_optimization_steps, u=None, a_index=None,
+           b_index=None, num_params=0, discrete_prior=False, seed=0, ext_eps=None, precision="f32"):
     """All learning rates at once (``arp_vi_run``), host buffers.
 
-    loc / rho / a_logit: [R, D] initial values (copied, not modified).
-    Returns dict(loc, rho, a_logit, elbo [R, steps])."""
+    loc / rho: [R, D] initial values, u: [R, P] unconstrained reparameterisation parameters (copied, not modified);
+    a_index / b_index [D]: slot of every coordinate's a / b, -1 = fixed (see include/autoreparam_b200.h).
+    Returns dict(loc, rho, u, elbo [R, steps], prior_logp [R, steps])."""
     lib = _lib.load(precision)
     dt = _lib.np_dtype(precision)
     D = model.num_coords
     R = len(learning_rates)
+    P = int(num_params)
     cfg = _lib.ViConfig()
     cfg.num_mc_samples, cfg.num_optimization_steps, cfg.num_runs = num_mc_samples, num_optimization_steps, R
     for i, lr in enumerate(learning_rates):
         cfg.learning_rates[i] = float(lr)
     cfg.seed = seed
-    cfg.learn_a = 0 if a_logit is None else 1
+    cfg.num_params = P
+    cfg.discrete_prior = 1 if discrete_prior else 0
     loc = np.array(np.broadcast_to(np.asarray(loc, dtype=dt), (R, D)))
     rho = np.array(np.broadcast_to(np.asarray(rho, dtype=dt), (R, D)))
-    al = None if a_logit is None else np.array(np.broadcast_to(np.asarray(a_logit, dtype=dt), (R, D)))
+    uu = ia = ib = None
+    if P > 0:
+        uu = np.array(np.broadcast_to(np.asarray(np.zeros(P) if u is None else u, dtype=dt), (R, P)))
+        ia = np.ascontiguousarray(np.asarray(a_index, dtype=np.int32))
+        ib = np.ascontiguousarray(np.asarray(b_index, dtype=np.int32))
+        assert ia.shape == (D,) and ib.shape == (D,)
     eps = _np(ext_eps, dt)
     if eps is not None:
         assert eps.shape == (num_optimization_steps, num_mc_samples, D)
     elbo = np.empty((R, num_optimization_steps), dtype=dt)
-    buf = _lib.ViBuffers(_p(loc), _p(rho), _p(al), _p(eps), _p(elbo))
+    plp = np.zeros((R, num_optimization_steps), dtype=dt)
+    buf = _lib.ViBuffers(_p(loc), _p(rho), _p(uu), _p(ia), _p(ib), _p(eps), _p(elbo), _p(plp))
     a_h, b_h = _np(a, dt), _np(b, dt)
     rc = lib.arp_vi_run(model.handle(precision), C.byref(cfg), _p(a_h), _p(b_h), C.byref(buf), _lib.ARP_MEM_HOST, None)
     _lib.check(lib, rc, "arp_vi_run")
-    return dict(loc=loc, rho=rho, a_logit=al, elbo=elbo)
+    return dict(loc=loc, rho=rho, u=uu, elbo=elbo, prior_logp=plp)
 
 
 def kernel_launch_count(precision="f32"):

@@ -26,12 +26,18 @@ import numpy as np
 
 
 class TargetGraph:
-    def __init__(self, model_config, method, a, b, learnable):
+    def __init__(self, model_config, method, a, b, learnable, a_index=None, b_index=None, params=()):
         self.model_config = model_config
         self.method = method
         self.a = np.asarray(a, dtype=np.float64)
         self.b = np.asarray(b, dtype=np.float64)
-        self.learnable = learnable  # True: a is optimised by VI (cVIP)
+        self.learnable = learnable  # True: the reparameterisation is optimised by VI (cVIP)
+        # learnable parameters: slot of every coordinate's a / b (-1 = fixed at self.a / self.b) and, per slot range,
+        # the key under which the reference stores it in learned_reparam: [(key, first_slot, shape), ...]
+        self.a_index = None if a_index is None else np.asarray(a_index, dtype=np.int32)
+        self.b_index = None if b_index is None else np.asarray(b_index, dtype=np.int32)
+        self.params = list(params)
+        self.num_params = sum(int(np.prod(shape)) if len(shape) else 1 for _, _, shape in self.params)
 
 
 def make_cp_graph(model_config):
@@ -45,17 +51,67 @@ def make_ncp_graph(model_config):
 
 
 def make_cvip_graph(model_config, parameterisation_type="exp", tied_pparams=False, tied_b_as_written=True):
-    """Learnable a, initialised at sigmoid(0) = 0.5 (program_transformations.py:507-510)."""
-    d = model_config.num_coords
-    a = np.full(d, 0.5)
-    if tied_pparams:
-        b = np.ones(d) if tied_b_as_written else a.copy()
-    else:
-        # untied: an independent learnable b = sigmoid(0) (:517-523); the VI kernel only learns `a`
-        raise NotImplementedError("untied VIP (independent learnable b) is not implemented; see DESIGN.md")
-    g = TargetGraph(model_config, "cVIP", a, b, True)
-    g.tie_b = tied_pparams and not tied_b_as_written
+    """Learnable reparameterisation, every parameter initialised at sigmoid(0) = 0.5
+    (program_transformations.py:486-533).
+
+    tied_pparams=True, tied_b_as_written=True   one `a` per coordinate, b = 1: what the reference's tied mode does
+                                                as written
+    tied_pparams=True, tied_b_as_written=False  one `a` per coordinate and b = a (the paper's intent)
+    tied_pparams=False                          `a` with the shape of the site's loc, an independent `b` with the
+                                                shape of its scale (:517-523: recenter passes 'scalar', so `_b` is
+                                                always created); a scalar loc / scale shares one parameter
+    Non-Normal sites (german_credit_gammascale's beta_log_scales) are never reparameterised."""
+    mc = model_config
+    d = mc.num_coords
+    a, b = np.ones(d), np.ones(d)
+    ia, ib = np.full(d, -1, dtype=np.int32), np.full(d, -1, dtype=np.int32)
+    params, slot = [], 0
+    for name, shape in mc.sites:
+        if name in mc.non_normal:
+            continue
+        o, size = mc.offsets[name]
+        if tied_pparams:
+            ia[o:o + size] = slot + np.arange(size)
+            if not tied_b_as_written:
+                ib[o:o + size] = slot + np.arange(size)
+            params.append((name + "_a", slot, shape))
+            slot += size
+        else:
+            if name in mc.scalar_loc:
+                ia[o:o + size] = slot
+                params.append((name + "_a", slot, ()))
+                slot += 1
+            else:
+                ia[o:o + size] = slot + np.arange(size)
+                params.append((name + "_a", slot, shape))
+                slot += size
+            if name in mc.scalar_scale:
+                ib[o:o + size] = slot
+                params.append((name + "_b", slot, ()))
+                slot += 1
+            else:
+                ib[o:o + size] = slot + np.arange(size)
+                params.append((name + "_b", slot, shape))
+                slot += size
+        a[o:o + size] = 0.5
+        if ib[o] >= 0:
+            b[o:o + size] = 0.5
+    g = TargetGraph(mc, "cVIP", a, b, True, ia, ib, params)
+    g.tie_b = bool(tied_pparams and not tied_b_as_written)
     return g
+
+
+def learned_reparam_from_params(target, values):
+    """Parameter values [P] of a cVIP fit -> the reference's ``learned_reparam`` dict ({site}_a [, {site}_b]).
+    With the paper's tie (b = a) `_b` is stored too, so that a later HMC / dVIP run rebuilds the same (a, b)."""
+    out = collections.OrderedDict()
+    values = np.asarray(values, dtype=np.float64)
+    for key, slot, shape in target.params:
+        size = int(np.prod(shape)) if len(shape) else 1
+        out[key] = np.asarray(values[slot:slot + size].reshape(shape), dtype=np.float32)
+        if getattr(target, "tie_b", False) and key.endswith("_a"):
+            out[key[:-2] + "_b"] = out[key].copy()
+    return out
 
 
 def reparam_to_ab(model_config, reparam):

@@ -111,13 +111,16 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
 
 
 def find_best_learning_rate(target, model_config, *, learning_rates, num_optimization_steps, num_mc_samples,
-                            seed=0, precision="f32", init_rng=None, log_fn=None):
+                            seed=0, precision="f32", init_rng=None, log_fn=None, discrete_prior=False):
     """Adam on the mean-field ELBO for every learning rate (``inference.py:26-154``).
 
     All learning rates run concurrently in one kernel launch.  Returns the
     reference's tuple ``(best_elbo, best_timeline, best_lr, step_size_init,
     learned_variational_params, learned_reparam)``; ``learned_reparam`` is None
-    unless ``target.learnable`` (cVIP)."""
+    unless ``target.learnable`` (cVIP).  ``discrete_prior`` (``main.py:244-253``): the mixture-of-Laplace
+    prior on the learnable parameters enters the objective; the returned ELBO is the 'pure' one
+    (``inference.py:150``: objective minus the prior term, both averaged over the last 32 steps)."""
+    from . import graphs
     mc = model_config
     D = mc.num_coords
     R = len(learning_rates)
@@ -125,14 +128,17 @@ def find_best_learning_rate(target, model_config, *, learning_rates, num_optimiz
     # program_transformations.py:207-215: loc = 1e-2 * randn, scale = softplus(-2); re-initialised per run
     loc0 = 1e-2 * rng.standard_normal((R, D))
     rho0 = np.full((R, D), -2.0)
-    al0 = np.zeros((R, D)) if target.learnable else None  # sigmoid(0) = 0.5, :507-510
+    P = target.num_params if target.learnable else 0
     out = engine.vi_run(mc, target.a, target.b, loc0, rho0, [float(l) for l in learning_rates],
                         num_mc_samples=num_mc_samples, num_optimization_steps=num_optimization_steps,
-                        a_logit=al0, seed=seed, precision=precision)
+                        u=np.zeros((R, P)) if P else None,        # sigmoid(0) = 0.5, :507-510
+                        a_index=target.a_index, b_index=target.b_index, num_params=P,
+                        discrete_prior=bool(discrete_prior and P), seed=seed, precision=precision)
     best = None
     for r, lr in enumerate(learning_rates):
         timeline = out["elbo"][r]
         this_elbo = float(np.mean(timeline[-32:]))                     # inference.py:121
+        this_plp = float(np.mean(out["prior_logp"][r][-32:]))          # inference.py:122
         if log_fn is not None:
             for step in range(0, num_optimization_steps, 100):         # inference.py:107-108
                 log_fn("step {} elbo {}".format(step, timeline[step]))
@@ -141,10 +147,11 @@ def find_best_learning_rate(target, model_config, *, learning_rates, num_optimiz
         if not np.isfinite(this_elbo):                                 # inference.py:127
             continue
         if best is None or best[0] < this_elbo:
-            best = (this_elbo, r, float(lr))
+            best = (this_elbo, r, float(lr), this_plp)
     if best is None:
         raise FloatingPointError("no learning rate produced a finite ELBO")
-    best_elbo, r, best_lr = best
+    best_elbo_with_prior, r, best_lr, best_plp = best
+    best_elbo = best_elbo_with_prior - best_plp                        # inference.py:150
     scale = np.logaddexp(out["rho"][r].astype(np.float64), 0.0)          # softplus
     params = collections.OrderedDict()
     for (name, shape), lo, sc in zip(mc.sites, mc.split(out["loc"][r]), mc.split(scale)):
@@ -153,9 +160,8 @@ def find_best_learning_rate(target, model_config, *, learning_rates, num_optimiz
     step_size_init = util.get_approximate_step_size(params, num_leapfrog_steps=1)  # inference.py:42-43
     learned_reparam = None
     if target.learnable:
-        a = 1.0 / (1.0 + np.exp(-out["a_logit"][r].astype(np.float64)))
-        learned_reparam = collections.OrderedDict(
-            (name + "_a", np.asarray(v, dtype=np.float32)) for (name, _), v in zip(mc.sites, mc.split(a)))
+        vals = 1.0 / (1.0 + np.exp(-out["u"][r].astype(np.float64)))
+        learned_reparam = graphs.learned_reparam_from_params(target, vals)
     return (best_elbo, list(out["elbo"][r]), best_lr, step_size_init, params, learned_reparam)
 
 

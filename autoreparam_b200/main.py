@@ -126,20 +126,19 @@ def _clean(d):
 
 def run_vi(FLAGS, model_config, results_dir, file_path):
     """main.py:234-290."""
-    target, actual_reparam = create_target_graph(FLAGS, model_config, results_dir)
     if os.path.exists(file_path):
         util.print("Already ran experiment {}-{} on model {} with dataset {}. Skipping".format(
             FLAGS.inference, FLAGS.method, FLAGS.model, FLAGS.dataset))
         return
-    if FLAGS.discrete_prior or FLAGS.reparameterise_variational:
-        raise NotImplementedError("--discrete_prior / --reparameterise_variational are outside the accelerated path")
+    target, actual_reparam = create_target_graph(FLAGS, model_config, results_dir)
     lrs = [float(x) for x in (FLAGS.learning_rates.split(",") if isinstance(FLAGS.learning_rates, str)
                               else FLAGS.learning_rates)]
     start_time = time.time()
     (elbo_final, elbo_timeline, learning_rate, initial_step_size, learned_variational_params,
      learned_reparam) = inference.find_best_learning_rate(
         target, model_config, learning_rates=lrs, num_optimization_steps=FLAGS.num_optimization_steps,
-        num_mc_samples=FLAGS.num_mc_samples, seed=FLAGS.seed, precision=FLAGS.precision, log_fn=util.print)
+        num_mc_samples=FLAGS.num_mc_samples, seed=FLAGS.seed, precision=FLAGS.precision, log_fn=util.print,
+        discrete_prior=FLAGS.discrete_prior)
     end_time = time.time()
     if learned_reparam is None and isinstance(actual_reparam, dict):
         learned_reparam = actual_reparam  # main.py:266-267: save actual parameters used for dVIP
@@ -356,9 +355,21 @@ def save_ess(file_path_base, samples, normalized_ess_final, param_names, num_cha
             out_f.write(io_buffer.getvalue())
 
 
+def check_supported(FLAGS):
+    """Flag combinations of the reference driver that are outside the accelerated hot path are rejected up front,
+    before any work (README: parity table)."""
+    if FLAGS.model in models.OUT_OF_SCOPE_MODELS:
+        raise NotImplementedError("model {} is outside the accelerated hot path (GP / MVN / funnel models: a per-step "
+                                  "Cholesky / eigh; see DESIGN.md)".format(FLAGS.model))
+    if FLAGS.reparameterise_variational:
+        raise NotImplementedError("--reparameterise_variational (make_variational_model_special, util.py:235-239) is "
+                                  "outside the accelerated hot path")
+
+
 def main(argv=None):
     """main.py:190-231."""
     FLAGS = build_parser().parse_args(argv)
+    check_supported(FLAGS)
     util.print("Loading model {} with dataset {}.".format(FLAGS.model, FLAGS.dataset))
     model_config = models.get_model_by_name(FLAGS.model, dataset=FLAGS.dataset, data_dir=FLAGS.data_dir)
     results_dir = FLAGS.results_dir if FLAGS.results_dir != "" else FLAGS.model + "_" + FLAGS.dataset

@@ -37,7 +37,11 @@ class ModelConfig:
       num_coords      D = total number of state coordinates
     """
 
-    def __init__(self, name, raw, sites, observed, c_fields):
+    def __init__(self, name, raw, sites, observed, c_fields, scalar_loc=(), scalar_scale=(), non_normal=()):
+        # learnable-parameter shapes of the site rule (program_transformations.py:563-566): `a` has the shape of the
+        # site's loc, `b` of its scale; a site listed in scalar_loc / scalar_scale passes a scalar there although the
+        # site itself is a vector.  non_normal sites are never reparameterised (:315-316,782-783).
+        self.scalar_loc, self.scalar_scale, self.non_normal = set(scalar_loc), set(scalar_scale), set(non_normal)
         self.name = name
         self.raw = raw
         self.sites = [(n, tuple(s)) for n, s in sites]
@@ -124,7 +128,11 @@ def from_data(model, raw):
         X, y = _f32(raw["X"]), _f32(raw["y"])
         n, f = X.shape
         sites = [("overall_log_scale", ()), ("beta_log_scales", (f,)), ("beta", (f,))]
-        return ModelConfig(model, raw, sites, {"y": y[None, :]}, dict(n=n, f=f, X=X, y=y))
+        gamma = model == "german_credit_gammascale"
+        # models.py:894-901: beta_log_scales ~ N(loc=overall_log_scale [scalar], scale=ones(F)); beta ~ N(zeros(F), exp(.))
+        return ModelConfig(model, raw, sites, {"y": y[None, :]}, dict(n=n, f=f, X=X, y=y),
+                           scalar_loc=() if gamma else ("beta_log_scales",),
+                           non_normal=("beta_log_scales",) if gamma else ())
     if model in ("radon", "radon_stddvs"):
         c, u, x, y = _i32(raw["county"]), _f32(raw["u"]), _f32(raw["x"]), _f32(raw["y"])
         j = len(u)
@@ -136,15 +144,18 @@ def from_data(model, raw):
         k = int(raw["n_state"])
         st, fe, bl, y = _i32(raw["state"]), _f32(raw["female"]), _f32(raw["black"]), _f32(raw["y"])
         sites = [("mua", ()), ("log_sigma_a", ()), ("a", (k,)), ("b1", ()), ("b2", ())]
+        # models.py:974: a ~ N(loc=mua [scalar], scale=ones(n_state) * exp(log_sigma_a))
         return ModelConfig(model, raw, sites, {"y": y.reshape(-1, 1)},
-                           dict(n=len(y), j=k, idx0=st, x1=fe, x2=bl, y=y))
+                           dict(n=len(y), j=k, idx0=st, x1=fe, x2=bl, y=y), scalar_loc=("a",))
     if model == "electric":
         npair, ng, ngp = int(raw["n_pair"]), int(raw["n_grade"]), int(raw["n_grade_pair"])
         pair, grade, gp = _i32(raw["pair"]), _i32(raw["grade"]), _i32(raw["grade_pair"])
         tr, y = _f32(raw["treatment"]), _f32(raw["y"])
         sites = [("mua", (ngp,)), ("sigma_y", (ng,)), ("a", (npair, 1)), ("b", (ng,))]
+        # models.py:1021-1028: mua, sigma_y, b have loc=0. (scalar) and vector scales; a has scale=1. (scalar)
         return ModelConfig(model, raw, sites, {"y": y},
-                           dict(n=len(y), j=npair, k=ng, k2=ngp, idx0=pair, idx1=grade, idx2=gp, x1=tr, y=y))
+                           dict(n=len(y), j=npair, k=ng, k2=ngp, idx0=pair, idx1=grade, idx2=gp, x1=tr, y=y),
+                           scalar_loc=("mua", "sigma_y", "b"), scalar_scale=("a",))
     if model == "time_series":
         x, y = _f32(raw["x"]), _f32(raw["y"])
         t = len(x)

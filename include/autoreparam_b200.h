@@ -102,6 +102,11 @@ int arp_log_joint_grad_engine(arp_model* m, const arp_real* a, const arp_real* b
 #define ARP_ENGINE_TCGEN05 2  /* tcgen05 tensor-core engine (german_credit, 0/1 outcomes, <= 64 features, any N) */
 #define ARP_ENGINE_TCGEN05_STREAM 3  /* alias of 2 (round 1 had a second, shared-memory-resident tcgen05 kernel) */
 
+/* d log_joint / d a and d log_joint / d b per coordinate ([C,D] each, either may be NULL): the adjoints of the site rule's
+ * parameters that the cVIP objective differentiates (program_transformations.py:507-523). */
+int arp_log_joint_param_grad(arp_model* m, const arp_real* a, const arp_real* b, const arp_real* z, int64_t C,
+                             arp_real* abar, arp_real* bbar, int mem, void* stream);
+
 /* HMC configuration: inference.hmc (inference.py:198-242) + main.py flags. */
 typedef struct arp_hmc_config {
   int32_t num_leapfrog_steps;   /* --num_leapfrog_steps */
@@ -195,7 +200,17 @@ int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* 
 
 /* VI: replaces util.get_mean_field_elbo (util.py:232-268) + the Adam loops of
  * inference.find_best_learning_rate (inference.py:26-154): all `num_runs`
- * learning rates are optimised concurrently (one CTA each) in one launch. */
+ * learning rates are optimised concurrently (one CTA each) in one launch.
+ *
+ * Learnable reparameterisation (cVIP; make_learnable_parametrisation, program_transformations.py:475-533): `num_params`
+ * unconstrained parameters u_p with value sigmoid(u_p) (tau = 1).  Coordinate d takes its `a` from slot a_index[d] and its
+ * `b` from slot b_index[d]; -1 keeps the value passed in `a` / `b`:
+ *   tied as the reference runs it   a_index[d] = d, b_index = -1 with b = 1     
+ *   tied, b = a (the paper)         a_index[d] = b_index[d] = d
+ *   untied (--tied_pparams=False)   a_index by the shape of the site's loc, b_index by the shape of its scale
+ *                                   (a site with a scalar loc / scale shares ONE parameter over its coordinates)
+ * discrete_prior = 1 adds the reference's mixture-of-Laplace log-prior of every parameter value (main.py:244-253,
+ * inference.py:50-54) to the objective; `elbo` then holds elbo + prior and `prior_logp` the prior term. */
 #define ARP_VI_MAX_RUNS 16
 typedef struct arp_vi_config {
   int32_t num_mc_samples;         /* --num_mc_samples (256) */
@@ -204,17 +219,19 @@ typedef struct arp_vi_config {
   double learning_rates[ARP_VI_MAX_RUNS]; /* --learning_rates; each is /5 after 1/3 and /20 after 2/3
                                              of the steps (inference.py:69-75) */
   uint64_t seed;
-  int32_t learn_a;                /* 1 = cVIP: a = sigmoid(a_logit) is optimised too
-                                     (program_transformations.py:507-510); b stays as passed, which is
-                                     what the reference's tied mode does as written */
+  int32_t num_params;             /* P learnable reparameterisation parameters; 0 = fixed (a, b) */
+  int32_t discrete_prior;         /* --discrete_prior */
 } arp_vi_config;
 
 typedef struct arp_vi_buffers {
   arp_real* loc;           /* [R,D] in/out  variational means (init 0.01*randn, program_transformations.py:207-210) */
   arp_real* rho;           /* [R,D] in/out  unconstrained scales, scale = softplus(rho) (init -2, :212-215) */
-  arp_real* a_logit;       /* [R,D] in/out  only if learn_a (init 0) */
+  arp_real* u;             /* [R,P] in/out  unconstrained reparameterisation parameters (init 0: sigmoid = 0.5, :507-510) */
+  const int32_t* a_index;  /* [D] HOST  parameter slot of coordinate d's a, or -1 (required if num_params > 0) */
+  const int32_t* b_index;  /* [D] HOST  same for b */
   const arp_real* ext_eps; /* [steps,S,D] optional injected standard normals (shared by the R runs) */
-  arp_real* elbo;          /* [R,steps] out  ELBO timeline (value at the pre-update parameters) */
+  arp_real* elbo;          /* [R,steps] out  objective timeline (value at the pre-update parameters) */
+  arp_real* prior_logp;    /* [R,steps] out  optional: the prior term inside `elbo` (0 without discrete_prior) */
 } arp_vi_buffers;
 
 int arp_vi_run(arp_model* m, const arp_vi_config* cfg, const arp_real* a, const arp_real* b,

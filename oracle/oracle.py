@@ -637,7 +637,19 @@ def get_min_ess(ess_parts, num_chains):
 # --------------------------------------------------------------------------- #
 # VI  (util.py:232-268, program_transformations.py:192-241, inference.py:26-154)
 # --------------------------------------------------------------------------- #
-def elbo_and_grads(model, d, loc, rho, eps, a=None, b=None, a_logit=None, dtype=torch.float64):
+def discrete_prior_logp(p):
+    """main.py:244-253: Mixture(Categorical(logits=[0, 5, 0]), [Laplace(0, 0.1), Uniform(0, 1), Laplace(1, 0.1)])
+    .log_prob(p) for p in (0, 1) -- TFP Mixture.log_prob = logsumexp(log cat_probs + component log_probs)
+    [TFP-from-memory]."""
+    logw = torch.log_softmax(torch.tensor([0.0, 5.0, 0.0], dtype=p.dtype), dim=0)
+    lap0 = -torch.abs(p) / 0.1 - math.log(0.2)
+    lap1 = -torch.abs(p - 1.0) / 0.1 - math.log(0.2)
+    uni = torch.zeros_like(p)
+    return torch.logsumexp(torch.stack([logw[0] + lap0, logw[1] + uni, logw[2] + lap1]), dim=0)
+
+
+def elbo_and_grads(model, d, loc, rho, eps, a=None, b=None, a_logit=None, dtype=torch.float64, u=None, a_index=None,
+                   b_index=None, discrete_prior=False):
     """One ELBO evaluation with S = eps.shape[0] injected standard normals.
 
     q = prod N(loc, softplus(rho)); z_s = loc + scale*eps_s;
@@ -645,19 +657,34 @@ def elbo_and_grads(model, d, loc, rho, eps, a=None, b=None, a_logit=None, dtype=
     through z AND directly (total-gradient estimator, util.py:253-266).
     If `a_logit` is given the rule is cVIP: a = sigmoid(a_logit)
     (program_transformations.py:507-510), and d/d a_logit is returned too.
-    Returns elbo, dict of gradients of **-ELBO** (what Adam minimises).
+    General learnable reparameterisation (tied b = a, untied a / b; program_transformations.py:512-523): `u` [P]
+    unconstrained parameters, coordinate d takes a = sigmoid(u[a_index[d]]) (b likewise) where the index is >= 0.
+    discrete_prior adds sum_p log prior(sigmoid(u_p)) to the objective (inference.py:50-54).
+    Returns objective, dict of gradients of **-objective** (what Adam minimises) [+ "prior_logp"].
     """
     loc = torch.tensor(np.asarray(loc), dtype=dtype, requires_grad=True)
     rho = torch.tensor(np.asarray(rho), dtype=dtype, requires_grad=True)
     eps = torch.as_tensor(np.asarray(eps), dtype=dtype)
     params = [loc, rho]
-    if a_logit is not None:
-        u = torch.tensor(np.asarray(a_logit), dtype=dtype, requires_grad=True)
-        a_t = torch.sigmoid(u)
-        params.append(u)
+    b_t = _as_flat(model, d, b, dtype, 1.0)
+    plp = torch.zeros((), dtype=dtype)
+    if u is not None:
+        ut = torch.tensor(np.asarray(u), dtype=dtype, requires_grad=True)
+        pv = torch.sigmoid(ut)
+        a_fix = _as_flat(model, d, a, dtype, 1.0)
+        ia = torch.as_tensor(np.asarray(a_index), dtype=torch.long)
+        ib = torch.as_tensor(np.asarray(b_index), dtype=torch.long)
+        a_t = torch.where(ia >= 0, pv[ia.clamp(min=0)], a_fix)
+        b_t = torch.where(ib >= 0, pv[ib.clamp(min=0)], b_t)
+        params.append(ut)
+        if discrete_prior:
+            plp = discrete_prior_logp(pv).sum()
+    elif a_logit is not None:
+        ut = torch.tensor(np.asarray(a_logit), dtype=dtype, requires_grad=True)
+        a_t = torch.sigmoid(ut)
+        params.append(ut)
     else:
         a_t = _as_flat(model, d, a, dtype, 1.0)
-    b_t = _as_flat(model, d, b, dtype, 1.0)
     scale = torch.nn.functional.softplus(rho)
     total = torch.zeros((), dtype=dtype)
     for s in range(eps.shape[0]):
@@ -666,10 +693,12 @@ def elbo_and_grads(model, d, loc, rho, eps, a=None, b=None, a_logit=None, dtype=
         _BODIES[model](tr, d)
         entropy = -normal_lp(z, loc, scale).sum()
         total = total + tr.lp + entropy
-    elbo = total / eps.shape[0]
+    elbo = total / eps.shape[0] + plp
     grads = torch.autograd.grad(-elbo, params)
-    out = {"loc": grads[0].numpy(), "rho": grads[1].numpy()}
-    if a_logit is not None:
+    out = {"loc": grads[0].numpy(), "rho": grads[1].numpy(), "prior_logp": float(plp.detach())}
+    if u is not None:
+        out["u"] = grads[2].numpy()
+    elif a_logit is not None:
         out["a_logit"] = grads[2].numpy()
     return float(elbo.detach()), out
 
@@ -696,21 +725,33 @@ def lr_schedule(step, base_lr, num_steps):
 
 
 def vi_run(model, d, loc0, rho0, eps_all, lr, num_steps, a=None, b=None, a_logit0=None,
-           dtype=torch.float64):
-    """num_steps of Adam on -ELBO with injected eps_all [num_steps, S, D]."""
+           dtype=torch.float64, u0=None, a_index=None, b_index=None, discrete_prior=False):
+    """num_steps of Adam on -objective with injected eps_all [num_steps, S, D]."""
     loc, rho = np.array(loc0, dtype=np.float64), np.array(rho0, dtype=np.float64)
-    ul = None if a_logit0 is None else np.array(a_logit0, dtype=np.float64)
-    st = {k: (np.zeros_like(loc), np.zeros_like(loc)) for k in ("loc", "rho", "a_logit")}
-    timeline = []
+    key = "u" if u0 is not None else "a_logit"
+    ul = None
+    if u0 is not None:
+        ul = np.array(u0, dtype=np.float64)
+    elif a_logit0 is not None:
+        ul = np.array(a_logit0, dtype=np.float64)
+    st = {k: (np.zeros_like(loc), np.zeros_like(loc)) for k in ("loc", "rho")}
+    if ul is not None:
+        st[key] = (np.zeros_like(ul), np.zeros_like(ul))
+    timeline, plps = [], []
     for step in range(num_steps):
-        e, g = elbo_and_grads(model, d, loc, rho, eps_all[step], a, b, ul, dtype)
+        if u0 is not None:
+            e, g = elbo_and_grads(model, d, loc, rho, eps_all[step], a, b, None, dtype, u=ul, a_index=a_index,
+                                  b_index=b_index, discrete_prior=discrete_prior)
+        else:
+            e, g = elbo_and_grads(model, d, loc, rho, eps_all[step], a, b, ul, dtype)
         timeline.append(e)
+        plps.append(g["prior_logp"])
         cur = lr_schedule(step, lr, num_steps)
         loc, m, v = adam_step(loc, g["loc"], *st["loc"], step + 1, cur); st["loc"] = (m, v)
         rho, m, v = adam_step(rho, g["rho"], *st["rho"], step + 1, cur); st["rho"] = (m, v)
         if ul is not None:
-            ul, m, v = adam_step(ul, g["a_logit"], *st["a_logit"], step + 1, cur); st["a_logit"] = (m, v)
-    return dict(loc=loc, rho=rho, a_logit=ul, elbo=np.array(timeline))
+            ul, m, v = adam_step(ul, g[key], *st[key], step + 1, cur); st[key] = (m, v)
+    return dict(loc=loc, rho=rho, a_logit=ul, u=ul, elbo=np.array(timeline), prior_logp=np.array(plps))
 
 
 # --------------------------------------------------------------------------- #

@@ -82,14 +82,75 @@ def test_vi_steps_match_oracle_fp64(model, method):
         a, b = common.ab_for(method, D)
         al0 = None
     ref = O.vi_run(model, raw, loc0, rho0, eps, lr, steps, a=a, b=b, a_logit0=al0)
+    kw = {} if al0 is None else dict(u=al0[None], a_index=np.arange(D), b_index=np.full(D, -1), num_params=D)
     out = engine.vi_run(mc, a, b, loc0[None], rho0[None], [lr], num_mc_samples=S, num_optimization_steps=steps,
-                        a_logit=None if al0 is None else al0[None], ext_eps=eps, precision="f64")
+                        ext_eps=eps, precision="f64", **kw)
     assert np.abs(out["elbo"][0] / ref["elbo"] - 1).max() < 1e-8, np.abs(out["elbo"][0] / ref["elbo"] - 1).max()
     assert np.abs(out["loc"][0] - ref["loc"]).max() < 1e-7
     assert np.abs(out["rho"][0] - ref["rho"]).max() < 1e-7
     if al0 is not None:
-        assert np.abs(out["a_logit"][0] - ref["a_logit"]).max() < 1e-7
-        assert np.abs(out["a_logit"][0]).max() > 1e-3   # the parameterisation really moved
+        assert np.abs(out["u"][0] - ref["a_logit"]).max() < 1e-7
+        assert np.abs(out["u"][0]).max() > 1e-3   # the parameterisation really moved
+
+
+@pytest.mark.parametrize("model", ["8schools", "german_credit_lognormalcentered", "german_credit_gammascale", "election",
+                                   "electric", "time_series", "radon_stddvs"])
+@pytest.mark.parametrize("mode", ["tied_b_eq_a", "untied", "untied_prior"])
+def test_vi_learnable_b_matches_oracle_fp64(model, mode):
+    """The paper's tied b = a, the untied mode (independent a / b with the shapes of the site's loc / scale:
+    program_transformations.py:512-523) and --discrete_prior (main.py:244-253): a few Adam steps with injected
+    normals equal the autograd oracle -- this pins the d/db adjoint of every model, the parameter sharing of scalar
+    loc / scale sites and the prior's gradient."""
+    from autoreparam_b200 import graphs
+    mc = common.model_config(model, "MN")
+    raw = common.raw_data(model, "MN")
+    D = mc.num_coords
+    S, steps, lr = 3, 5, 0.05
+    rng = np.random.default_rng(22)
+    eps = rng.standard_normal((steps, S, D))
+    loc0 = 0.01 * rng.standard_normal(D)
+    rho0 = np.full(D, -2.0)
+    tgt = graphs.make_cvip_graph(mc, tied_pparams=(mode == "tied_b_eq_a"), tied_b_as_written=False)
+    P = tgt.num_params
+    assert P > 0 and tgt.a_index.max() < P and tgt.b_index.max() < P
+    u0 = 0.3 * rng.standard_normal(P)       # away from the symmetric start so that every adjoint is exercised
+    prior = mode == "untied_prior"
+    ref = O.vi_run(model, raw, loc0, rho0, eps, lr, steps, a=tgt.a, b=tgt.b, u0=u0, a_index=tgt.a_index,
+                   b_index=tgt.b_index, discrete_prior=prior)
+    out = engine.vi_run(mc, tgt.a, tgt.b, loc0[None], rho0[None], [lr], num_mc_samples=S, num_optimization_steps=steps,
+                        u=u0[None], a_index=tgt.a_index, b_index=tgt.b_index, num_params=P, discrete_prior=prior,
+                        ext_eps=eps, precision="f64")
+    assert np.abs(out["elbo"][0] / ref["elbo"] - 1).max() < 1e-8, np.abs(out["elbo"][0] / ref["elbo"] - 1).max()
+    assert np.abs(out["prior_logp"][0] - ref["prior_logp"]).max() < 1e-9
+    assert np.abs(out["loc"][0] - ref["loc"]).max() < 1e-7
+    assert np.abs(out["rho"][0] - ref["rho"]).max() < 1e-7
+    assert np.abs(out["u"][0] - ref["u"]).max() < 1e-7
+    assert np.abs(out["u"][0] - u0).max() > 1e-3
+    if prior:
+        assert np.abs(ref["prior_logp"]).max() > 0
+
+
+@pytest.mark.parametrize("model", common.MODELS)
+def test_param_adjoints_match_autograd(model):
+    """d log_joint / d a and / d b per coordinate (arp_log_joint_param_grad) against autograd, general (a, b)."""
+    import torch
+    mc = common.model_config(model)
+    raw = common.raw_data(model)
+    D = mc.num_coords
+    a, b = common.ab_for("VIP_ab", D)
+    z = common.random_states(model, D, 3, seed=4).astype(np.float32).astype(np.float64)
+    ab, bb = engine.log_joint_param_grad(mc, z, a, b, precision="f64")
+    for c in range(3):
+        at = torch.tensor(a, dtype=torch.float64, requires_grad=True)
+        bt = torch.tensor(b, dtype=torch.float64, requires_grad=True)
+        tr = O.Tracer(O._split(model, raw, torch.as_tensor(z[c]), torch.float64), O._split(model, raw, at, torch.float64),
+                      O._split(model, raw, bt, torch.float64), torch.float64)
+        O._BODIES[model](tr, raw)
+        ga, gb = torch.autograd.grad(tr.lp, [at, bt], allow_unused=True)
+        ga = np.zeros(D) if ga is None else ga.numpy()
+        gb = np.zeros(D) if gb is None else gb.numpy()
+        assert common.rel_err(ab[c:c + 1], ga[None]).max() < 1e-10, ("abar", c)
+        assert common.rel_err(bb[c:c + 1], gb[None]).max() < 1e-10, ("bbar", c, np.abs(bb[c] - gb).argmax())
 
 
 def test_vi_learning_rates_run_concurrently_and_converge():
