@@ -161,7 +161,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // set, but the parity tests go there) a relative error of 6e-7 in sigma moves eta by several 1e-3 and the tensor-core
 // gradient drifted to 1e-5 of the fp64 oracle where the SIMT engine (expf) holds 1e-7 .. 1e-6.
 #ifndef TC_EXP_MODE
-#define TC_EXP_MODE 2
+#define TC_EXP_MODE 1
 #endif
 __device__ __forceinline__ float exp_fast(float x) {
 #if TC_EXP_MODE == 0

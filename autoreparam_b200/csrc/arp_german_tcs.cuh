@@ -237,6 +237,9 @@ __launch_bounds__(TCS_THREADS, 1)
 #endif
 k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
   using K = Tcs<NF>;
+  // multi-run launch (leapfrog-step tuning grid): this CTA's run overrides L, the transition counts, the step sizes
+  // and the output buffers; chain0 = index of the CTA's first chain inside its run
+  const int chain0 = hmc_apply_slice(p, (int)blockIdx.x * TC_CHAINS);
   constexpr int FPW = K::FPW, NLOC = K::NLOC;
   constexpr bool V_IN_REGS = (NF <= 32);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -359,7 +362,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
   } else {
     // ====================== chain workers (4 per chain) ======================
     const int w = tid >> 7, r = tid & 127;
-    const int chain = blockIdx.x * TC_CHAINS + r;
+    const int row = blockIdx.x * TC_CHAINS + r;    // workspace row
+    const int chain = chain0 + r;                  // chain index inside the run: RNG streams, outputs
     const bool valid = chain < p.C;
     const int D = p.D, F = tp.F;
     const bool bias = tp.bias != 0;
@@ -368,14 +372,14 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const int nf = F / TC_NQ + (w < F % TC_NQ ? 1 : 0);
     const int fstart = w * (F / TC_NQ) + min(w, F % TC_NQ);
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const size_t co = (size_t)chain * ws.sc;
+    const size_t co = (size_t)row * ws.sc;
     Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd}, VG{ws.v + co, ws.sd};
     float* xs = reinterpret_cast<float*>(smem + K::XS) + tid;
     const float* pa_s = reinterpret_cast<const float*>(smem + K::PAR);
     const float* pb_s = pa_s + (2 * NF + 4);
     const float* pe_s = pb_s + (2 * NF + 4);
-    float lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
-    int nacc = ws.nacc[chain];
+    float lp_cur = ws.lp[row], Hc = ws.H[row], lavg = ws.lavg[row], mult = ws.mult[row];
+    int nacc = ws.nacc[row];
     const unsigned int gchain = p.chain_offset + (unsigned int)chain;
     uint32_t ph[2] = {0, 0}, pg = 0;
     const float a0 = pa_s[0], b0 = pb_s[0];
@@ -691,7 +695,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     }
     if (w == 0) {
       G(0) = g0_cur;   // coordinate 0 lives in registers during the run
-      ws.lp[chain] = lp_cur; ws.H[chain] = Hc; ws.lavg[chain] = lavg; ws.mult[chain] = mult; ws.nacc[chain] = nacc;
+      ws.lp[row] = lp_cur; ws.H[row] = Hc; ws.lavg[row] = lavg; ws.mult[row] = mult; ws.nacc[row] = nacc;
     }
   }
   tc_fence_before();
@@ -780,10 +784,11 @@ static inline cudaError_t tcs_launch(int nf_pad, dim3 grid, cudaStream_t st, con
 
 static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt, const HmcArgs& p, const real* z0,
                                  cudaStream_t st, bool want_final, DevBuf* wsbuf, DevBuf* dfz, DevBuf* scal, DevBuf* nacc,
-                                 std::atomic<long long>* launches, std::string* err) {
+                                 std::atomic<long long>* launches, std::string* err, int n_runs = 1) {
 #define TCS_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { *err = std::string(#expr) + ": " + cudaGetErrorString(_e); return 1; } } while (0)
   const long long C = p.C;
-  const long long Cpad = (C + TC_CHAINS - 1) / TC_CHAINS * TC_CHAINS;
+  // n_runs > 1: p.slices describes the runs, each owning p.slice_rows = round_up(C, 128) workspace rows
+  const long long Cpad = n_runs * ((C + TC_CHAINS - 1) / TC_CHAINS * TC_CHAINS);
   const long long Dpad = (p.D + 7) / 8 * 8;
   const size_t vec = (size_t)Cpad * Dpad;
   TCS_CUDA(wsbuf->alloc(7 * vec * sizeof(real)));

@@ -40,7 +40,30 @@ struct HmcArgs {
   real* samples;             // [S, C, D] or null
   real* samples_orig;        // [S, C, D] or null
   unsigned char* is_accepted;  // [S, C] or null
+  // several independent runs in ONE launch (the num_leapfrog_steps tuning grid, reference main.py:316-329 run once per
+  // L): run i owns workspace rows [i * slice_rows, (i + 1) * slice_rows) -- whole blocks -- and takes its own
+  // (L, transitions, adaptation / burn-in lengths, kept samples, step sizes, output buffers) from slices[i]
+  const struct HmcSlice* slices;   // null: one run, the fields above
+  int slice_rows;
 };
+
+struct HmcSlice {
+  int L, T, num_adapt, num_burnin, S;
+  const real* eps0;            // [D]
+  real* samples;               // [S, C, D] or null
+  unsigned char* is_accepted;  // [S, C] or null
+};
+
+// Per-block view of the launch arguments: in a multi-run launch the block's run overrides the per-run fields.  Returns
+// the chain index inside the run (which keys z0, the RNG streams and the outputs); `row` indexes the workspace.
+__device__ __forceinline__ int hmc_apply_slice(HmcArgs& p, int row) {
+  if (!p.slices) return row;
+  const int sl = row / p.slice_rows;
+  const HmcSlice s = p.slices[sl];
+  p.L = s.L; p.T = s.T; p.num_adapt = s.num_adapt; p.num_burnin = s.num_burnin; p.S = s.S;
+  p.eps0 = s.eps0; p.samples = s.samples; p.samples_orig = nullptr; p.is_accepted = s.is_accepted;
+  return row - sl * p.slice_rows;
+}
 
 template <int KIND, int LPC, bool WITH_A, int FP>
 __global__ void __launch_bounds__(ARP_BLOCK)
@@ -64,20 +87,21 @@ template <int KIND, int LPC, int FP>
 __global__ void __launch_bounds__(ARP_BLOCK)
 k_hmc_init(DevModel m, HmcWs ws, HmcArgs p, const real* z0) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int chain = gtid / LPC;
+  const int row = gtid / LPC;
   const int sub = gtid % LPC;
+  const int chain = hmc_apply_slice(p, row);     // every run of a multi-run launch starts from the same z0
   const bool valid = chain < p.C;
-  const size_t co = (size_t)chain * ws.sc;
+  const size_t co = (size_t)row * ws.sc;
   Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
   for (int d = sub; d < p.D; d += LPC) Z(d) = valid ? z0[(size_t)chain * p.D + d] : (real)0;
   __syncwarp();
   real lp = vg<KIND, LPC, false, FP>(m, p.a, p.b, Z, G, XC, Vec{nullptr, 1}, Vec{nullptr, 1}, sub, true);
   if (sub == 0) {
-    ws.lp[chain] = lp;
-    ws.H[chain] = 0;
-    ws.lavg[chain] = 0;
-    ws.mult[chain] = 1;
-    ws.nacc[chain] = 0;
+    ws.lp[row] = lp;
+    ws.H[row] = 0;
+    ws.lavg[row] = 0;
+    ws.mult[row] = 1;
+    ws.nacc[row] = 0;
   }
 }
 
@@ -85,17 +109,18 @@ template <int KIND, int LPC, int FP>
 __global__ void __launch_bounds__(ARP_BLOCK)
 k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int chain = gtid / LPC;
+  const int row = gtid / LPC;
   const int sub = gtid % LPC;
+  const int chain = hmc_apply_slice(p, row);
   const bool valid = chain < p.C;
   const int D = p.D;
-  const size_t co = (size_t)chain * ws.sc;
+  const size_t co = (size_t)row * ws.sc;
   Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
   Vec X{ws.x + co, ws.sd}, GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
   Vec V{ws.v + co, ws.sd};
   const real* __restrict__ eps0 = p.eps0;
-  real lp_cur = ws.lp[chain], Hc = ws.H[chain], lavg = ws.lavg[chain], mult = ws.mult[chain];
-  int nacc = ws.nacc[chain];
+  real lp_cur = ws.lp[row], Hc = ws.H[row], lavg = ws.lavg[row], mult = ws.mult[row];
+  int nacc = ws.nacc[row];
   const unsigned int gchain = p.chain_offset + (unsigned int)chain;
 
   for (int t = 0; t < p.T; ++t) {
@@ -191,11 +216,11 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
     __syncwarp();
   }
   if (sub == 0) {
-    ws.lp[chain] = lp_cur;
-    ws.H[chain] = Hc;
-    ws.lavg[chain] = lavg;
-    ws.mult[chain] = mult;
-    ws.nacc[chain] = nacc;
+    ws.lp[row] = lp_cur;
+    ws.H[row] = Hc;
+    ws.lavg[row] = lavg;
+    ws.mult[row] = mult;
+    ws.nacc[row] = nacc;
   }
 }
 

@@ -517,6 +517,130 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
   return 0;
 }
 
+// ------------------------------------------------------------- several runs, one launch ---
+extern "C" int arp_hmc_run_many(arp_model* m, const arp_hmc_config* cfgs, int32_t num_runs, const arp_real* a,
+                                const arp_real* b, int64_t C, const arp_hmc_buffers* bufs, int mem, void* stream) {
+  if (!m || !cfgs || !a || !b || !bufs || C <= 0 || num_runs < 1 || num_runs > 64) return fail("arp_hmc_run_many: bad argument");
+  if (!bufs[0].z0) return fail("arp_hmc_run_many: bufs[0].z0 is required (every run starts from it)");
+  for (int i = 0; i < num_runs; ++i) {
+    const arp_hmc_config& c = cfgs[i];
+    if (c.num_leapfrog_steps < 1 || c.num_results < 1 || c.num_burnin_steps < 0 || c.num_steps_between_results < 0)
+      return fail("arp_hmc_run_many: bad configuration");
+    if (c.num_steps_between_results != cfgs[0].num_steps_between_results || c.seed != cfgs[0].seed ||
+        c.chain_offset != cfgs[0].chain_offset || c.engine != cfgs[0].engine || c.lanes_per_chain != cfgs[0].lanes_per_chain)
+      return fail("arp_hmc_run_many: the runs may differ in num_leapfrog_steps, num_results, num_burnin_steps and "
+                  "num_adaptation_steps only");
+    if (!bufs[i].eps0) return fail("arp_hmc_run_many: eps0 is required for every run");
+    if (bufs[i].ext_momenta || bufs[i].ext_log_u || bufs[i].samples_orig || bufs[i].final_z)
+      return fail("arp_hmc_run_many: injected streams, raw samples and final states are single-run features");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = m->dev.D;
+  const bool host = mem == ARP_MEM_HOST;
+  const arp_hmc_config& c0 = cfgs[0];
+#ifndef ARP_FP64
+  const bool tc_ok = (m->dev.kind == MODEL_GERMAN_LOGNORMAL || m->dev.kind == MODEL_GERMAN_GAMMA) && m->tcs.ready();
+  if (c0.engine < 0 || c0.engine > 3) return fail("arp_hmc_run_many: unknown engine");
+  if (c0.engine >= 2 && !tc_ok) return fail("arp_hmc_run_many: the tcgen05 engine needs a german_credit model");
+  // engine and lane layout are chosen as a SEPARATE run of C chains would choose them: identical arithmetic
+  const bool use_tc = tc_ok && (c0.engine >= 2 || (c0.engine == 0 && german_tc_auto(C)));
+#else
+  if (c0.engine >= 2) return fail("arp_hmc_run_many: the fp64 check build has no tcgen05 engine");
+  const bool use_tc = false;
+#endif
+  const int lpc = use_tc ? 1 : pick_lpc(m, C, c0.lanes_per_chain);
+  const int cpb = use_tc ? 128 : ARP_BLOCK / lpc;
+  const long long slice_rows = round_up(C, cpb);
+
+  DevBuf da, db, dz0, deps, dslices;
+  std::vector<DevBuf> dsamp(num_runs), dacc(num_runs);
+  if (stage_in(da, a, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  if (stage_in(db, b, D * sizeof(real), ARP_MEM_HOST, st)) return 1;
+  const real* z0 = bufs[0].z0;
+  if (host) {
+    if (stage_in(dz0, z0, (size_t)C * D * sizeof(real), mem, st)) return 1;
+    z0 = dz0.as<real>();
+  }
+  // per-run step sizes: one [num_runs, D] device table
+  ARP_CUDA(deps.alloc((size_t)num_runs * D * sizeof(real)));
+  std::vector<HmcSlice> slices(num_runs);
+  for (int i = 0; i < num_runs; ++i) {
+    ARP_CUDA(cudaMemcpyAsync(deps.as<real>() + (size_t)i * D, bufs[i].eps0, D * sizeof(real),
+                             host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+    const long long S = cfgs[i].num_results;
+    HmcSlice& s = slices[i];
+    s.L = cfgs[i].num_leapfrog_steps; s.T = (int)arp_hmc_num_transitions(&cfgs[i]);
+    s.num_adapt = cfgs[i].num_adaptation_steps; s.num_burnin = cfgs[i].num_burnin_steps; s.S = (int)S;
+    s.eps0 = deps.as<real>() + (size_t)i * D;
+    s.samples = bufs[i].samples; s.is_accepted = bufs[i].is_accepted;
+    if (host) {
+      if (bufs[i].samples) { ARP_CUDA(dsamp[i].alloc((size_t)S * C * D * sizeof(real))); s.samples = dsamp[i].as<real>(); }
+      if (bufs[i].is_accepted) { ARP_CUDA(dacc[i].alloc((size_t)S * C)); s.is_accepted = dacc[i].as<unsigned char>(); }
+    }
+  }
+  if (stage_in(dslices, slices.data(), slices.size() * sizeof(HmcSlice), ARP_MEM_HOST, st)) return 1;
+  ARP_CUDA(cudaStreamSynchronize(st));   // `slices` (host vector) has been consumed
+
+  HmcArgs p{};
+  p.C = (int)C; p.D = D; p.L = slices[0].L; p.T = slices[0].T; p.t_begin = 0;
+  p.num_adapt = slices[0].num_adapt; p.num_burnin = slices[0].num_burnin;
+  p.stride = 1 + c0.num_steps_between_results; p.S = slices[0].S;
+  p.seed = c0.seed; p.chain_offset = (unsigned int)c0.chain_offset;
+  p.target_accept = (real)(c0.target_accept_prob > 0 ? c0.target_accept_prob : 0.75);
+  p.eps0 = slices[0].eps0; p.a = da.as<real>(); p.b = db.as<real>();
+  p.slices = dslices.as<HmcSlice>(); p.slice_rows = (int)slice_rows;
+
+  DevBuf wsbuf, scal, nacc, dfz;
+  real* mult_dev = nullptr;
+  int* nacc_dev = nullptr;
+#ifndef ARP_FP64
+  if (use_tc) {
+    if (german_tcs_hmc(m->tcs, m->dev, m->fp, p, z0, st, false, &wsbuf, &dfz, &scal, &nacc, &g_launches, &g_last_error, num_runs))
+      return 1;
+    mult_dev = scal.as<real>(); nacc_dev = nacc.as<int>();
+  } else
+#endif
+  {
+    const long long Cpad = slice_rows * num_runs, Dpad = round_up(D, 8);
+    const size_t vec = (size_t)Cpad * Dpad;
+    ARP_CUDA(wsbuf.alloc(7 * vec * sizeof(real)));
+    ARP_CUDA(cudaMemsetAsync(wsbuf.p, 0, 7 * vec * sizeof(real), st));
+    ARP_CUDA(scal.alloc(4 * Cpad * sizeof(real)));
+    ARP_CUDA(nacc.alloc(Cpad * sizeof(int)));
+    HmcWs ws{};
+    real* base = wsbuf.as<real>();
+    ws.z = base; ws.g = base + vec; ws.xc = base + 2 * vec; ws.x = base + 3 * vec;
+    ws.gx = base + 4 * vec; ws.xcx = base + 5 * vec; ws.v = base + 6 * vec;
+    real* sb = scal.as<real>();
+    ws.mult = sb; ws.lp = sb + Cpad; ws.H = sb + 2 * Cpad; ws.lavg = sb + 3 * Cpad;
+    ws.nacc = nacc.as<int>();
+    if (lpc == 1) { ws.sd = (int)Cpad; ws.sc = 1; } else { ws.sd = 1; ws.sc = (int)Dpad; }
+    const dim3 grid((unsigned)(Cpad / cpb)), block(ARP_BLOCK);
+    const DevModel dm = m->dev;
+    const int fp = m->fp;
+#define BODY(KIND, LPC, FP)                                          \
+    k_hmc_init<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p, z0); \
+    k_hmc_run<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p);
+    ARP_DISPATCH(dm.kind, lpc, fp, BODY)
+#undef BODY
+    g_launches.fetch_add(1);
+    ARP_LAUNCH_CHECK();
+    mult_dev = ws.mult; nacc_dev = ws.nacc;
+  }
+  const cudaMemcpyKind kd = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  for (int i = 0; i < num_runs; ++i) {
+    const long long S = cfgs[i].num_results;
+    if (host) {
+      if (bufs[i].samples) ARP_CUDA(cudaMemcpyAsync(bufs[i].samples, slices[i].samples, (size_t)S * C * D * sizeof(real), kd, st));
+      if (bufs[i].is_accepted) ARP_CUDA(cudaMemcpyAsync(bufs[i].is_accepted, slices[i].is_accepted, (size_t)S * C, kd, st));
+    }
+    if (bufs[i].step_mult) ARP_CUDA(cudaMemcpyAsync(bufs[i].step_mult, mult_dev + i * slice_rows, C * sizeof(real), kd, st));
+    if (bufs[i].accept_count) ARP_CUDA(cudaMemcpyAsync(bufs[i].accept_count, nacc_dev + i * slice_rows, C * sizeof(int), kd, st));
+  }
+  ARP_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // ---------------------------------------------------------------- interleaved ---
 extern "C" int arp_hmc_interleaved_run(arp_model* m, const arp_ilv_config* cfg, const arp_real* a_a, const arp_real* b_a,
                                        const arp_real* a_b, const arp_real* b_b, int64_t C, const arp_ilv_buffers* buf,

@@ -144,6 +144,63 @@ def hmc_run(model, z0, eps0, a, b, *, num_leapfrog_steps, num_results, num_burni
     return out
 
 
+def hmc_run_many(model, z0, eps0_list, a, b, *, num_leapfrog_steps, num_results, num_burnin_steps,
+                 num_adaptation_steps, num_steps_between_results=1, seed=0, chain_offset=0, target_accept_prob=0.75,
+                 engine=ENGINE_AUTO, lanes_per_chain=0, precision="f32", want_samples=True):
+    """Several HMC runs in ONE launch (``arp_hmc_run_many``): the leapfrog-step tuning grid.
+
+    ``num_leapfrog_steps`` / ``num_results`` / ``num_burnin_steps`` / ``num_adaptation_steps`` are lists (one entry
+    per run; a scalar is broadcast), ``eps0_list`` one [D] array per run; every run starts from ``z0`` [C, D]
+    (numpy: host buffers; torch.cuda: device buffers).  Returns a list of dicts like ``hmc_run``."""
+    lib = _lib.load(precision)
+    dt = _lib.np_dtype(precision)
+    D = model.num_coords
+    n = len(eps0_list)
+    bc = lambda v: list(v) if isinstance(v, (list, tuple, np.ndarray)) else [v] * n
+    Ls, Ss, Bs, As = bc(num_leapfrog_steps), bc(num_results), bc(num_burnin_steps), bc(num_adaptation_steps)
+    assert len(Ls) == len(Ss) == len(Bs) == len(As) == n
+    cfgs = (_lib.HmcConfig * n)()
+    for i in range(n):
+        cfgs[i] = _lib.HmcConfig(int(Ls[i]), int(Ss[i]), int(Bs[i]), int(As[i]), num_steps_between_results, seed,
+                                 chain_offset, target_accept_prob, lanes_per_chain, engine)
+    a_h, b_h = _np(a, dt), _np(b, dt)
+    if _is_torch(z0):
+        import torch
+        tdt = _torch_dtype(precision)
+        z0 = z0.contiguous()
+        dev = z0.device
+        conv = lambda v: torch.as_tensor(v, dtype=tdt, device=dev).contiguous()
+        mk = lambda shape, dtype: torch.empty(shape, dtype=dtype, device=dev)
+        u8, i32 = torch.uint8, torch.int32
+        mem, st = _lib.ARP_MEM_DEVICE, _stream()
+    else:
+        tdt = dt
+        z0 = _np(z0, dt)
+        conv = lambda v: _np(v, dt)
+        mk = lambda shape, dtype: np.empty(shape, dtype=dtype)
+        u8, i32 = np.uint8, np.int32
+        mem, st = _lib.ARP_MEM_HOST, None
+    Cn = z0.shape[0]
+    assert tuple(z0.shape) == (Cn, D)
+    bufs = (_lib.HmcBuffers * n)()
+    outs, keep = [], []
+    for i in range(n):
+        eps = conv(eps0_list[i])
+        assert tuple(eps.shape) == (D,)
+        keep.append(eps)
+        o = dict(step_mult=mk((Cn,), tdt), accept_count=mk((Cn,), i32))
+        if want_samples:
+            o["samples"] = mk((int(Ss[i]), Cn, D), tdt)
+            o["is_accepted"] = mk((int(Ss[i]), Cn), u8)
+        bufs[i] = _lib.HmcBuffers(_p(z0), _p(eps), None, None, _p(o.get("samples")), None, _p(o.get("is_accepted")),
+                                  None, _p(o["step_mult"]), _p(o["accept_count"]))
+        o["num_transitions"] = hmc_num_transitions(int(Ss[i]), int(Bs[i]), num_steps_between_results)
+        outs.append(o)
+    rc = lib.arp_hmc_run_many(model.handle(precision), cfgs, n, _p(a_h), _p(b_h), Cn, bufs, mem, st)
+    _lib.check(lib, rc, "arp_hmc_run_many")
+    return outs
+
+
 def hmc_interleaved_run(model, x0, eps0_a, eps0_b, rule_a, rule_b, *, num_leapfrog_steps_a, num_leapfrog_steps_b,
                         num_results, num_burnin_steps, num_adaptation_steps, num_steps_between_results=1, seed=0,
                         chain_offset=0, target_accept_prob=0.75, adaptation_rate=0.05, ext_momenta=None,

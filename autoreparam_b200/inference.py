@@ -49,13 +49,15 @@ def _flat_step_sizes(model_config, step_size_init):
 
 def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, num_leapfrog_steps, num_samples,
         num_burnin_steps, num_adaptation_steps, num_chains_to_save=0, seed=0, chain_offset=0, device="cuda",
-        engine_kind=engine.ENGINE_AUTO, precision="f32", keep_on_device=False):
+        engine_kind=engine.ENGINE_AUTO, precision="f32", keep_on_device=False, return_is_accepted=True):
     """HMC + dual-averaging adaptation + thinning + to-centred + ESS (``inference.py:198-242``).
 
     target            TargetGraph (graphs.py) -- carries the (a, b) rule, so ``reparam`` is accepted
                       for signature parity only.
     step_size_init    list per site (VI's sigma_q); eps0 = sigma_q / (L / 4)**2  (inference.py:212-216)
     initial_states    list of [C, *site] arrays (util.variational_inits_from_params) or flat [C, D]
+    return_is_accepted  False: the [S, C] accept flags stay on the device (``is_accepted`` is None); their sum is in
+                      ``accept_stats`` -- all the drop-in driver reads (main.py:372-373)
     """
     import torch
 
@@ -88,15 +90,15 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
     distributed.allreduce_sum_(acc)
     rhat_dev = distributed.rhat_from_stats(stats, num_samples) if (C > 1 or distributed.is_multi()) else None
     # device -> host through pinned buffers, one synchronisation: only what the caller consumes
-    dev_out = [ess_dev, out["is_accepted"], out["step_mult"], out["accept_count"], acc] + \
-        ([rhat_dev] if rhat_dev is not None else [])
-    host = [_pinned_like(t, tag) for tag, t in enumerate(dev_out)]
+    dev_out = [ess_dev, out["step_mult"], out["accept_count"], acc] + \
+        ([rhat_dev] if rhat_dev is not None else [None]) + ([out["is_accepted"]] if return_is_accepted else [None])
+    host = [None if t is None else _pinned_like(t, tag) for tag, t in enumerate(dev_out)]
     for h, t in zip(host, dev_out):
-        h.copy_(t, non_blocking=True)
+        if t is not None:
+            h.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    ess_flat, is_acc_u8, step_mult, accept_count, acc_host = [h.numpy().copy() for h in host[:5]]
-    rhat = host[5].numpy().copy() if rhat_dev is not None else None
-    is_acc = is_acc_u8.view(np.bool_)
+    ess_flat, step_mult, accept_count, acc_host, rhat, is_acc_u8 = [None if h is None else h.numpy().copy() for h in host]
+    is_acc = None if is_acc_u8 is None else is_acc_u8.view(np.bool_)
     samples = None
     if num_chains_to_save > 0:
         samples = mc.split(out["samples"][:, :num_chains_to_save].cpu().numpy())
@@ -108,6 +110,48 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
     if keep_on_device:
         return res, out
     return res
+
+
+def hmc_tuning_grid(target, model_config, step_size_init, initial_states, *, num_leapfrog_steps, num_samples,
+                    num_burnin_steps, num_adaptation_steps, seed=0, chain_offset=0, device="cuda",
+                    engine_kind=engine.ENGINE_AUTO, precision="f32"):
+    """The whole ``num_leapfrog_steps`` tuning grid in ONE launch (``arp_hmc_run_many``): what the reference does
+    with one ``--inference=HMCtuning --num_leapfrog_steps=L`` process per L (``main.py:316-329, 375-384``).
+    All arguments that the reference rescales per L (``--count_in_leapfrog_steps``, ``main.py:318-324``) are lists,
+    one entry per L.  Each run equals ``hmc(...)`` with that L (same initial states, same random streams).
+    Returns a list of ``HmcResult`` (``samples`` / ``is_accepted`` None: the tuning driver only reads ESS)."""
+    import torch
+
+    mc = model_config
+    Ls = [int(l) for l in num_leapfrog_steps]
+    n = len(Ls)
+    bc = lambda v: [int(x) for x in v] if isinstance(v, (list, tuple, np.ndarray)) else [int(v)] * n
+    Ss, Bs, As = bc(num_samples), bc(num_burnin_steps), bc(num_adaptation_steps)
+    z0 = initial_states if (isinstance(initial_states, np.ndarray) and initial_states.ndim == 2) \
+        else mc.join(list(initial_states))
+    C, D = z0.shape
+    sig = _flat_step_sizes(mc, step_size_init)
+    eps = [sig / (float(l) / 4.0) ** 2 for l in Ls]                      # inference.py:212-216
+    dev = torch.device(device)
+    tdt = torch.float32 if precision == "f32" else torch.float64
+    z_dev = torch.as_tensor(np.ascontiguousarray(z0), dtype=tdt).to(dev)
+    outs = engine.hmc_run_many(mc, z_dev, eps, target.a, target.b, num_leapfrog_steps=Ls, num_results=Ss,
+                               num_burnin_steps=Bs, num_adaptation_steps=As, seed=seed, chain_offset=chain_offset,
+                               engine=engine_kind, precision=precision)
+    results = []
+    for o, S in zip(outs, Ss):
+        ess_dev, mean_dev, var_dev = engine.ess(o["samples"], precision=precision, want_moments=True)
+        stats = distributed.allreduce_sum_(distributed.rhat_stats(mean_dev, var_dev))
+        acc = torch.stack([o["is_accepted"].sum(dtype=torch.float64), o["accept_count"].sum(dtype=torch.float64),
+                           torch.tensor(float(C), dtype=torch.float64, device=dev)])
+        distributed.allreduce_sum_(acc)
+        rhat = distributed.rhat_from_stats(stats, S).cpu().numpy() if (C > 1 or distributed.is_multi()) else None
+        ess_flat = ess_dev.cpu().numpy()
+        results.append(HmcResult(ess=mc.split(ess_flat), is_accepted=None, samples=None, rhat=rhat,
+                                 step_mult=o["step_mult"].cpu().numpy(), accept_count=o["accept_count"].cpu().numpy(),
+                                 num_transitions=o["num_transitions"], ess_flat=ess_flat,
+                                 accept_stats=tuple(float(v) for v in acc.cpu().numpy())))
+    return results
 
 
 def find_best_learning_rate(target, model_config, *, learning_rates, num_optimization_steps, num_mc_samples,

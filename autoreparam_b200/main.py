@@ -47,7 +47,8 @@ def build_parser():
     a("--learning_rates", default="0.02,0.05,0.1,0.2,0.4", help="Learning rates (list)")
     a("--num_optimization_steps", type=int, default=3000)
     a("--num_mc_samples", type=int, default=256)
-    a("--num_leapfrog_steps", type=int, default=None)
+    a("--num_leapfrog_steps", default=None,
+      help="int; with --inference=HMCtuning also a comma-separated list: the whole grid then runs in ONE launch")
     a("--count_in_leapfrog_steps", type=_bool, nargs="?", const=True, default=False)
     a("--num_samples", type=int, default=50000)
     a("--num_chains", type=int, default=100)
@@ -163,8 +164,73 @@ def get_best_num_leapfrog_steps_from_tuning_runs(tuning_runs):
     return best_run["num_leapfrog_steps"]
 
 
+def _parse_leapfrog_steps(FLAGS):
+    v = FLAGS.num_leapfrog_steps
+    if v is None or v == "":
+        return []
+    if isinstance(v, (int, np.integer)):
+        return [int(v)]
+    return [int(x) for x in str(v).split(",") if x.strip()]
+
+
+def run_hmc_tuning_grid(FLAGS, model_config, results_dir, file_path, grid):
+    """--inference=HMCtuning --num_leapfrog_steps=L1,L2,...: the reference runs one process per L (main.py:316-329,
+    375-384); here (chains x L) is the batch axis of ONE launch and one `tuning_runs` entry per L is appended, in the
+    order given, exactly as the separate invocations would have written them."""
+    if not os.path.exists(file_path):
+        raise Exception("Run VI first to find initial step sizes")
+    with open(file_path) as f:
+        prev_results = json.load(f)
+    done = set(r["num_leapfrog_steps"] for r in prev_results.get("tuning_runs", []))
+    todo = []
+    for L in grid:
+        if L in done:
+            print("A tuning run already exists for HMC with {} leapfrog steps skipping.".format(L))
+        else:
+            todo.append(L)
+    if not todo:
+        return
+    rank, world = distributed.rank_world()
+    _check_sharding(FLAGS, world)
+    rng = np.random.default_rng(FLAGS.seed + 1)
+    initial_states = list(util.variational_inits_from_params(
+        prev_results["learned_variational_params"], param_names=model_config.param_names,
+        num_inits=FLAGS.num_chains, rng=rng).values())
+    target, _ = create_target_graph(FLAGS, model_config, results_dir)
+    lo, hi = distributed.shard_range(FLAGS.num_chains, rank, world)
+    z0 = model_config.join(initial_states)[lo:hi]
+    scale = (lambda v, L: int(v / float(L))) if FLAGS.count_in_leapfrog_steps else (lambda v, L: v)   # main.py:318-324
+    Ss = [scale(FLAGS.num_samples, L) for L in todo]
+    Bs = [scale(FLAGS.num_burnin_steps, L) for L in todo]
+    As = [scale(FLAGS.num_adaptation_steps, L) for L in todo]
+    util.print("\nNumber of leaprog steps: grid {} in one launch.\n".format(todo))
+    start_time = time.time()
+    results = inference.hmc_tuning_grid(target, model_config, prev_results["initial_step_size"], z0,
+                                        num_leapfrog_steps=todo, num_samples=Ss, num_burnin_steps=Bs,
+                                        num_adaptation_steps=As, seed=FLAGS.seed, chain_offset=lo,
+                                        device=distributed.local_device(), precision=FLAGS.precision)
+    mcmc_time = time.time() - start_time
+    for L, S, B, res in zip(todo, Ss, Bs, results):
+        ess_flat = distributed.gather_chains(res.ess_flat, distributed.local_device())
+        if rank != 0:
+            continue
+        normalized = [1000 * e / (S * L) for e in model_config.split(ess_flat)]
+        ess_min, sem_min = util.get_min_ess(normalized, FLAGS.num_chains)
+        util.print("L = {}: ESS per 1000 gradients: {} +/- {}".format(L, ess_min, sem_min))
+        acceptance_rate = res.accept_stats[0] * 100. / float(S * FLAGS.num_chains)
+        # mcmc_time: the grid shares one launch; every entry carries the time of the whole grid divided evenly
+        save_hmc_results(file_path=file_path, tuning_runs={
+            "num_leapfrog_steps": L, "ess_min": float(ess_min), "sem_min": float(sem_min),
+            "acceptance_rate": float(acceptance_rate), "mcmc_time": mcmc_time / len(todo), "num_samples": S,
+            "num_burnin_steps": B})
+
+
 def run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False):
     """main.py:296-398."""
+    grid = _parse_leapfrog_steps(FLAGS)
+    if tuning and len(grid) > 1:
+        return run_hmc_tuning_grid(FLAGS, model_config, results_dir, file_path, grid)
+    FLAGS.num_leapfrog_steps = grid[0] if grid else None
     if os.path.exists(file_path):
         with open(file_path) as f:
             prev_results = json.load(f)
@@ -208,7 +274,7 @@ def run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False):
                         num_leapfrog_steps=FLAGS.num_leapfrog_steps, num_samples=FLAGS.num_samples,
                         num_burnin_steps=FLAGS.num_burnin_steps, num_adaptation_steps=FLAGS.num_adaptation_steps,
                         num_chains_to_save=n_save, seed=FLAGS.seed, chain_offset=lo, device=device,
-                        precision=FLAGS.precision)
+                        precision=FLAGS.precision, return_is_accepted=False)
     ess_flat = distributed.gather_chains(res.ess_flat, device)            # [C, D] over all ranks
     n_accepted = res.accept_stats[0]     # accepted kept transitions of ALL ranks (all-reduced inside inference.hmc)
     samples = res.samples

@@ -264,16 +264,21 @@ def main():
     target = graphs.TargetGraph(mc, args.method, a, b, False)
     step_sizes = mc.split(sigma_q)
     h2d = z0.nbytes + eps0.astype(np.float32).nbytes + 2 * D * 4
-    d2h = C * D * 4 + S * C + C * 8 + D * 8   # ESS [C, D], is_accepted [S, C] u8, step_mult + accept_count [C], R-hat [D] f64
+    # what main.py's run_hmc consumes comes back: ESS [C, D], step_mult + accept_count [C], accept counters, R-hat [D] f64.
+    # The [S, C, D] centred samples (3.3 GB) and the [S, C] accept flags stay in HBM: the reference's sess.run returns
+    # them (main.py:350-360), but the driver only ever reduces them to ESS / an accept count (and saves
+    # --num_chains_to_save traces, 0 by default).
+    d2h = C * D * 4 + C * 8 + 3 * 8 + D * 8
     inference.hmc(target, mc, step_sizes, z0, num_leapfrog_steps=L, num_samples=S,
                   num_burnin_steps=args.num_burnin_steps, num_adaptation_steps=args.num_adaptation_steps,
-                  seed=1, chain_offset=chain_lo, device=dev, engine_kind=args.engine)
+                  seed=1, chain_offset=chain_lo, device=dev, engine_kind=args.engine, return_is_accepted=False)
     barrier()
     e0 = time.perf_counter()
     for i in range(args.steps):
         res = inference.hmc(target, mc, step_sizes, z0, num_leapfrog_steps=L, num_samples=S,
                             num_burnin_steps=args.num_burnin_steps, num_adaptation_steps=args.num_adaptation_steps,
-                            seed=2000 + i, chain_offset=chain_lo, device=dev, engine_kind=args.engine)
+                            seed=2000 + i, chain_offset=chain_lo, device=dev, engine_kind=args.engine,
+                            return_is_accepted=False)
     barrier()
     e2e_s = time.perf_counter() - e0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -309,7 +314,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "grad_evals/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h),
+                    "returns": "ESS [C,D], step sizes / accept counts [C], R-hat [D] (reduced over all ranks); the [S,C,D] "
+                               "samples and [S,C] accept flags stay on the device (main.py reduces them to these)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf,

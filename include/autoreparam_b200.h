@@ -155,6 +155,16 @@ int64_t arp_hmc_num_transitions(const arp_hmc_config* cfg);
 int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_real* a, const arp_real* b, int64_t C,
                 const arp_hmc_buffers* buf, int mem, void* stream);
 
+/* Several HMC runs in ONE launch: replaces the loop of `--inference=HMCtuning --num_leapfrog_steps=L` invocations
+ * (main.py:316-329, 375-384: one process per L, each appending one entry to `tuning_runs`).  Run i takes
+ * num_leapfrog_steps / num_results / num_burnin_steps / num_adaptation_steps from cfgs[i] and eps0 + the output
+ * buffers (samples, is_accepted, step_mult, accept_count) from bufs[i]; every run starts from bufs[0].z0 and draws
+ * the SAME random streams a separate arp_hmc_run with cfgs[i] would (results are identical to num_runs separate
+ * calls).  seed, chain_offset, engine, lanes_per_chain and num_steps_between_results come from cfgs[0] and must
+ * agree.  (chains x runs) is the batch axis: 100 chains x 6 values of L fill 600 chain slots of one grid. */
+int arp_hmc_run_many(arp_model* m, const arp_hmc_config* cfgs, int32_t num_runs, const arp_real* a, const arp_real* b,
+                     int64_t C, const arp_hmc_buffers* bufs, int mem, void* stream);
+
 /* Interleaved CP / NCP sampler (--method=i): replaces inference.hmc_interleaved (inference.py:258-329)
  * + interleaved.Interleaved.one_step (interleaved.py:113-155): per transition one HMC step under rule A
  * (CP), one under rule B (NCP), each preceded by a re-bootstrap of (log-prob, gradient) in that rule's

@@ -182,6 +182,16 @@ mine = samples[:, lo:hi]
 r = distributed.rhat_allreduce(mine.mean(0), mine.var(0), S)
 ref = util.rhat_from_moments(samples.mean(0), samples.var(0), S)
 assert np.allclose(r, ref, rtol=1e-10), (r, ref)
+# the tensor path inference.hmc / main.run_hmc use (device tensors + one all-reduce; gloo tensors here)
+import torch
+st = distributed.rhat_stats(torch.as_tensor(mine.mean(0)), torch.as_tensor(mine.var(0)))
+distributed.allreduce_sum_(st)
+assert int(round(float(st[-1]))) == C, "chain count is reduced over the ranks"
+r2 = distributed.rhat_from_stats(st, S).numpy()
+assert np.allclose(r2, ref, rtol=1e-10), (r2, ref)
+acc = torch.tensor([float(hi - lo), 2.0 * (hi - lo)], dtype=torch.float64)
+distributed.allreduce_sum_(acc)
+assert acc.tolist() == [float(C), 2.0 * C]
 distributed.barrier(); distributed.shutdown()
 open(os.path.join(sys.argv[2], "ok_%d" % rank), "w").write("ok")
 """
@@ -201,3 +211,69 @@ def test_sharded_reductions_world_size_2_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+def test_cvip_parameter_maps_tied_and_untied():
+    """make_cvip_graph: which learnable parameter every coordinate's (a, b) reads
+    (program_transformations.py:486-533, 563-566): tied as written (b = 1), the paper's tie b = a, and the untied mode
+    where `a` has the shape of the site's loc and `b` of its scale."""
+    from autoreparam_b200 import graphs
+    from tests import common
+    mc = common.model_config("german_credit_lognormalcentered")
+    F, D = 62, 125
+    t = graphs.make_cvip_graph(mc, tied_pparams=True, tied_b_as_written=True)
+    assert t.num_params == D and (t.a_index == np.arange(D)).all() and (t.b_index == -1).all()
+    assert (t.a == 0.5).all() and (t.b == 1.0).all()
+    t = graphs.make_cvip_graph(mc, tied_pparams=True, tied_b_as_written=False)
+    assert t.num_params == D and (t.b_index == t.a_index).all() and (t.b == 0.5).all()
+    lr = graphs.learned_reparam_from_params(t, np.linspace(0.1, 0.9, D))
+    assert set(lr) == {"overall_log_scale_a", "overall_log_scale_b", "beta_log_scales_a", "beta_log_scales_b",
+                       "beta_a", "beta_b"} and np.array_equal(lr["beta_a"], lr["beta_b"])
+    a, b = graphs.reparam_to_ab(mc, lr)
+    assert np.allclose(a, np.linspace(0.1, 0.9, D), atol=1e-6) and np.allclose(b, a)
+    # untied: beta_log_scales ~ N(loc = overall_log_scale [scalar], scale = ones(F)): ONE a, F b's
+    t = graphs.make_cvip_graph(mc, tied_pparams=False)
+    keys = [(k, sh) for k, _, sh in t.params]
+    assert keys == [("overall_log_scale_a", ()), ("overall_log_scale_b", ()), ("beta_log_scales_a", ()),
+                    ("beta_log_scales_b", (F,)), ("beta_a", (F,)), ("beta_b", (F,))]
+    assert t.num_params == 2 + 1 + F + 2 * F
+    assert len(set(t.a_index[1:1 + F])) == 1 and len(set(t.b_index[1:1 + F])) == F
+    lr = graphs.learned_reparam_from_params(t, np.random.default_rng(0).uniform(size=t.num_params))
+    assert np.shape(lr["beta_log_scales_a"]) == () and np.shape(lr["beta_log_scales_b"]) == (F,)
+    a, b = graphs.reparam_to_ab(mc, lr)
+    assert np.allclose(a[1:1 + F], float(lr["beta_log_scales_a"])) and np.allclose(b[1:1 + F], lr["beta_log_scales_b"])
+    # gammascale: beta_log_scales is not a Normal site -> never reparameterised, a = b = 1 there
+    mg = common.model_config("german_credit_gammascale")
+    t = graphs.make_cvip_graph(mg, tied_pparams=True)
+    assert (t.a_index[1:1 + F] == -1).all() and (t.a[1:1 + F] == 1.0).all() and t.num_params == 1 + F
+    # electric: a ~ N(loc [96, 1], scale = 1. scalar); mua / sigma_y / b have scalar locs and vector scales
+    me = common.model_config("electric")
+    t = graphs.make_cvip_graph(me, tied_pparams=False)
+    shapes = dict((k, sh) for k, _, sh in t.params)
+    assert shapes["a_a"] == (96, 1) and shapes["a_b"] == () and shapes["mua_a"] == () and shapes["mua_b"] == (4,)
+
+
+def test_leapfrog_grid_flag_parsing():
+    from autoreparam_b200 import main
+    P = main.build_parser()
+    assert main._parse_leapfrog_steps(P.parse_args(["--num_leapfrog_steps=4"])) == [4]
+    assert main._parse_leapfrog_steps(P.parse_args(["--num_leapfrog_steps", "2,4,8,16"])) == [2, 4, 8, 16]
+    assert main._parse_leapfrog_steps(P.parse_args([])) == []
+    with pytest.raises(NotImplementedError):
+        main.check_supported(P.parse_args(["--model=gp_poisson"]))
+    with pytest.raises(NotImplementedError):
+        main.check_supported(P.parse_args(["--reparameterise_variational"]))
+    main.check_supported(P.parse_args(["--discrete_prior", "--tied_pparams=False"]))
+
+
+def test_discrete_prior_density_known_values():
+    """Oracle restatement of the mixture-of-Laplace prior (main.py:244-253) against a direct evaluation."""
+    import torch
+    from oracle import oracle as O
+    p = torch.tensor([0.0, 0.03, 0.5, 0.97, 1.0], dtype=torch.float64)
+    got = O.discrete_prior_logp(p).numpy()
+    w = np.exp([0.0, 5.0, 0.0]); w /= w.sum()
+    lap = lambda x, m: np.exp(-np.abs(x - m) / 0.1) / 0.2
+    ref = np.log(w[0] * lap(p.numpy(), 0.0) + w[1] * 1.0 + w[2] * lap(p.numpy(), 1.0))
+    assert np.allclose(got, ref, atol=1e-12)
+    assert got[0] > got[2] and abs(got[0] - got[4]) < 1e-12     # mass piles up at 0 and 1, symmetric

@@ -128,3 +128,30 @@ def test_radon_posterior_matches_closed_form():
         z_score = np.abs(m_hat - mean) / (sd / np.sqrt(C))
         assert z_score.max() < 6.0, (method, z_score.max())
         assert np.abs(s_hat / sd - 1).max() < 0.08, (method, np.abs(s_hat / sd - 1).max())
+
+
+@pytest.mark.parametrize("model,eng", [("8schools", engine.ENGINE_SIMT), ("radon", engine.ENGINE_SIMT),
+                                       ("german_synth", engine.ENGINE_TCGEN05)])
+def test_tuning_grid_in_one_launch_equals_separate_runs(model, eng):
+    """arp_hmc_run_many: (chains x L) as the batch axis of one launch -- every run must reproduce the separate
+    arp_hmc_run with the same L bit for bit (same initial states, same Philox streams, same arithmetic), including
+    runs whose sample / burn-in / adaptation counts differ (--count_in_leapfrog_steps)."""
+    C = 100 if model != "german_synth" else 128 + 60
+    mc = common.model_config(model)
+    D = mc.num_coords
+    a, b = common.ab_for("NCP", D)
+    z0 = common.random_states(model, D, C, seed=5, scale=0.3).astype(np.float32)
+    Ls, Ss, Bs, As = [1, 4, 7], [12, 6, 4], [9, 5, 3], [8, 4, 2]
+    sig = np.full(D, 0.05)
+    eps = [sig / (L / 4.0) ** 2 for L in Ls]
+    many = engine.hmc_run_many(mc, z0, eps, a, b, num_leapfrog_steps=Ls, num_results=Ss, num_burnin_steps=Bs,
+                               num_adaptation_steps=As, seed=11, chain_offset=7, engine=eng)
+    for i, L in enumerate(Ls):
+        one = engine.hmc_run(mc, z0, eps[i], a, b, num_leapfrog_steps=L, num_results=Ss[i], num_burnin_steps=Bs[i],
+                             num_adaptation_steps=As[i], seed=11, chain_offset=7, engine=eng, want_final=False)
+        assert np.array_equal(many[i]["samples"], one["samples"]), L
+        assert np.array_equal(many[i]["is_accepted"], one["is_accepted"]), L
+        assert np.array_equal(many[i]["step_mult"], one["step_mult"]), L
+        assert np.array_equal(many[i]["accept_count"], one["accept_count"]), L
+        assert many[i]["num_transitions"] == one["num_transitions"]
+    assert many[1]["is_accepted"].mean() > 0.2
