@@ -26,13 +26,15 @@ class HmcConfig(C.Structure):
     _fields_ = [("num_leapfrog_steps", C.c_int32), ("num_results", C.c_int32), ("num_burnin_steps", C.c_int32),
                 ("num_adaptation_steps", C.c_int32), ("num_steps_between_results", C.c_int32),
                 ("seed", C.c_uint64), ("chain_offset", C.c_int64), ("target_accept_prob", C.c_double),
-                ("lanes_per_chain", C.c_int32), ("engine", C.c_int32)]
+                ("lanes_per_chain", C.c_int32), ("engine", C.c_int32), ("stream_window", C.c_int32)]
 
 
 class HmcBuffers(C.Structure):
     _fields_ = [("z0", C.c_void_p), ("eps0", C.c_void_p), ("ext_momenta", C.c_void_p), ("ext_log_u", C.c_void_p),
                 ("samples", C.c_void_p), ("samples_orig", C.c_void_p), ("is_accepted", C.c_void_p),
-                ("final_z", C.c_void_p), ("step_mult", C.c_void_p), ("accept_count", C.c_void_p)]
+                ("final_z", C.c_void_p), ("step_mult", C.c_void_p), ("accept_count", C.c_void_p),
+                ("stream_mean", C.c_void_p), ("stream_var", C.c_void_p), ("stream_ess", C.c_void_p),
+                ("stream_truncated", C.c_void_p)]
 
 
 class IlvConfig(C.Structure):

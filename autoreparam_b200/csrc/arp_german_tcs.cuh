@@ -29,6 +29,22 @@ __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, %1;
 #ifndef TCS_PROFILE
 #define TCS_PROFILE 0   // 1: one lane per worker warp accumulates clock() per phase and printf()s it (timing study only)
 #endif
+// TCS_GSPLIT 1: GEMM2 keeps SEPARATE TMEM accumulators for the head x head pass (q1 X1: the big products) and for the two
+// tail passes (q1 X2 + q2 X1: 2^-11 of it), and the workers add them in fp32 at the end of the step.  The tensor core's
+// fp32 accumulator is what limits the accuracy of G = X^T q: every MMA truncates at the magnitude of the running sum, and
+// with one accumulator for all three passes that is 192 dependent accumulations per step on partial sums ~10 x the
+// result (gradient at 1e-5 of the fp64 oracle, max-norm, typical-set states; the SIMT engine: 2e-7 .. 7e-7).  Split, the
+// head accumulator sees 64 accumulations (32 with NF = 32, where TMEM has room for one head accumulator per chunk
+// parity) and the tail sums are formed at their own scale.  Costs two (one) extra tcgen05.ld per step, no extra MMA.
+// (Measured and removed in round 2: a fresh accumulator per chunk / per group of 2 or 4 chunks with the running sum
+// kept by the workers in TMEM: 4 x more accurate, but 12 - 15 % slower -- the extra tcgen05.ld / st in the chunk loop.)
+// Default (1): split for NF = 64 only -- the real 1000 x 62 data, where the elementwise 1e-5 gradient test needs it and
+// the second accumulator costs 1 % (one extra load per step); for NF = 32 (two head accumulators + tails: three loads
+// per step, more spills at the 96-register cap) it was measured 5 % slower (158.8 vs 150.8 ms per bench step) for a
+// gradient that already passes the test.  2: split for both.  0: off.
+#ifndef TCS_GSPLIT
+#define TCS_GSPLIT 1
+#endif
 #define TCS_THREADS (TC_WORKERS + 64)
 #define TCS_MMA_WARP (TC_WORKERS / 32)
 #define TCS_PROD_WARP (TC_WORKERS / 32 + 1)
@@ -58,8 +74,13 @@ struct Tcs {
   static constexpr bool MOM_AHEAD = (NF == 32);
   static constexpr uint32_t MOM = TMEM_PTR + 16;
   static constexpr uint32_t BYTES = MOM + (MOM_AHEAD ? NLOC * TC_WORKERS * 4 : 0);
-  // TMEM columns
-  static constexpr uint32_t COL_H = 0, COL_G = 256, COL_R2 = 320;
+  // TMEM columns: H 0 .. 255 (two chunk buffers; the fp16 head of q overwrites H in place), G accumulators, fp16 tail
+  // of q 320 .. 447.  NF = 32: G head accumulators at 256 / 288 (even / odd chunks), tail accumulator at 448;
+  // NF = 64: one head accumulator at 256 .. 319, tail accumulator at 448 .. 511.
+  static constexpr uint32_t COL_H = 0, COL_G = 256, COL_R2 = 320, COL_GB = 448;
+  static constexpr bool GSPLIT = (TCS_GSPLIT == 2) || (TCS_GSPLIT == 1 && NF == 64);
+  static constexpr int NHEAD = (NF == 32) ? 2 : 1;
+  static constexpr uint32_t COL_G1 = COL_G + 32;   // NHEAD == 2 only
   static constexpr uint32_t IDESC_G1 = (1u << 4) | ((uint32_t)(TC_CHUNK >> 3) << 17) | ((128u >> 4) << 24);
   static constexpr uint32_t IDESC_G2 = (1u << 4) | (1u << 16) | ((uint32_t)(NF >> 3) << 17) | ((128u >> 4) << 24);
   static_assert(BYTES <= 232448, "shared memory budget");
@@ -68,7 +89,6 @@ struct Tcs {
 struct TcsParams {
   const uint8_t* img;   // nchunk stage images
   int N, F, nchunk;
-  int bias;             // 1: K-slot NF - 1 of every image row holds 1.0 and the A operand puts -31 there (see tcs_epilogue32)
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -112,34 +132,22 @@ __device__ __forceinline__ void split_pack_trunc(float x0, float x1, uint32_t& h
 #define TCS_SPLIT split_pack
 #endif
 
-// BIAS: the clamp is folded into the GEMM and an add.  A spare K-slot (F < NF) carries the constant -31: the image rows
-// hold 1.0 there and the A operand -31, so GEMM1 yields h' = h - 31 and with e' = 2^h' = 2^-31 2^h
-//   ds = sat(e' + 2^-31) = 2^-31 (1 + 2^h) clamped at 1      (one FADD.SAT instead of the half-rate FMNMX + FADD),
-//   q  = 2^-31 / ds  (clamped at h = 31, q < 5e-10),  prod of four ds >= 2^-124: no under- / overflow;
-// last step: min(h, 31) + log2 q = min(h', 0) - log2 ds, i.e. per group  sum min(h', 0) + log2(1 / prod ds).
-#define TCS_2M31 4.656612873077392578125e-10f
-template <bool SHARE, bool LAST, bool BIAS>
+// (Measured and removed in round 2: folding the clamp into GEMM1 through a bias K-slot -- h' = h - 31, one FADD.SAT
+// instead of the half-rate FMNMX + FADD per element -- changed nothing (153.1 vs 153.2 ms), and carrying both epilogue
+// variants in the kernel cost 4 %.  The epilogue is not dispatch-bound; see DESIGN.md.)
+template <bool SHARE, bool LAST>
 __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1, uint32_t* r2, float& lik) {
   float m[8][4], e[8][4], p01[8], p23[8], inv[8];
   auto stage_a = [&](int g) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if constexpr (BIAS) {
-        const float hp = __uint_as_float(hv[4 * g + q]);
-        if (LAST) m[g][q] = fminf(hp, 0.f);
-        e[g][q] = ex2_approx(hp);
-      } else {
-        m[g][q] = fminf(__uint_as_float(hv[4 * g + q]), 30.f);
-        e[g][q] = ex2_approx(m[g][q]);
-      }
+      m[g][q] = fminf(__uint_as_float(hv[4 * g + q]), 30.f);
+      e[g][q] = ex2_approx(m[g][q]);
     }
   };
   auto stage_b = [&](int g) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if constexpr (BIAS) e[g][q] = __saturatef(e[g][q] + TCS_2M31);
-      else e[g][q] += 1.0f;
-    }
+    for (int q = 0; q < 4; ++q) e[g][q] += 1.0f;
     if constexpr (SHARE) {
       p01[g] = e[g][0] * e[g][1];
       p23[g] = e[g][2] * e[g][3];
@@ -152,12 +160,11 @@ __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1,
   auto stage_c = [&](int g) {
     float qv[4];
     if constexpr (SHARE) {
-      const float is = BIAS ? inv[g] * TCS_2M31 : inv[g];
-      const float i01 = is * p23[g], i23 = is * p01[g];
+      const float i01 = inv[g] * p23[g], i23 = inv[g] * p01[g];
       qv[0] = i01 * e[g][1]; qv[1] = i01 * e[g][0]; qv[2] = i23 * e[g][3]; qv[3] = i23 * e[g][2];
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) qv[q] = BIAS ? e[g][q] * TCS_2M31 : e[g][q];
+      for (int q = 0; q < 4; ++q) qv[q] = e[g][q];
     }
     if (LAST) {
       // ln sigmoid(t eta) / ln2 = h + log2 q.  The two terms cancel for well-predicted observations, so the
@@ -166,9 +173,8 @@ __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1,
       if constexpr (SHARE) {
         lik += ((m[g][0] + m[g][1]) + (m[g][2] + m[g][3])) + lg2_approx(inv[g]);
       } else {
-        // BIAS: e[][] holds 1 / ds here and min(h', 0) - log2 ds is the term; else qv = q and min(h, 30) + log2 q
-        const float t0 = m[g][0] + lg2_approx(BIAS ? e[g][0] : qv[0]), t1 = m[g][1] + lg2_approx(BIAS ? e[g][1] : qv[1]);
-        const float t2 = m[g][2] + lg2_approx(BIAS ? e[g][2] : qv[2]), t3 = m[g][3] + lg2_approx(BIAS ? e[g][3] : qv[3]);
+        const float t0 = m[g][0] + lg2_approx(qv[0]), t1 = m[g][1] + lg2_approx(qv[1]);
+        const float t2 = m[g][2] + lg2_approx(qv[2]), t3 = m[g][3] + lg2_approx(qv[3]);
         lik += (t0 + t1) + (t2 + t3);
       }
     }
@@ -228,7 +234,7 @@ __device__ __noinline__ void tcs_draw_momenta_call(uint64_t seed, uint32_t gchai
 
 // GAMMA = german_credit_gammascale (models.py:930-945): beta_log_scales is not a Normal site (never
 // reparameterised); beta ~ N(0, exp(overall_log_scale + beta_log_scales)).
-template <int NF, bool GAMMA>
+template <int NF, bool GAMMA, bool MULTI = false>
 __global__ void
 #ifdef TCS_MAXNREG
 __maxnreg__(TCS_MAXNREG)
@@ -237,9 +243,10 @@ __launch_bounds__(TCS_THREADS, 1)
 #endif
 k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
   using K = Tcs<NF>;
-  // multi-run launch (leapfrog-step tuning grid): this CTA's run overrides L, the transition counts, the step sizes
-  // and the output buffers; chain0 = index of the CTA's first chain inside its run
-  const int chain0 = hmc_apply_slice(p, (int)blockIdx.x * TC_CHAINS);
+  // multi-run launch (leapfrog-step tuning grid): this CTA's run supplies L, the transition counts, the step sizes and
+  // the output buffers; rv.chain = index of the CTA's first chain inside its run
+  const HmcRun rv = hmc_run_view<MULTI>(p, (int)blockIdx.x * TC_CHAINS);
+  const int chain0 = rv.chain;
   constexpr int FPW = K::FPW, NLOC = K::NLOC;
   constexpr bool V_IN_REGS = (NF <= 32);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -254,7 +261,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     for (int i = tid; i < p.D; i += TCS_THREADS) {
       par[i] = p.a[i];
       par[(2 * NF + 4) + i] = p.b[i];
-      par[2 * (2 * NF + 4) + i] = p.eps0[i];
+      par[2 * (2 * NF + 4) + i] = ARP_RUN(eps0)[i];
     }
   }
   if (warp == TCS_MMA_WARP) {
@@ -275,7 +282,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_s;
-  const int n_lf = p.T * p.L;
+  const int n_lf = ARP_RUN(T) * ARP_RUN(L);
   const int NCH = tp.nchunk;
 
   if (warp == TCS_PROD_WARP) {
@@ -334,8 +341,17 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               for (int kk = 0; kk < 2; ++kk) {
                 const uint32_t a_t = pa_sel[q] == 0 ? a_h + 32 * w + 8 * kk : a_r2 + 16 * w + 8 * kk;
                 const uint32_t og = 4 * w + 2 * kk;  // 8-observation group inside the chunk
-                mma_ts(tmu + K::COL_G, a_t, b_base + (uint64_t)((pb_sel[q] * K::XCHUNK + og * K::SG) >> 4), K::IDESC_G2,
-                       (c | q | w | kk) ? 1u : 0u);
+                if constexpr (!K::GSPLIT) {
+                  mma_ts(tmu + K::COL_G, a_t, b_base + (uint64_t)((pb_sel[q] * K::XCHUNK + og * K::SG) >> 4), K::IDESC_G2,
+                         (c | q | w | kk) ? 1u : 0u);
+                } else if (q == 0) {
+                  const uint32_t hc = K::NHEAD == 2 ? (uint32_t)(c >> 1) : (uint32_t)c;   // uses of this accumulator so far
+                  mma_ts(tmu + ((K::NHEAD == 2 && (c & 1)) ? K::COL_G1 : K::COL_G), a_t,
+                         b_base + (uint64_t)((pb_sel[q] * K::XCHUNK + og * K::SG) >> 4), K::IDESC_G2, (hc | w | kk) ? 1u : 0u);
+                } else {
+                  mma_ts(tmu + K::COL_GB, a_t, b_base + (uint64_t)((pb_sel[q] * K::XCHUNK + og * K::SG) >> 4), K::IDESC_G2,
+                         (c | (q - 1) | w | kk) ? 1u : 0u);
+                }
               }
           tc_commit(stage_free_bar);   // stage free once GEMM2(c) has read it
         }
@@ -363,10 +379,9 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     // ====================== chain workers (4 per chain) ======================
     const int w = tid >> 7, r = tid & 127;
     const int row = blockIdx.x * TC_CHAINS + r;    // workspace row
-    const int chain = chain0 + r;                  // chain index inside the run: RNG streams, outputs
+    const int chain = MULTI ? chain0 + r : row;    // chain index inside the run: RNG streams, outputs
     const bool valid = chain < p.C;
     const int D = p.D, F = tp.F;
-    const bool bias = tp.bias != 0;
     // features are dealt to the four workers of a chain in contiguous, balanced ranges (25 -> 7, 6, 6, 6); worker w
     // owns K-slots [FPW w, FPW w + nf) of the A operand / X images and the matching columns of G
     const int nf = F / TC_NQ + (w < F % TC_NQ ? 1 : 0);
@@ -428,7 +443,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
     const bool mom_ahead = K::MOM_AHEAD && !p.ext_momenta;
     if (mom_ahead) tcs_draw_momenta_call<FPW>(p.seed, gchain, (unsigned int)p.t_begin, fstart, nf, F, mom_next, 3);
 
-    for (int t = 0; t < p.T; ++t) {
+    for (int t = 0; t < ARP_RUN(T); ++t) {
       const int tg = p.t_begin + t;
       TCS_TICK(9)
       // current state: global loads issued before the Philox block so that their L2 round trip hides behind it
@@ -468,8 +483,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       // GEMM1 return inf / NaN and the clamp below would swallow it: such a trajectory is rejected outright
       bool ovf = false;
       TCS_TICK(0)
-      for (int l = 0; l < p.L; ++l) {
-        const bool last = (l == p.L - 1);
+      for (int l = 0; l < ARP_RUN(L); ++l) {
+        const bool last = (l == ARP_RUN(L) - 1);
         float lp_top = 0.f;
         const Site s0 = site_fwd_fast(xs[0], 0.f, ARP_LOG_10, a0, b0, lp_top);
 #pragma unroll
@@ -488,8 +503,6 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
               const Site sb = site_fwd_fast(xs[(1 + FPW + k) * TC_WORKERS], 0.f, ls, pa_s[1 + F + f], pb_s[1 + F + f], dummy);
               be[k8] = sb.x * LOG2E;   // GEMM1 then yields log2(e) t eta: one FMUL less per likelihood element
               ovf |= !(fabsf(be[k8]) < 60000.f);   // outside the fp16 range of the A operand (or NaN)
-            } else if (bias && w == TC_NQ - 1 && k == FPW - 1) {
-              be[k8] = -31.f;   // the bias slot (K-slot NF - 1; free because F < NF)
             }
           }
           uint4 hi, lo;
@@ -507,8 +520,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         // and every worker of the CTA would otherwise idle (~2.3k clk per step); half of the draw in each of the last
         // two leapfrog steps (all of it in the only step when L = 1)
         {
-          const int parts = (last ? 2 : 0) | ((l == p.L - 2 || p.L == 1) ? 1 : 0);
-          if (mom_ahead && parts && t + 1 < p.T)
+          const int parts = (last ? 2 : 0) | ((l == ARP_RUN(L) - 2 || ARP_RUN(L) == 1) ? 1 : 0);
+          if (mom_ahead && parts && t + 1 < ARP_RUN(T))
             tcs_draw_momenta_call<FPW>(p.seed, gchain, (unsigned int)(tg + 1), fstart, nf, F, mom_next, parts);
         }
         TCS_TICK(1)
@@ -523,13 +536,8 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
           TC_LD32(h_addr, hv);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           TCS_TICK(3)
-          if (bias) {
-            if (last) tcs_epilogue32<K::RCP_SHARE, true, true>(hv, r1, r2, lik);
-            else tcs_epilogue32<K::RCP_SHARE, false, true>(hv, r1, r2, lik);
-          } else {
-            if (last) tcs_epilogue32<K::RCP_SHARE, true, false>(hv, r1, r2, lik);
-            else tcs_epilogue32<K::RCP_SHARE, false, false>(hv, r1, r2, lik);
-          }
+          if (last) tcs_epilogue32<K::RCP_SHARE, true>(hv, r1, r2, lik);
+          else tcs_epilogue32<K::RCP_SHARE, false>(hv, r1, r2, lik);
           TCS_TICK(14)
           TC_ST16(tmem + lane_off + K::COL_H + b * TC_CHUNK + 32 * w, r1);
           TC_ST16(tmem + lane_off + K::COL_R2 + b * 64 + 16 * w, r2);
@@ -543,9 +551,33 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
         TCS_TICK(5)
         tc_fence_after();
         uint32_t gv[FPW];
-        if constexpr (FPW == 8) { TC_LD8(tmem + lane_off + K::COL_G + 8 * w, gv); }
-        else { TC_LD16(tmem + lane_off + K::COL_G + 16 * w, gv); }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        {
+          auto g_load = [&](uint32_t col, uint32_t* dst) {
+            const uint32_t ga = tmem + lane_off + col + FPW * w;
+            if constexpr (FPW == 8) { TC_LD8(ga, dst); } else { TC_LD16(ga, dst); }
+          };
+          g_load(K::COL_G, gv);
+          if constexpr (K::GSPLIT) {
+          // two rounds through one scratch array (head of the odd chunks, then the tails): all three accumulators in
+          // flight at once were 16 more live registers at the 96-register cap (stack frame 56 -> 80 B)
+          uint32_t gt[FPW];
+          const bool two = K::NHEAD == 2 && NCH > 1;     // the odd-chunk accumulator has been written
+          if constexpr (K::NHEAD == 2) {
+            if (two) g_load(K::COL_G1, gt);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (two) {
+#pragma unroll
+              for (int k = 0; k < FPW; ++k) gv[k] = __float_as_uint(__uint_as_float(gv[k]) + __uint_as_float(gt[k]));
+            }
+          }
+          g_load(K::COL_GB, gt);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < FPW; ++k) gv[k] = __float_as_uint(__uint_as_float(gv[k]) + __uint_as_float(gt[k]));
+          } else {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+        }
         float acc0 = 0.f, lps = 0.f;
         // NF = 64: fetch all momenta before the update loop (inside it every iteration would wait an L2 round trip)
         float vq[V_IN_REGS ? 1 : 2 * FPW];
@@ -648,19 +680,19 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
       }
       TCS_TICK(12)
       const int t1 = tg + 1;
-      if (t1 <= p.num_adapt) {
+      if (t1 <= ARP_RUN(num_adapt)) {
         const float ft = (float)t1;
         Hc += p.target_accept - expf(log_alpha < 0.f ? log_alpha : 0.f);
         const float log_step = ARP_LOG_10 - Hc * sqrtf(ft) / ((ft + 10.f) * 0.05f);
         const float eta = powf(ft, -0.75f);
         lavg = eta * log_step + (1.f - eta) * lavg;
-        mult = (t1 < p.num_adapt) ? expf(log_step) : expf(lavg);
+        mult = (t1 < ARP_RUN(num_adapt)) ? expf(log_step) : expf(lavg);
       }
       TCS_TICK(13)
-      const int since = tg - p.num_burnin;
+      const int since = tg - ARP_RUN(num_burnin);
       if (since >= 0 && (since % p.stride) == 0 && valid) {
         const int s = since / p.stride;
-        if (s < p.S) {
+        if (s < ARP_RUN(S)) {
           const size_t o = ((size_t)s * p.C + chain) * D;
           float xq[NLOC], zq[NLOC];
 #pragma unroll
@@ -668,18 +700,18 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
             xq[i] = 0.f; zq[i] = 0.f;
             if (owned(i) && (i > 0 || w == 0)) {
               const int d = dof(i);
-              if (p.samples) xq[i] = XCc(d);
-              if (p.samples_orig) zq[i] = Z(d);
+              if (ARP_RUN(samples)) xq[i] = XCc(d);
+              if (ARP_RUN(samples_orig)) zq[i] = Z(d);
             }
           }
 #pragma unroll
           for (int i = 0; i < NLOC; ++i)
             if (owned(i) && (i > 0 || w == 0)) {
               const int d = dof(i);
-              if (p.samples) p.samples[o + d] = xq[i];
-              if (p.samples_orig) p.samples_orig[o + d] = zq[i];
+              if (ARP_RUN(samples)) ARP_RUN(samples)[o + d] = xq[i];
+              if (ARP_RUN(samples_orig)) ARP_RUN(samples_orig)[o + d] = zq[i];
             }
-          if (p.is_accepted && w == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
+          if (ARP_RUN(is_accepted) && w == 0) ARP_RUN(is_accepted)[(size_t)s * p.C + chain] = acc ? 1 : 0;
         }
       }
     }
@@ -709,7 +741,7 @@ k_german_tcs_hmc(TcsParams tp, HmcWs ws, HmcArgs p) {
 struct GermanTcs {
   DevBuf img;
   int N = 0, F = 0, nf_pad = 0, nchunk = 0;
-  bool ok = false, bias = false;
+  bool ok = false;
 
   // X [N, F] fp32 row-major, y [N] in {0, 1} -> per-chunk stage images (head | tail) of the rows t_n X_n,
   // t_n = 2 y_n - 1, zero padded
@@ -743,22 +775,6 @@ struct GermanTcs {
         memcpy(st + XCHUNK + off, &h2, 2);
       }
     }
-    // bias slot (K-slot nf_pad - 1, unused when f < nf_pad): 1.0 in the head image of EVERY row, padded rows included,
-    // so that a padded row still behaves as h = 0 (q = 1/2, zero contribution to X^T q) -- see tcs_epilogue32
-#ifndef TCS_NO_BIAS
-    bias = f < nf_pad;
-#else
-    bias = false;
-#endif
-    if (bias) {
-      const int sl = nf_pad - 1;
-      const __half one = __float2half_rn(1.f);
-      for (int i = 0; i < nchunk * TC_CHUNK; ++i) {
-        const int c = i / TC_CHUNK, rloc = i % TC_CHUNK;
-        const size_t off = (size_t)(rloc / 8) * SG + (size_t)(sl / 8) * 128 + (size_t)(rloc % 8) * 16 + (size_t)(sl % 8) * 2;
-        memcpy(buf.data() + (size_t)c * STAGE + off, &one, 2);
-      }
-    }
     cudaError_t e = upload(img, buf);
     if (e != cudaSuccess) { *err = cudaGetErrorString(e); return false; }
     N = n; F = f; ok = true;
@@ -767,19 +783,18 @@ struct GermanTcs {
   bool ready() const { return ok; }
 };
 
+template <int NF, bool GAMMA, bool MULTI>
+static inline cudaError_t tcs_launch_one(dim3 grid, cudaStream_t st, const TcsParams& tp, const HmcWs& ws, const HmcArgs& p) {
+  cudaError_t e = cudaFuncSetAttribute(k_german_tcs_hmc<NF, GAMMA, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Tcs<NF>::BYTES);
+  if (e != cudaSuccess) return e;
+  k_german_tcs_hmc<NF, GAMMA, MULTI><<<grid, TCS_THREADS, Tcs<NF>::BYTES, st>>>(tp, ws, p);
+  return cudaGetLastError();
+}
 template <bool GAMMA>
 static inline cudaError_t tcs_launch(int nf_pad, dim3 grid, cudaStream_t st, const TcsParams& tp, const HmcWs& ws, const HmcArgs& p) {
-  cudaError_t e;
-  if (nf_pad == 32) {
-    e = cudaFuncSetAttribute(k_german_tcs_hmc<32, GAMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tcs<32>::BYTES);
-    if (e != cudaSuccess) return e;
-    k_german_tcs_hmc<32, GAMMA><<<grid, TCS_THREADS, Tcs<32>::BYTES, st>>>(tp, ws, p);
-  } else {
-    e = cudaFuncSetAttribute(k_german_tcs_hmc<64, GAMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tcs<64>::BYTES);
-    if (e != cudaSuccess) return e;
-    k_german_tcs_hmc<64, GAMMA><<<grid, TCS_THREADS, Tcs<64>::BYTES, st>>>(tp, ws, p);
-  }
-  return cudaGetLastError();
+  if (p.slices) return nf_pad == 32 ? tcs_launch_one<32, GAMMA, true>(grid, st, tp, ws, p) : tcs_launch_one<64, GAMMA, true>(grid, st, tp, ws, p);
+  return nf_pad == 32 ? tcs_launch_one<32, GAMMA, false>(grid, st, tp, ws, p) : tcs_launch_one<64, GAMMA, false>(grid, st, tp, ws, p);
 }
 
 static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt, const HmcArgs& p, const real* z0,
@@ -806,16 +821,20 @@ static inline int german_tcs_hmc(GermanTcs& tc, const DevModel& dm, int fp_simt,
   if (ws.gx - ws.g != ws.xcx - ws.xc) { *err = "german_tcs_hmc: workspace layout"; return 1; }   // buffer-set flip
   const dim3 grid((unsigned)(Cpad / TC_CHAINS));
   const bool gamma = dm.kind == MODEL_GERMAN_GAMMA;
+#define TCS_INIT(KIND, FP)                                                                        \
+  do {                                                                                            \
+    if (p.slices) k_hmc_init<KIND, 1, FP, true><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);       \
+    else k_hmc_init<KIND, 1, FP, false><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);               \
+  } while (0)
   if (gamma) {
-    if (fp_simt == 32) k_hmc_init<MODEL_GERMAN_GAMMA, 1, 32><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
-    else k_hmc_init<MODEL_GERMAN_GAMMA, 1, 64><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
+    if (fp_simt == 32) TCS_INIT(MODEL_GERMAN_GAMMA, 32); else TCS_INIT(MODEL_GERMAN_GAMMA, 64);
   } else {
-    if (fp_simt == 32) k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 32><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
-    else k_hmc_init<MODEL_GERMAN_LOGNORMAL, 1, 64><<<grid, ARP_BLOCK, 0, st>>>(dm, ws, p, z0);
+    if (fp_simt == 32) TCS_INIT(MODEL_GERMAN_LOGNORMAL, 32); else TCS_INIT(MODEL_GERMAN_LOGNORMAL, 64);
   }
+#undef TCS_INIT
   launches->fetch_add(1);
   TCS_CUDA(cudaGetLastError());
-  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk, tc.bias ? 1 : 0};
+  TcsParams tp{tc.img.as<uint8_t>(), tc.N, tc.F, tc.nchunk};
   TCS_CUDA(gamma ? tcs_launch<true>(tc.nf_pad, grid, st, tp, ws, p) : tcs_launch<false>(tc.nf_pad, grid, st, tp, ws, p));
   launches->fetch_add(1);
   if (want_final) {

@@ -45,6 +45,18 @@ struct HmcArgs {
   // (L, transitions, adaptation / burn-in lengths, kept samples, step sizes, output buffers) from slices[i]
   const struct HmcSlice* slices;   // null: one run, the fields above
   int slice_rows;
+  // streaming statistics of the kept (centred) samples, for runs whose [S, C, D] traces cannot be stored
+  // (BASELINE configs[4]: 65 536 chains x 10 003 coordinates): per (chain, coordinate) a pivot (the first kept
+  // sample), the sum of y = x - pivot, a ring of the last W values of y, the first W values, and the W lag products
+  // sum_t y_t y_{t-k}.  All planes share the workspace layout (element (d, row) at d * sd + row * sc); k_stream_finalize
+  // turns them into mean / variance / ESS.  W = 0: off.
+  int stream_W;
+  size_t stream_plane;             // elements per plane
+  real* stream_pivot;              // [plane]
+  real* stream_sum;                // [plane]
+  real* stream_ring;               // [W][plane]
+  real* stream_head;               // [W][plane]
+  real* stream_acc;                // [W][plane]
 };
 
 struct HmcSlice {
@@ -54,16 +66,33 @@ struct HmcSlice {
   unsigned char* is_accepted;  // [S, C] or null
 };
 
-// Per-block view of the launch arguments: in a multi-run launch the block's run overrides the per-run fields.  Returns
-// the chain index inside the run (which keys z0, the RNG streams and the outputs); `row` indexes the workspace.
-__device__ __forceinline__ int hmc_apply_slice(HmcArgs& p, int row) {
-  if (!p.slices) return row;
-  const int sl = row / p.slice_rows;
-  const HmcSlice s = p.slices[sl];
-  p.L = s.L; p.T = s.T; p.num_adapt = s.num_adapt; p.num_burnin = s.num_burnin; p.S = s.S;
-  p.eps0 = s.eps0; p.samples = s.samples; p.samples_orig = nullptr; p.is_accepted = s.is_accepted;
-  return row - sl * p.slice_rows;
+// Per-block view of the per-run launch arguments of a multi-run launch.  Kernels are templated on MULTI and read a
+// field through ARP_RUN(f): the single-run instantiation takes it straight from the kernel parameters (constant-bank
+// operands, no registers), the multi-run one from this struct.  (Measured on the tcgen05 kernel: overriding fields of
+// the by-value parameter struct made ptxas copy it to local memory, -2 %; holding the per-run fields in registers in
+// the single-run path too cost 3 %.)
+struct HmcRun {
+  int L, T, num_adapt, num_burnin, S;
+  int chain;                   // index of workspace row `row` inside its run: keys z0, the RNG streams and the outputs
+  const real* eps0;
+  real* samples;
+  real* samples_orig;
+  unsigned char* is_accepted;
+};
+template <bool MULTI>
+__device__ __forceinline__ HmcRun hmc_run_view(const HmcArgs& p, int row) {
+  HmcRun r{};
+  r.chain = row;
+  if constexpr (MULTI) {
+    const int sl = row / p.slice_rows;
+    const HmcSlice s = p.slices[sl];
+    r.L = s.L; r.T = s.T; r.num_adapt = s.num_adapt; r.num_burnin = s.num_burnin; r.S = s.S;
+    r.chain = row - sl * p.slice_rows;
+    r.eps0 = s.eps0; r.samples = s.samples; r.samples_orig = nullptr; r.is_accepted = s.is_accepted;
+  }
+  return r;
 }
+#define ARP_RUN(f) (MULTI ? rv.f : p.f)
 
 template <int KIND, int LPC, bool WITH_A, int FP>
 __global__ void __launch_bounds__(ARP_BLOCK)
@@ -83,13 +112,13 @@ k_log_joint_grad(DevModel m, const real* __restrict__ a, const real* __restrict_
   if (chain < C && sub == 0 && lp_out) lp_out[chain] = lp;
 }
 
-template <int KIND, int LPC, int FP>
+template <int KIND, int LPC, int FP, bool MULTI = false>
 __global__ void __launch_bounds__(ARP_BLOCK)
 k_hmc_init(DevModel m, HmcWs ws, HmcArgs p, const real* z0) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = gtid / LPC;
   const int sub = gtid % LPC;
-  const int chain = hmc_apply_slice(p, row);     // every run of a multi-run launch starts from the same z0
+  const int chain = hmc_run_view<MULTI>(p, row).chain;  // every run of a multi-run launch starts from the same z0
   const bool valid = chain < p.C;
   const size_t co = (size_t)row * ws.sc;
   Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
@@ -105,25 +134,41 @@ k_hmc_init(DevModel m, HmcWs ws, HmcArgs p, const real* z0) {
   }
 }
 
-template <int KIND, int LPC, int FP>
+template <int KIND, int LPC, int FP, bool MULTI = false>
 __global__ void __launch_bounds__(ARP_BLOCK)
-k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
+k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int smem_dpad) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = gtid / LPC;
   const int sub = gtid % LPC;
-  const int chain = hmc_apply_slice(p, row);
+  const HmcRun rv = hmc_run_view<MULTI>(p, row);
+  const int chain = rv.chain;
   const bool valid = chain < p.C;
   const int D = p.D;
   const size_t co = (size_t)row * ws.sc;
   Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
   Vec X{ws.x + co, ws.sd}, GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
   Vec V{ws.v + co, ws.sd};
-  const real* __restrict__ eps0 = p.eps0;
+  // LPC > 1 and the seven state vectors of the block's chains fit in shared memory (smem_dpad > 0): the whole run
+  // works on a shared-memory copy (stride 1 per chain, as the [row][d] global layout) -- north_star's "one chain per
+  // warp, state on chip"; the global workspace is touched at the start and at the end only.
+  extern __shared__ __align__(16) unsigned char hmc_smem_raw[];
+  const bool on_chip = LPC > 1 && smem_dpad > 0;
+  if (on_chip) {
+    real* base = reinterpret_cast<real*>(hmc_smem_raw) + (size_t)(threadIdx.x / LPC) * 7 * smem_dpad;
+    for (int d = sub; d < D; d += LPC) {
+      base[d] = Z(d); base[smem_dpad + d] = G(d); base[2 * smem_dpad + d] = XC(d);
+    }
+    Z = Vec{base, 1}; G = Vec{base + smem_dpad, 1}; XC = Vec{base + 2 * smem_dpad, 1};
+    X = Vec{base + 3 * smem_dpad, 1}; GX = Vec{base + 4 * smem_dpad, 1}; XCX = Vec{base + 5 * smem_dpad, 1};
+    V = Vec{base + 6 * smem_dpad, 1};
+    __syncwarp();
+  }
+  const real* __restrict__ eps0 = ARP_RUN(eps0);
   real lp_cur = ws.lp[row], Hc = ws.H[row], lavg = ws.lavg[row], mult = ws.mult[row];
   int nacc = ws.nacc[row];
   const unsigned int gchain = p.chain_offset + (unsigned int)chain;
 
-  for (int t = 0; t < p.T; ++t) {
+  for (int t = 0; t < ARP_RUN(T); ++t) {
     const int tg = p.t_begin + t;
     // ---- momenta v0 ~ N(0, I); proposal starts at the current state
     real ke0 = 0;
@@ -157,7 +202,7 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
     }
     // ---- L leapfrog steps, two half kicks per step as TFP 0.7 does
     real lpx = 0, ke1 = 0;
-    for (int l = 0; l < p.L; ++l) {
+    for (int l = 0; l < ARP_RUN(L); ++l) {
       for (int d = sub; d < D; d += LPC) {
         const real e = ldg(eps0 + d) * mult;
         const real v = V(d) + (real)0.5 * e * GX(d);
@@ -165,7 +210,7 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
         X(d) = X(d) + e * v;
       }
       __syncwarp();
-      const bool last = (l == p.L - 1);
+      const bool last = (l == ARP_RUN(L) - 1);
       lpx = vg<KIND, LPC, false, FP>(m, p.a, p.b, X, GX, XCX, Vec{nullptr, 1}, Vec{nullptr, 1}, sub, last);
       __syncwarp();
       for (int d = sub; d < D; d += LPC) {
@@ -194,26 +239,52 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
     }
     // ---- per-chain dual averaging (TFP defaults: gamma 0.05, t0 10, kappa 0.75)
     const int t1 = tg + 1;
-    if (t1 <= p.num_adapt) {
+    if (t1 <= ARP_RUN(num_adapt)) {
       const real ft = (real)t1;
       Hc += p.target_accept - r_exp(log_alpha < (real)0 ? log_alpha : (real)0);
       const real log_step = ARP_LOG_10 - Hc * r_sqrt(ft) / ((ft + (real)10) * (real)0.05);
       const real eta = r_pow(ft, (real)-0.75);
       lavg = eta * log_step + ((real)1 - eta) * lavg;
-      mult = (t1 < p.num_adapt) ? r_exp(log_step) : r_exp(lavg);
+      mult = (t1 < ARP_RUN(num_adapt)) ? r_exp(log_step) : r_exp(lavg);
     }
     // ---- keep every `stride`-th state after burn-in
-    const int since = tg - p.num_burnin;
+    const int since = tg - ARP_RUN(num_burnin);
     if (since >= 0 && (since % p.stride) == 0 && valid) {
       const int s = since / p.stride;
-      if (s < p.S) {
+      if (s < ARP_RUN(S)) {
         const size_t o = ((size_t)s * p.C + chain) * D;
-        if (p.samples) for (int d = sub; d < D; d += LPC) p.samples[o + d] = XC(d);
-        if (p.samples_orig) for (int d = sub; d < D; d += LPC) p.samples_orig[o + d] = Z(d);
-        if (p.is_accepted && sub == 0) p.is_accepted[(size_t)s * p.C + chain] = acc ? 1 : 0;
+        if (ARP_RUN(samples)) for (int d = sub; d < D; d += LPC) ARP_RUN(samples)[o + d] = XC(d);
+        if (ARP_RUN(samples_orig)) for (int d = sub; d < D; d += LPC) ARP_RUN(samples_orig)[o + d] = Z(d);
+        if (ARP_RUN(is_accepted) && sub == 0) ARP_RUN(is_accepted)[(size_t)s * p.C + chain] = acc ? 1 : 0;
+        if (p.stream_W > 0) {
+          const int W = p.stream_W, slot = s % W, kmax = s < W - 1 ? s : W - 1;
+          const size_t plane = p.stream_plane;
+          for (int d = sub; d < D; d += LPC) {
+            const size_t e = (size_t)d * ws.sd + co;
+            const real xv = XC(d);
+            real piv;
+            if (s == 0) { piv = xv; p.stream_pivot[e] = xv; } else piv = p.stream_pivot[e];
+            const real y = xv - piv;
+            p.stream_sum[e] += y;
+            p.stream_ring[(size_t)slot * plane + e] = y;
+            if (s < W) p.stream_head[(size_t)s * plane + e] = y;
+            p.stream_acc[e] = fma(y, y, p.stream_acc[e]);
+            for (int k = 1; k <= kmax; ++k) {
+              int sl = slot - k;
+              if (sl < 0) sl += W;
+              real* a = p.stream_acc + (size_t)k * plane + e;
+              *a = fma(y, p.stream_ring[(size_t)sl * plane + e], *a);
+            }
+          }
+        }
       }
     }
     __syncwarp();
+  }
+  if (on_chip) {   // final state back to the workspace (final_z, and the contract that (z, g, xc) describe the chain)
+    for (int d = sub; d < D; d += LPC) {
+      ws.z[co + (size_t)d * ws.sd] = Z(d); ws.g[co + (size_t)d * ws.sd] = G(d); ws.xc[co + (size_t)d * ws.sd] = XC(d);
+    }
   }
   if (sub == 0) {
     ws.lp[row] = lp_cur;
@@ -222,6 +293,44 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p) {
     ws.mult[row] = mult;
     ws.nacc[row] = nacc;
   }
+}
+
+// Streaming statistics -> mean, biased variance and ESS per (chain, coordinate), [C][D] outputs.  With y = x - pivot,
+// m = mean(y) and A_k = sum_{t >= k} y_t y_{t-k}:
+//   c_k = sum_{t >= k} (y_t - m)(y_{t-k} - m) = A_k - m [(sum - head_k) + (sum - tail_k)] + (S - k) m^2,
+// head_k / tail_k = sums of the first / last k kept values -- exactly the centred lag products TFP's
+// effective_sample_size forms, so for a series whose first negative autocorrelation lies inside the window the
+// result equals arp_ess on the stored trace (up to fp32 round-off); otherwise `truncated` is set and the ESS uses all
+// W lags (an upper bound).  Same truncation rule and weights as arp_ess (reference inference.py:240).
+__global__ void k_stream_finalize(HmcWs ws, HmcArgs p, int S, real* mean_cd, real* var_cd, real* ess_cd, int* trunc_cd) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)p.C * p.D) return;
+  const int c = (int)(i / p.D), d = (int)(i % p.D);
+  const size_t e = (size_t)d * ws.sd + (size_t)c * ws.sc, plane = p.stream_plane;
+  const int W = p.stream_W;
+  const double sum = (double)p.stream_sum[e], m = sum / S;
+  if (mean_cd) mean_cd[i] = (real)((double)p.stream_pivot[e] + m);
+  const int K = W < S ? W : S;
+  double head = 0, tail = 0, acov0 = 0, acc = 0;
+  bool done = false;
+  for (int k = 0; k < K; ++k) {
+    if (k > 0) {
+      head += (double)p.stream_head[(size_t)(k - 1) * plane + e];
+      int sl = (S - k) % W;                      // slot of kept sample S - k
+      tail += (double)p.stream_ring[(size_t)sl * plane + e];
+    }
+    const double ck = (double)p.stream_acc[(size_t)k * plane + e] - m * ((sum - head) + (sum - tail)) + (double)(S - k) * m * m;
+    if (k == 0) {
+      acov0 = ck / S;
+      if (var_cd) var_cd[i] = (real)acov0;
+      if (!(acov0 > 0.0)) { if (ess_cd) ess_cd[i] = (real)NAN; if (trunc_cd) trunc_cd[i] = 0; return; }
+    }
+    const double rho = (ck / (double)(S - k)) / acov0;
+    if (rho < 0.0) { done = true; break; }
+    acc += (double)(S - k) / S * rho;
+  }
+  if (ess_cd) ess_cd[i] = (real)((double)S / (-1.0 + 2.0 * acc));
+  if (trunc_cd) trunc_cd[i] = (done || K == S) ? 0 : 1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -240,6 +240,20 @@ static int pick_lpc(const arp_model* m, long long C, int forced) {
 
 static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
+// On-chip state of the SIMT HMC kernel: with LPC > 1 the block's ARP_BLOCK / LPC chains keep their seven state vectors
+// in shared memory when that fits in 96 KB (two blocks per SM).  Returns the padded row length (0 = use the global
+// workspace) and the dynamic shared-memory size.  ARP_HMC_ONCHIP=0 disables it (A/B measurements).
+static int hmc_onchip_dpad(int lpc, int D, size_t* bytes) {
+  *bytes = 0;
+  static const bool off = [] { const char* e = getenv("ARP_HMC_ONCHIP"); return e && e[0] == '0'; }();
+  if (lpc <= 1 || off) return 0;
+  const int dpad = (int)round_up(D, 4) + 1;          // + 1: the chains of a warp start in different banks
+  const size_t b = (size_t)(ARP_BLOCK / lpc) * 7 * dpad * sizeof(real);
+  if (b > 96 * 1024) return 0;
+  *bytes = b;
+  return dpad;
+}
+
 // copies `n` reals from a caller buffer (host or device) into a fresh device buffer
 static int stage_in(DevBuf& buf, const void* src, size_t bytes, int mem, cudaStream_t st) {
   ARP_CUDA(buf.alloc(bytes));
@@ -414,11 +428,13 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
   if (cfg->engine < 0 || cfg->engine > 3) return fail("arp_hmc_run: unknown engine");
   if (cfg->engine >= 2 && !tc_ok)
     return fail("arp_hmc_run: the tcgen05 engine needs a german_credit model with 0/1 outcomes and at most 64 features");
-  const bool use_tc = tc_ok && (cfg->engine >= 2 || (cfg->engine == 0 && german_tc_auto(C)));
+  if (cfg->engine >= 2 && cfg->stream_window > 0) return fail("arp_hmc_run: streaming statistics need the SIMT engine");
+  const bool use_tc = tc_ok && cfg->stream_window <= 0 && (cfg->engine >= 2 || (cfg->engine == 0 && german_tc_auto(C)));
 #else
   if (cfg->engine >= 2) return fail("arp_hmc_run: the fp64 check build has no tcgen05 engine");
   const bool use_tc = false;
 #endif
+  if (cfg->stream_window < 0 || cfg->stream_window > 1024) return fail("arp_hmc_run: stream_window must be in [0, 1024]");
 
   // ---- stage inputs
   DevBuf da, db, dz0, deps, dmom, dlu, dsamp, dorig, dacc;
@@ -449,7 +465,7 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
   p.samples = samples; p.samples_orig = samples_orig; p.is_accepted = is_acc;
 
   DevBuf wsbuf, scal, nacc;
-  DevBuf dfz;
+  DevBuf dfz, dstream, dsout;
   real* out_mult_dev = nullptr;
   int* out_nacc_dev = nullptr;
   real* final_z_dev = nullptr;
@@ -482,18 +498,48 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
     ws.mult = sb; ws.lp = sb + Cpad; ws.H = sb + 2 * Cpad; ws.lavg = sb + 3 * Cpad;
     ws.nacc = nacc.as<int>();
     if (lpc == 1) { ws.sd = (int)Cpad; ws.sc = 1; } else { ws.sd = 1; ws.sc = (int)Dpad; }
+    const int W = cfg->stream_window;
+    if (W > 0) {   // streaming statistics: (3 W + 2) planes in the workspace layout, zero-initialised
+      ARP_CUDA(dstream.alloc((size_t)(3 * W + 2) * vec * sizeof(real)));
+      ARP_CUDA(cudaMemsetAsync(dstream.p, 0, (size_t)(3 * W + 2) * vec * sizeof(real), st));
+      real* sbase = dstream.as<real>();
+      p.stream_W = W; p.stream_plane = vec;
+      p.stream_pivot = sbase; p.stream_sum = sbase + vec; p.stream_ring = sbase + 2 * vec;
+      p.stream_head = sbase + (size_t)(2 + W) * vec; p.stream_acc = sbase + (size_t)(2 + 2 * W) * vec;
+    }
     const dim3 grid((unsigned)(Cpad / cpb)), block(ARP_BLOCK);
     const DevModel dm = m->dev;
     const int fp = m->fp;
-#define BODY(KIND, LPC, FP)                                          \
-    k_hmc_init<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p, z0); \
-    k_hmc_run<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p);
+    size_t oc_bytes = 0;
+    const int oc_dpad = hmc_onchip_dpad(lpc, D, &oc_bytes);
+#define BODY(KIND, LPC, FP)                                                                                           \
+    k_hmc_init<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p, z0);                                                  \
+    if (oc_bytes > 48 * 1024)                                                                                          \
+      ARP_CUDA(cudaFuncSetAttribute(k_hmc_run<KIND, LPC, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_bytes)); \
+    k_hmc_run<KIND, LPC, FP><<<grid, block, oc_bytes, st>>>(dm, ws, p, oc_dpad);
     ARP_DISPATCH(dm.kind, lpc, fp, BODY)
 #undef BODY
     g_launches.fetch_add(1);
     ARP_LAUNCH_CHECK();
     out_mult_dev = ws.mult;
     out_nacc_dev = ws.nacc;
+    if (W > 0 && (buf->stream_mean || buf->stream_var || buf->stream_ess || buf->stream_truncated)) {
+      const size_t n = (size_t)C * D;
+      real *om = buf->stream_mean, *ov = buf->stream_var, *oe = buf->stream_ess;
+      int* ot = buf->stream_truncated;
+      if (host) {
+        ARP_CUDA(dsout.alloc(3 * n * sizeof(real) + n * sizeof(int)));
+        om = dsout.as<real>(); ov = om + n; oe = ov + n; ot = reinterpret_cast<int*>(oe + n);
+      }
+      k_stream_finalize<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws, p, (int)S, om, ov, oe, ot);
+      ARP_LAUNCH_CHECK();
+      if (host) {
+        if (buf->stream_mean) ARP_CUDA(cudaMemcpyAsync(buf->stream_mean, om, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+        if (buf->stream_var) ARP_CUDA(cudaMemcpyAsync(buf->stream_var, ov, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+        if (buf->stream_ess) ARP_CUDA(cudaMemcpyAsync(buf->stream_ess, oe, n * sizeof(real), cudaMemcpyDeviceToHost, st));
+        if (buf->stream_truncated) ARP_CUDA(cudaMemcpyAsync(buf->stream_truncated, ot, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+      }
+    }
     if (buf->final_z) {
       ARP_CUDA(dfz.alloc((size_t)C * D * sizeof(real)));
       const long long n = (long long)C * D;
@@ -618,9 +664,13 @@ extern "C" int arp_hmc_run_many(arp_model* m, const arp_hmc_config* cfgs, int32_
     const dim3 grid((unsigned)(Cpad / cpb)), block(ARP_BLOCK);
     const DevModel dm = m->dev;
     const int fp = m->fp;
-#define BODY(KIND, LPC, FP)                                          \
-    k_hmc_init<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p, z0); \
-    k_hmc_run<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p);
+    size_t oc_bytes = 0;
+    const int oc_dpad = hmc_onchip_dpad(lpc, D, &oc_bytes);
+#define BODY(KIND, LPC, FP)                                                                                           \
+    k_hmc_init<KIND, LPC, FP, true><<<grid, block, 0, st>>>(dm, ws, p, z0);                                            \
+    if (oc_bytes > 48 * 1024)                                                                                          \
+      ARP_CUDA(cudaFuncSetAttribute(k_hmc_run<KIND, LPC, FP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_bytes)); \
+    k_hmc_run<KIND, LPC, FP, true><<<grid, block, oc_bytes, st>>>(dm, ws, p, oc_dpad);
     ARP_DISPATCH(dm.kind, lpc, fp, BODY)
 #undef BODY
     g_launches.fetch_add(1);

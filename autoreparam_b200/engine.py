@@ -81,7 +81,7 @@ def hmc_num_transitions(num_results, num_burnin_steps, num_steps_between_results
 def hmc_run(model, z0, eps0, a, b, *, num_leapfrog_steps, num_results, num_burnin_steps, num_adaptation_steps,
             num_steps_between_results=1, seed=0, chain_offset=0, target_accept_prob=0.75, ext_momenta=None,
             ext_log_u=None, want_samples=True, want_orig=False, want_final=True, engine=ENGINE_AUTO,
-            lanes_per_chain=0, precision="f32", out=None):
+            lanes_per_chain=0, precision="f32", out=None, stream_window=0, want_is_accepted=None):
     """Run every transition of every chain in one launch (``arp_hmc_run``).
 
     Host mode: numpy in, numpy out.  Device mode: ``z0`` is a torch.cuda tensor;
@@ -89,12 +89,16 @@ def hmc_run(model, z0, eps0, a, b, *, num_leapfrog_steps, num_results, num_burni
     ``is_accepted`` tensors to reuse across calls).
     Returns a dict: samples [S,C,D] (centred), samples_orig, is_accepted [S,C] uint8,
     final_z [C,D], step_mult [C], accept_count [C].
+    ``stream_window`` = W > 0 (SIMT engine): additionally stream_mean / stream_var / stream_ess [C,D] and
+    stream_truncated [C,D] int32 from in-kernel streaming statistics with a W-lag window -- combine with
+    ``want_samples=False`` for runs whose traces do not fit in memory.
     """
     lib = _lib.load(precision)
     dt = _lib.np_dtype(precision)
     D = model.num_coords
     cfg = _lib.HmcConfig(num_leapfrog_steps, num_results, num_burnin_steps, num_adaptation_steps,
-                         num_steps_between_results, seed, chain_offset, target_accept_prob, lanes_per_chain, engine)
+                         num_steps_between_results, seed, chain_offset, target_accept_prob, lanes_per_chain, engine,
+                         int(stream_window))
     T = lib.arp_hmc_num_transitions(C.byref(cfg))
     a_h, b_h = _np(a, dt), _np(b, dt)
     out = dict(out or {})
@@ -127,7 +131,7 @@ def hmc_run(model, z0, eps0, a, b, *, num_leapfrog_steps, num_results, num_burni
         assert tuple(lu.shape) == (T, Cn)
     if want_samples and "samples" not in out:
         out["samples"] = mk((S, Cn, D), tdt)
-    if want_samples and "is_accepted" not in out:
+    if (want_samples if want_is_accepted is None else want_is_accepted) and "is_accepted" not in out:
         out["is_accepted"] = mk((S, Cn), u8)
     if want_orig and "samples_orig" not in out:
         out["samples_orig"] = mk((S, Cn, D), tdt)
@@ -135,9 +139,14 @@ def hmc_run(model, z0, eps0, a, b, *, num_leapfrog_steps, num_results, num_burni
         out["final_z"] = mk((Cn, D), tdt)
     out["step_mult"] = mk((Cn,), tdt)
     out["accept_count"] = mk((Cn,), i32)
+    if stream_window > 0:
+        for k in ("stream_mean", "stream_var", "stream_ess"):
+            out[k] = mk((Cn, D), tdt)
+        out["stream_truncated"] = mk((Cn, D), i32)
     buf = _lib.HmcBuffers(_p(z0), _p(eps0), _p(mom), _p(lu), _p(out.get("samples")), _p(out.get("samples_orig")),
                           _p(out.get("is_accepted")), _p(out.get("final_z")), _p(out["step_mult"]),
-                          _p(out["accept_count"]))
+                          _p(out["accept_count"]), _p(out.get("stream_mean")), _p(out.get("stream_var")),
+                          _p(out.get("stream_ess")), _p(out.get("stream_truncated")))
     rc = lib.arp_hmc_run(model.handle(precision), C.byref(cfg), _p(a_h), _p(b_h), Cn, C.byref(buf), mem, st)
     _lib.check(lib, rc, "arp_hmc_run")
     out["num_transitions"] = int(T)
@@ -162,7 +171,7 @@ def hmc_run_many(model, z0, eps0_list, a, b, *, num_leapfrog_steps, num_results,
     cfgs = (_lib.HmcConfig * n)()
     for i in range(n):
         cfgs[i] = _lib.HmcConfig(int(Ls[i]), int(Ss[i]), int(Bs[i]), int(As[i]), num_steps_between_results, seed,
-                                 chain_offset, target_accept_prob, lanes_per_chain, engine)
+                                 chain_offset, target_accept_prob, lanes_per_chain, engine, 0)
     a_h, b_h = _np(a, dt), _np(b, dt)
     if _is_torch(z0):
         import torch
@@ -193,7 +202,7 @@ def hmc_run_many(model, z0, eps0_list, a, b, *, num_leapfrog_steps, num_results,
             o["samples"] = mk((int(Ss[i]), Cn, D), tdt)
             o["is_accepted"] = mk((int(Ss[i]), Cn), u8)
         bufs[i] = _lib.HmcBuffers(_p(z0), _p(eps), None, None, _p(o.get("samples")), None, _p(o.get("is_accepted")),
-                                  None, _p(o["step_mult"]), _p(o["accept_count"]))
+                                  None, _p(o["step_mult"]), _p(o["accept_count"]), None, None, None, None)
         o["num_transitions"] = hmc_num_transitions(int(Ss[i]), int(Bs[i]), num_steps_between_results)
         outs.append(o)
     rc = lib.arp_hmc_run_many(model.handle(precision), cfgs, n, _p(a_h), _p(b_h), Cn, bufs, mem, st)

@@ -49,7 +49,8 @@ def _flat_step_sizes(model_config, step_size_init):
 
 def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, num_leapfrog_steps, num_samples,
         num_burnin_steps, num_adaptation_steps, num_chains_to_save=0, seed=0, chain_offset=0, device="cuda",
-        engine_kind=engine.ENGINE_AUTO, precision="f32", keep_on_device=False, return_is_accepted=True):
+        engine_kind=engine.ENGINE_AUTO, precision="f32", keep_on_device=False, return_is_accepted=True,
+        stream_window=0):
     """HMC + dual-averaging adaptation + thinning + to-centred + ESS (``inference.py:198-242``).
 
     target            TargetGraph (graphs.py) -- carries the (a, b) rule, so ``reparam`` is accepted
@@ -58,6 +59,9 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
     initial_states    list of [C, *site] arrays (util.variational_inits_from_params) or flat [C, D]
     return_is_accepted  False: the [S, C] accept flags stay on the device (``is_accepted`` is None); their sum is in
                       ``accept_stats`` -- all the drop-in driver reads (main.py:372-373)
+    stream_window     W > 0: no [S, C, D] trace is stored; mean / variance / ESS come from in-kernel streaming
+                      statistics with a W-lag window (for runs whose traces do not fit: BASELINE configs[4]).
+                      ``num_chains_to_save`` must then be 0.
     """
     import torch
 
@@ -75,11 +79,20 @@ def hmc(target, model_config, step_size_init, initial_states, reparam=None, *, n
     z_pin = _pinned_like(torch.from_numpy(z_np), "z0")
     z_pin.copy_(torch.from_numpy(z_np))
     z_dev = z_pin.to(dev, non_blocking=True)
-    out = engine.hmc_run(mc, z_dev, eps0, target.a, target.b, num_leapfrog_steps=num_leapfrog_steps,
-                         num_results=num_samples, num_burnin_steps=num_burnin_steps,
-                         num_adaptation_steps=num_adaptation_steps, seed=seed, chain_offset=chain_offset,
-                         want_final=False, engine=engine_kind, precision=precision)
-    ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
+    if stream_window > 0:
+        assert num_chains_to_save == 0, "streaming statistics keep no traces"
+        out = engine.hmc_run(mc, z_dev, eps0, target.a, target.b, num_leapfrog_steps=num_leapfrog_steps,
+                             num_results=num_samples, num_burnin_steps=num_burnin_steps,
+                             num_adaptation_steps=num_adaptation_steps, seed=seed, chain_offset=chain_offset,
+                             want_final=False, engine=engine.ENGINE_SIMT, precision=precision, want_samples=False,
+                             want_is_accepted=True, stream_window=stream_window)
+        ess_dev, mean_dev, var_dev = out["stream_ess"], out["stream_mean"], out["stream_var"]
+    else:
+        out = engine.hmc_run(mc, z_dev, eps0, target.a, target.b, num_leapfrog_steps=num_leapfrog_steps,
+                             num_results=num_samples, num_burnin_steps=num_burnin_steps,
+                             num_adaptation_steps=num_adaptation_steps, seed=seed, chain_offset=chain_offset,
+                             want_final=False, engine=engine_kind, precision=precision)
+        ess_dev, mean_dev, var_dev = engine.ess(out["samples"], precision=precision, want_moments=True)
     # R-hat from the per-chain moments: [C, D] -> packed sums [3 D + 1] on the device, summed over the ranks (one small
     # NCCL all-reduce when the chains are sharded over several GPUs), -> [D].  Accept counters ride in a second
     # 3-element all-reduce.  These are the only collectives of an HMC run.

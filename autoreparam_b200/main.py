@@ -59,6 +59,9 @@ def build_parser():
     a("--seed", type=int, default=0, help="Philox / initialisation seed (the reference is unseeded).")
     a("--data_dir", default=None, help="Directory holding the reference's data files (default ./data/).")
     a("--precision", default="f32", choices=["f32", "f64"])
+    a("--stream_window", type=int, default=0,
+      help="W > 0: keep no [S, C, D] trace; ESS / R-hat from in-kernel streaming statistics with a W-lag window "
+           "(chain counts whose traces do not fit in memory).")
     a("--tied_b_as_written", type=_bool, nargs="?", const=True, default=True,
       help="True: tied VIP uses b = 1 as the reference does as written; False: the paper's b = a.")
     return p
@@ -274,7 +277,7 @@ def run_hmc(FLAGS, model_config, results_dir, file_path, tuning=False):
                         num_leapfrog_steps=FLAGS.num_leapfrog_steps, num_samples=FLAGS.num_samples,
                         num_burnin_steps=FLAGS.num_burnin_steps, num_adaptation_steps=FLAGS.num_adaptation_steps,
                         num_chains_to_save=n_save, seed=FLAGS.seed, chain_offset=lo, device=device,
-                        precision=FLAGS.precision, return_is_accepted=False)
+                        precision=FLAGS.precision, return_is_accepted=False, stream_window=FLAGS.stream_window)
     ess_flat = distributed.gather_chains(res.ess_flat, device)            # [C, D] over all ranks
     n_accepted = res.accept_stats[0]     # accepted kept transitions of ALL ranks (all-reduced inside inference.hmc)
     samples = res.samples

@@ -119,6 +119,8 @@ typedef struct arp_hmc_config {
   double target_accept_prob;    /* 0.75 [TFP default] */
   int32_t lanes_per_chain;      /* 0 = auto; 1,8,32 = force */
   int32_t engine;               /* ARP_ENGINE_* */
+  int32_t stream_window;        /* W > 0: streaming statistics of the kept samples with a lag window of W lags (see
+                                   arp_hmc_buffers.stream_*); SIMT engine only */
 } arp_hmc_config;
 
 /* Buffers of one HMC run.  `mem` applies to every non-NULL pointer here.
@@ -132,6 +134,7 @@ typedef struct arp_hmc_config {
  *   final_z       [C,D]  out  optional final state
  *   step_mult     [C]    out  optional final per-chain step-size multiplier (eps = eps0 * mult)
  *   accept_count  [C]    out  optional number of accepted transitions per chain (all transitions)
+ *   stream_*      [C,D]  out  optional streaming statistics, see below
  */
 typedef struct arp_hmc_buffers {
   const arp_real* z0;
@@ -144,6 +147,14 @@ typedef struct arp_hmc_buffers {
   arp_real* final_z;
   arp_real* step_mult;
   int32_t* accept_count;
+  /* streaming statistics (cfg.stream_window = W > 0; each pointer optional), for runs whose [S,C,D] traces cannot be
+   * stored (BASELINE configs[4]: 65 536 chains x 10 003 coordinates): the kernel keeps, per (chain, coordinate), a ring
+   * of the last W kept values and W lag-product sums instead of the trace -- (3 W + 2) floats instead of S. */
+  arp_real* stream_mean;      /* [C,D] out  mean of the kept centred samples */
+  arp_real* stream_var;       /* [C,D] out  their biased variance */
+  arp_real* stream_ess;       /* [C,D] out  ESS (same estimator as arp_ess) from the lags inside the window */
+  int32_t* stream_truncated;  /* [C,D] out  1 where no negative autocorrelation appeared inside the window: the ESS then
+                                 uses all W lags and is an upper bound */
 } arp_hmc_buffers;
 
 /* total transitions of a run: 1 + burnin + (1+between)*(S-1)  [TFP sample_chain] */

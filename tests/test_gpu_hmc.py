@@ -155,3 +155,36 @@ def test_tuning_grid_in_one_launch_equals_separate_runs(model, eng):
         assert np.array_equal(many[i]["accept_count"], one["accept_count"]), L
         assert many[i]["num_transitions"] == one["num_transitions"]
     assert many[1]["is_accepted"].mean() > 0.2
+
+
+@pytest.mark.parametrize("model,lpc", [("8schools", 1), ("radon", 8), ("time_series", 1), ("election", 32)])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_streaming_statistics_match_stored_trace(model, lpc, precision):
+    """In-kernel streaming mean / variance / windowed ESS (for runs whose traces do not fit, BASELINE configs[4])
+    against the same run's stored trace: moments to round-off; ESS equal to arp_ess wherever the first negative
+    autocorrelation lies inside the window, flagged as truncated (and an upper bound) elsewhere."""
+    C, L, S = 37, 3, 400
+    W = 48 if model != "time_series" else 256     # the local-linear-trend chains mix slowly: wider window
+    mc = common.model_config(model)
+    D = mc.num_coords
+    a, b = common.ab_for("NCP" if model != "time_series" else "CP", D)
+    z0 = common.random_states(model, D, C, seed=8, scale=0.3)
+    eps0 = np.full(D, 0.02 if model != "time_series" else 1e-4)
+    out = engine.hmc_run(mc, z0, eps0, a, b, num_leapfrog_steps=L, num_results=S, num_burnin_steps=50,
+                         num_adaptation_steps=40, seed=4, engine=engine.ENGINE_SIMT, lanes_per_chain=lpc,
+                         precision=precision, stream_window=W)
+    x = out["samples"].astype(np.float64)
+    tol = 2e-4 if precision == "f32" else 1e-9
+    assert np.abs(out["stream_mean"] - x.mean(0)).max() < tol * (1 + np.abs(x).max())
+    v = x.var(0)
+    okv = v > 1e-12 * (1 + np.abs(x).max() ** 2)
+    assert np.abs(out["stream_var"][okv] / v[okv] - 1).max() < 50 * tol
+    ref = engine.ess(out["samples"], precision=precision)
+    tr = out["stream_truncated"].astype(bool)
+    good = ~tr & np.isfinite(ref) & okv
+    assert good.mean() > (0.3 if model != "time_series" else 0.02), good.mean()   # the window resolves a share of the series
+    etol = 5e-3 if precision == "f32" else 1e-6
+    assert np.abs(out["stream_ess"][good] / ref[good] - 1).max() < etol, np.abs(out["stream_ess"][good] / ref[good] - 1).max()
+    if tr.any():                                    # truncated window: upper bound
+        sel = tr & np.isfinite(ref)
+        assert (out["stream_ess"][sel] >= ref[sel] * (1 - 1e-3)).all()
