@@ -74,59 +74,69 @@ struct Vec {
 //   prior term   N(z ; a*mu, sigma^b)           (program_transformations.py:569-572)
 //   centred      x = mu + sigma^(1-b) (z - a mu) (:574-576,600)
 // `ls` is log(sigma).  CP is a=b=1, NCP a=b=0.
-struct Site {
-  real x;    // centred value
-  real r;    // sigma^(1-b)
-  real usb;  // u / sigma^b  with u = (z - a mu) / sigma^b
-  real dz;   // z - a mu
+// The scalar type is a template parameter: every model works in `real`; the time-series scans run their site
+// arithmetic in double even in the fp32 build (see vg_time_series).
+template <typename T>
+struct SiteT {
+  T x;    // centred value
+  T r;    // sigma^(1-b)
+  T usb;  // u / sigma^b  with u = (z - a mu) / sigma^b
+  T dz;   // z - a mu
 };
+typedef SiteT<real> Site;
 
-__device__ __forceinline__ Site site_fwd(real z, real mu, real ls, real a, real b, real& lp) {
-  Site s;
-  real sb_inv;
-  if (b == (real)1) {
+#define ARP_HALF_LOG_2PI_D 0.91893853320467274178
+
+template <typename T>
+__device__ __forceinline__ SiteT<T> site_fwd(T z, T mu, T ls, T a, T b, T& lp) {
+  SiteT<T> s;
+  T sb_inv;
+  if (b == (T)1) {
     sb_inv = r_exp(-ls);
-    s.r = (real)1;
-  } else if (b == (real)0) {
-    sb_inv = (real)1;
+    s.r = (T)1;
+  } else if (b == (T)0) {
+    sb_inv = (T)1;
     s.r = r_exp(ls);
   } else {
     sb_inv = r_exp(-b * ls);
-    s.r = r_exp(((real)1 - b) * ls);
+    s.r = r_exp(((T)1 - b) * ls);
   }
   s.dz = z - a * mu;
-  real u = s.dz * sb_inv;
+  T u = s.dz * sb_inv;
   s.usb = u * sb_inv;
   s.x = mu + s.r * s.dz;
-  lp += (real)-0.5 * u * u - b * ls - ARP_HALF_LOG_2PI;
+  lp += (T)-0.5 * u * u - b * ls - (T)ARP_HALF_LOG_2PI_D;
   return s;
 }
 
 // sigma == 1 (ls == 0): sigma^b = 1 for every b.
-__device__ __forceinline__ Site site_fwd_unit(real z, real mu, real a, real& lp) {
-  Site s;
-  s.r = (real)1;
+template <typename T>
+__device__ __forceinline__ SiteT<T> site_fwd_unit(T z, T mu, T a, T& lp) {
+  SiteT<T> s;
+  s.r = (T)1;
   s.dz = z - a * mu;
   s.usb = s.dz;
   s.x = mu + s.dz;
-  lp += (real)-0.5 * s.dz * s.dz - ARP_HALF_LOG_2PI;
+  lp += (T)-0.5 * s.dz * s.dz - (T)ARP_HALF_LOG_2PI_D;
   return s;
 }
 
 // Reverse sweep of one site, with d/d(log sigma)
 // instead of d/d(sigma):  lsbar = xbar dz (1-b) r + (u^2 - 1) b.
-__device__ __forceinline__ void site_rev(const Site& s, real xbar, real mu, real a, real b,
-                                         real& zbar, real& mubar, real& lsbar, real& abar) {
+template <typename T>
+__device__ __forceinline__ void site_rev(const SiteT<T>& s, T xbar, T mu, T a, T b,
+                                         T& zbar, T& mubar, T& lsbar, T& abar) {
   zbar = xbar * s.r - s.usb;
-  mubar = xbar * ((real)1 - s.r * a) + a * s.usb;
-  lsbar = xbar * s.dz * ((real)1 - b) * s.r + (s.usb * s.dz - (real)1) * b;
+  mubar = xbar * ((T)1 - s.r * a) + a * s.usb;
+  lsbar = xbar * s.dz * ((T)1 - b) * s.r + (s.usb * s.dz - (T)1) * b;
   abar = mu * (s.usb - xbar * s.r);
 }
 
 // d log_joint / d b of one site: ln(sigma) [(u^2 - 1) - xbar (z - a mu) sigma^(1-b)].
 // Needed only when b is learned (untied VIP, or the paper's tied b = a): program_transformations.py:512-523.
-__device__ __forceinline__ real site_bbar(const Site& s, real xbar, real ls) {
-  return ls * ((s.usb * s.dz - (real)1) - xbar * s.dz * s.r);
+template <typename T>
+__device__ __forceinline__ T site_bbar(const SiteT<T>& s, T xbar, T ls) {
+  return ls * ((s.usb * s.dz - (T)1) - xbar * s.dz * s.r);
 }
 
 // --------------------------------------------------------------- Philox ---

@@ -136,7 +136,7 @@ k_hmc_init(DevModel m, HmcWs ws, HmcArgs p, const real* z0) {
 
 template <int KIND, int LPC, int FP, bool MULTI = false>
 __global__ void __launch_bounds__(ARP_BLOCK)
-k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int smem_dpad) {
+k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = gtid / LPC;
   const int sub = gtid % LPC;
@@ -148,25 +148,33 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int smem_dpad) {
   Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
   Vec X{ws.x + co, ws.sd}, GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
   Vec V{ws.v + co, ws.sd};
-  // LPC > 1 and the seven state vectors of the block's chains fit in shared memory (smem_dpad > 0): the whole run
-  // works on a shared-memory copy (stride 1 per chain, as the [row][d] global layout) -- north_star's "one chain per
-  // warp, state on chip"; the global workspace is touched at the start and at the end only.
+  // The seven state vectors of the block's chains fit in shared memory (oc_dpad > 0): the whole run works on a
+  // shared-memory copy -- north_star's "state on chip"; the global workspace is touched at the start and at the end
+  // only.  LPC > 1: chain-major (stride 1 inside a vector, oc_stride floats between chains, chosen = LPC mod 32 so
+  // that the chains of a warp tile the 32 banks: with an arbitrary stride 70 % of the shared-memory wavefronts of the
+  // radon kernel were bank conflicts).  LPC = 1 (D small, e.g. 8schools): coordinate-major, thread t owns column t.
   extern __shared__ __align__(16) unsigned char hmc_smem_raw[];
-  const bool on_chip = LPC > 1 && smem_dpad > 0;
+  // (LPC = 1: compiled for 8schools only -- for time_series, D = 123, 64 on-chip chains per SM were no faster than the
+  // HBM-resident layout at full occupancy, and carrying both paths slowed the latter)
+  const bool on_chip = oc_dpad > 0 && (LPC > 1 || KIND == MODEL_8SCHOOLS);
   if (on_chip) {
-    real* base = reinterpret_cast<real*>(hmc_smem_raw) + (size_t)(threadIdx.x / LPC) * 7 * smem_dpad;
+    real* base;
+    int sd, vs;   // element stride, vector stride
+    if (LPC > 1) { base = reinterpret_cast<real*>(hmc_smem_raw) + (size_t)(threadIdx.x / LPC) * oc_stride; sd = 1; vs = oc_dpad; }
+    else { base = reinterpret_cast<real*>(hmc_smem_raw) + threadIdx.x; sd = (int)blockDim.x; vs = oc_dpad * (int)blockDim.x; }
     for (int d = sub; d < D; d += LPC) {
-      base[d] = Z(d); base[smem_dpad + d] = G(d); base[2 * smem_dpad + d] = XC(d);
+      base[d * sd] = Z(d); base[vs + d * sd] = G(d); base[2 * vs + d * sd] = XC(d);
     }
-    Z = Vec{base, 1}; G = Vec{base + smem_dpad, 1}; XC = Vec{base + 2 * smem_dpad, 1};
-    X = Vec{base + 3 * smem_dpad, 1}; GX = Vec{base + 4 * smem_dpad, 1}; XCX = Vec{base + 5 * smem_dpad, 1};
-    V = Vec{base + 6 * smem_dpad, 1};
+    Z = Vec{base, sd}; G = Vec{base + vs, sd}; XC = Vec{base + 2 * vs, sd};
+    X = Vec{base + 3 * vs, sd}; GX = Vec{base + 4 * vs, sd}; XCX = Vec{base + 5 * vs, sd};
+    V = Vec{base + 6 * vs, sd};
     __syncwarp();
   }
   const real* __restrict__ eps0 = ARP_RUN(eps0);
   real lp_cur = ws.lp[row], Hc = ws.H[row], lavg = ws.lavg[row], mult = ws.mult[row];
   int nacc = ws.nacc[row];
   const unsigned int gchain = p.chain_offset + (unsigned int)chain;
+  bool flipped = false;   // the current state lives in the proposal buffers (odd number of accepted proposals)
 
   for (int t = 0; t < ARP_RUN(T); ++t) {
     const int tg = p.t_begin + t;
@@ -196,28 +204,43 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int smem_dpad) {
       __syncwarp();
     }
     ke0 = group_sum<LPC>(ke0);
-    for (int d = sub; d < D; d += LPC) {
-      X(d) = Z(d);
-      GX(d) = G(d);
-    }
-    // ---- L leapfrog steps, two half kicks per step as TFP 0.7 does
+    // ---- L leapfrog steps, two half kicks per step as TFP 0.7 does (v += e g / 2 twice, each rounded separately).
+    // Sweeps over the state are what a large model pays for (state in HBM: 10^4 coordinates per chain), so they are
+    // fused: the first kick reads the CURRENT state directly (no copy into the proposal buffers), the second half
+    // kick of step l and the first of step l + 1 share one sweep, the last half kick only forms the kinetic energy,
+    // and an accepted proposal swaps the roles of the two buffer sets instead of being copied.
     real lpx = 0, ke1 = 0;
-    for (int l = 0; l < ARP_RUN(L); ++l) {
+    {
+#pragma unroll 4
       for (int d = sub; d < D; d += LPC) {
         const real e = ldg(eps0 + d) * mult;
-        const real v = V(d) + (real)0.5 * e * GX(d);
+        const real v = V(d) + (real)0.5 * e * G(d);
         V(d) = v;
-        X(d) = X(d) + e * v;
+        X(d) = Z(d) + e * v;
       }
+    }
+    for (int l = 0; l < ARP_RUN(L); ++l) {
       __syncwarp();
       const bool last = (l == ARP_RUN(L) - 1);
       lpx = vg<KIND, LPC, false, FP>(m, p.a, p.b, X, GX, XCX, Vec{nullptr, 1}, Vec{nullptr, 1}, sub, last);
       __syncwarp();
-      for (int d = sub; d < D; d += LPC) {
-        const real e = ldg(eps0 + d) * mult;
-        const real v = V(d) + (real)0.5 * e * GX(d);
-        V(d) = v;
-        if (last) ke1 = fma(v, v, ke1);
+      if (last) {
+#pragma unroll 4
+        for (int d = sub; d < D; d += LPC) {
+          const real e = ldg(eps0 + d) * mult;
+          const real v = V(d) + (real)0.5 * e * GX(d);
+          ke1 = fma(v, v, ke1);
+        }
+      } else {
+#pragma unroll 4
+        for (int d = sub; d < D; d += LPC) {
+          const real e = ldg(eps0 + d) * mult;
+          const real gx = GX(d);
+          real v = V(d) + (real)0.5 * e * gx;
+          v = v + (real)0.5 * e * gx;
+          V(d) = v;
+          X(d) = X(d) + e * v;
+        }
       }
     }
     ke1 = group_sum<LPC>(ke1);
@@ -228,12 +251,12 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int smem_dpad) {
     if (p.ext_log_u) log_u = p.ext_log_u[(size_t)tg * p.C + (valid ? chain : 0)];
     else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
     const bool acc = log_u < log_alpha;
-    if (acc) {
-      for (int d = sub; d < D; d += LPC) {
-        Z(d) = X(d);
-        G(d) = GX(d);
-        XC(d) = XCX(d);
-      }
+    if (acc) {   // the proposal's buffers become the current state (every lane of the chain takes the same decision)
+      Vec t;
+      t = Z; Z = X; X = t;
+      t = G; G = GX; GX = t;
+      t = XC; XC = XCX; XCX = t;
+      flipped = !flipped;
       lp_cur = lpx;
       ++nacc;
     }
@@ -281,9 +304,11 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int smem_dpad) {
     }
     __syncwarp();
   }
-  if (on_chip) {   // final state back to the workspace (final_z, and the contract that (z, g, xc) describe the chain)
+  if (on_chip || flipped) {   // final state back to (z, g, xc) of the workspace: final_z, and the contract that they describe the chain
+    __syncwarp();
     for (int d = sub; d < D; d += LPC) {
-      ws.z[co + (size_t)d * ws.sd] = Z(d); ws.g[co + (size_t)d * ws.sd] = G(d); ws.xc[co + (size_t)d * ws.sd] = XC(d);
+      const real zv = Z(d), gv = G(d), xv = XC(d);
+      ws.z[co + (size_t)d * ws.sd] = zv; ws.g[co + (size_t)d * ws.sd] = gv; ws.xc[co + (size_t)d * ws.sd] = xv;
     }
   }
   if (sub == 0) {

@@ -197,6 +197,11 @@ extern "C" void arp_model_destroy(arp_model* m) { delete m; }
 extern "C" int arp_model_num_coords(const arp_model* m) { return m ? m->dev.D : -1; }
 
 // ------------------------------------------------------------------ dispatch ---
+static int hmc_onchip_dpad(int kind, int lpc, int D, size_t* bytes, int* stride, int* block);
+
+// lanes per chain of the SIMT engine.  Measured on B200 (profiles/r02_simt.md): with the chain state in shared
+// memory, 8 lanes per chain beat one lane per chain at every chain count for the hierarchical models (radon 2.2e9 vs
+// 7.0e8 grad-evals/s at 131 072 chains); 8schools (D = 10) is fastest with one lane per chain once the chip is full.
 static int pick_lpc(const arp_model* m, long long C, int forced) {
 #ifdef ARP_DEV_GERMAN_ONLY
   return 1;
@@ -204,7 +209,9 @@ static int pick_lpc(const arp_model* m, long long C, int forced) {
   if (forced == 1 || forced == 8 || forced == 32) return forced;
   if (m->dev.kind == MODEL_TIME_SERIES) return 1;  // sequential scan: extra lanes would idle
   const long long target = 148LL * 4 * 32 * 4;      // ~4 warps per SM sub-partition
-  if (C >= target) return 1;
+  size_t b; int st, blk;
+  const bool onchip8 = hmc_onchip_dpad(m->dev.kind, 8, m->dev.D, &b, &st, &blk) > 0;
+  if (C >= target && !(onchip8 && m->dev.kind != MODEL_8SCHOOLS)) return 1;
   if (C * 8 >= target) return 8;
   return 32;
 }
@@ -240,18 +247,30 @@ static int pick_lpc(const arp_model* m, long long C, int forced) {
 
 static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
-// On-chip state of the SIMT HMC kernel: with LPC > 1 the block's ARP_BLOCK / LPC chains keep their seven state vectors
-// in shared memory when that fits in 96 KB (two blocks per SM).  Returns the padded row length (0 = use the global
-// workspace) and the dynamic shared-memory size.  ARP_HMC_ONCHIP=0 disables it (A/B measurements).
-static int hmc_onchip_dpad(int lpc, int D, size_t* bytes) {
-  *bytes = 0;
+// On-chip state of the SIMT HMC kernel: the block's chains keep their seven state vectors in shared memory when that
+// fits in 96 KB (two blocks per SM).  Returns the padded vector length (0 = use the global workspace), the stride
+// between chains (LPC > 1), the dynamic shared-memory size and the block size.  LPC = 1 (one thread per chain,
+// coordinate-major [7][D][block]) is compiled for 8schools only.  (Measured and not kept: time_series, D = 123, with
+// 32-thread blocks = 64 on-chip chains per SM: 2.67e8 grad-evals/s, the same as the HBM-resident layout at full
+// occupancy -- the sequential scan is latency-bound with two warps per SM.)  ARP_HMC_ONCHIP=0 disables it (A/B).
+static int hmc_onchip_dpad(int kind, int lpc, int D, size_t* bytes, int* stride, int* block) {
+  *bytes = 0; *stride = 0; *block = ARP_BLOCK;
   static const bool off = [] { const char* e = getenv("ARP_HMC_ONCHIP"); return e && e[0] == '0'; }();
-  if (lpc <= 1 || off) return 0;
-  const int dpad = (int)round_up(D, 4) + 1;          // + 1: the chains of a warp start in different banks
-  const size_t b = (size_t)(ARP_BLOCK / lpc) * 7 * dpad * sizeof(real);
+  if (off) return 0;
+  if (lpc > 1) {
+    const int dpad = (int)round_up(D, 4);
+    // chain stride = LPC (mod 32): the chains of a warp (32 / LPC of them) start LPC banks apart
+    *stride = (int)round_up(7 * dpad, 32) + (lpc < 32 ? lpc : 0);
+    const size_t b = (size_t)(ARP_BLOCK / lpc) * *stride * sizeof(real);
+    if (b > 96 * 1024) return 0;
+    *bytes = b;
+    return dpad;
+  }
+  if (kind != MODEL_8SCHOOLS) return 0;
+  const size_t b = (size_t)7 * D * ARP_BLOCK * sizeof(real);
   if (b > 96 * 1024) return 0;
   *bytes = b;
-  return dpad;
+  return D;
 }
 
 // copies `n` reals from a caller buffer (host or device) into a fresh device buffer
@@ -511,12 +530,14 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
     const DevModel dm = m->dev;
     const int fp = m->fp;
     size_t oc_bytes = 0;
-    const int oc_dpad = hmc_onchip_dpad(lpc, D, &oc_bytes);
+    int oc_stride = 0, oc_block = ARP_BLOCK;
+    const int oc_dpad = hmc_onchip_dpad(m->dev.kind, lpc, D, &oc_bytes, &oc_stride, &oc_block);
+    const dim3 grid_run((unsigned)(Cpad * lpc / oc_block)), block_run(oc_block);
 #define BODY(KIND, LPC, FP)                                                                                           \
     k_hmc_init<KIND, LPC, FP><<<grid, block, 0, st>>>(dm, ws, p, z0);                                                  \
     if (oc_bytes > 48 * 1024)                                                                                          \
       ARP_CUDA(cudaFuncSetAttribute(k_hmc_run<KIND, LPC, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_bytes)); \
-    k_hmc_run<KIND, LPC, FP><<<grid, block, oc_bytes, st>>>(dm, ws, p, oc_dpad);
+    k_hmc_run<KIND, LPC, FP><<<grid_run, block_run, oc_bytes, st>>>(dm, ws, p, oc_dpad, oc_stride);
     ARP_DISPATCH(dm.kind, lpc, fp, BODY)
 #undef BODY
     g_launches.fetch_add(1);
@@ -665,12 +686,14 @@ extern "C" int arp_hmc_run_many(arp_model* m, const arp_hmc_config* cfgs, int32_
     const DevModel dm = m->dev;
     const int fp = m->fp;
     size_t oc_bytes = 0;
-    const int oc_dpad = hmc_onchip_dpad(lpc, D, &oc_bytes);
+    int oc_stride = 0, oc_block = ARP_BLOCK;
+    const int oc_dpad = hmc_onchip_dpad(m->dev.kind, lpc, D, &oc_bytes, &oc_stride, &oc_block);
+    const dim3 grid_run((unsigned)(Cpad * lpc / oc_block)), block_run(oc_block);
 #define BODY(KIND, LPC, FP)                                                                                           \
     k_hmc_init<KIND, LPC, FP, true><<<grid, block, 0, st>>>(dm, ws, p, z0);                                            \
     if (oc_bytes > 48 * 1024)                                                                                          \
       ARP_CUDA(cudaFuncSetAttribute(k_hmc_run<KIND, LPC, FP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oc_bytes)); \
-    k_hmc_run<KIND, LPC, FP, true><<<grid, block, oc_bytes, st>>>(dm, ws, p, oc_dpad);
+    k_hmc_run<KIND, LPC, FP, true><<<grid_run, block_run, oc_bytes, st>>>(dm, ws, p, oc_dpad, oc_stride);
     ARP_DISPATCH(dm.kind, lpc, fp, BODY)
 #undef BODY
     g_launches.fetch_add(1);

@@ -467,74 +467,91 @@ __device__ real vg_electric(const DevModel& m, const real* a, const real* b,
 // scan for the centred values and reverse scan for the adjoints.  The scan is
 // sequential per chain: with LPC > 1 every lane runs it redundantly and lane 0
 // writes.
+// The scans run in DOUBLE in the fp32 build as well (state, gradient and centred values stay `real`): the level alpha_t
+// absorbs -beta * year (|beta * year| ~ 2e3 for the raw years 1959 .. 2018, models.py:1098-1113) against an observation
+// scale of 0.12, so one fp32 ulp of alpha_t is 1e-3 standard deviations of the residual and 60 accumulated roundings of
+// the level put the fp32 log-joint / gradient at 2e-4 of the fp64 oracle (round 1 waived the tolerance); with the
+// recurrences and the residual in double the fp32 build meets 1e-5.  ~2e3 flop per evaluation: the double rate is
+// irrelevant next to the state traffic.
 template <int LPC, bool WITH_A>
 __device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
                                Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
+  typedef double acc_t;
+  typedef SiteT<acc_t> SiteA;
   const int T = m.K;
   const int oBeta = 2 + 2 * T;
   const bool wr = (sub == 0);
-  real lp = 0;
-  Site s_sa = site_fwd_unit(z(0), (real)0, (*(a + 0)), lp);
-  Site s_sm = site_fwd_unit(z(1), (real)0, (*(a + 1)), lp);
-  Site s_be = site_fwd_unit(z(oBeta), (real)0, (*(a + oBeta)), lp);
-  const real sa = s_sa.x, sm = s_sm.x, be = s_be.x;
-  const real sig_a = r_softplus(sa), sig_m = r_softplus(sm);
-  const real lsa = r_log(sig_a), lsm = r_log(sig_m);
-  const real obs_sd = (real)0.12f;  // the reference's scale=0.12 is a float32 graph constant
-  const real inv_obs = (real)1 / obs_sd;
-  const real log_obs = r_log(obs_sd);
+  acc_t lp = 0;
+  auto A = [&](int i) { return (acc_t)(*(a + i)); };
+  auto B = [&](int i) { return (acc_t)(*(b + i)); };
+  SiteA s_sa = site_fwd_unit((acc_t)z(0), (acc_t)0, A(0), lp);
+  SiteA s_sm = site_fwd_unit((acc_t)z(1), (acc_t)0, A(1), lp);
+  SiteA s_be = site_fwd_unit((acc_t)z(oBeta), (acc_t)0, A(oBeta), lp);
+  const acc_t sa = s_sa.x, sm = s_sm.x, be = s_be.x;
+  const acc_t sig_a = r_softplus(sa), sig_m = r_softplus(sm);
+  const acc_t lsa = r_log(sig_a), lsm = r_log(sig_m);
+  const acc_t obs_sd = (acc_t)0.12f;  // the reference's scale=0.12 is a float32 graph constant
+  const acc_t inv_obs = (acc_t)1 / obs_sd;
+  const acc_t log_obs = r_log(obs_sd);
   // forward scan
-  real al_prev = 0, mu_prev = 0;
+  acc_t al_prev = 0, mu_prev = 0;
   for (int t = 0; t < T; ++t) {
     const int ia = 2 + 2 * t, im = 3 + 2 * t;
-    Site s_al = site_fwd(z(ia), al_prev + mu_prev, lsa, (*(a + ia)), (*(b + ia)), lp);
-    Site s_mu = site_fwd(z(im), mu_prev, lsm, (*(a + im)), (*(b + im)), lp);
-    if (wr) { xc(ia) = s_al.x; xc(im) = s_mu.x; }
+    SiteA s_al = site_fwd((acc_t)z(ia), al_prev + mu_prev, lsa, A(ia), B(ia), lp);
+    SiteA s_mu = site_fwd((acc_t)z(im), mu_prev, lsm, A(im), B(im), lp);
+    if (wr) {
+      // centred values as a two-term sum: the head is the `real` output, the tail is parked in the gradient slot of the
+      // same coordinate (free until the reverse scan reaches it) so that the reverse scan sees them in full precision
+      const real ah = (real)s_al.x, mh = (real)s_mu.x;
+      xc(ia) = ah; xc(im) = mh;
+      g(ia) = (real)(s_al.x - (acc_t)ah); g(im) = (real)(s_mu.x - (acc_t)mh);
+    }
     al_prev = s_al.x;
     mu_prev = s_mu.x;
-    const real e = (ldg(m.y + t) - s_al.x - be * ldg(m.x1 + t)) * inv_obs;
-    lp += (real)-0.5 * e * e - log_obs - ARP_HALF_LOG_2PI;
+    const acc_t e = ((acc_t)ldg(m.y + t) - s_al.x - be * (acc_t)ldg(m.x1 + t)) * inv_obs;
+    lp += (acc_t)-0.5 * e * e - log_obs - (acc_t)ARP_HALF_LOG_2PI_D;
   }
   __syncwarp();
   // reverse scan
-  real carry_al = 0, carry_mu = 0, acc_lsa = 0, acc_lsm = 0, acc_be = 0;
+  acc_t carry_al = 0, carry_mu = 0, acc_lsa = 0, acc_lsm = 0, acc_be = 0;
   for (int t = T - 1; t >= 0; --t) {
     const int ia = 2 + 2 * t, im = 3 + 2 * t;
-    const real alp = (t > 0) ? xc(ia - 2) : (real)0;
-    const real mup = (t > 0) ? xc(im - 2) : (real)0;
-    const real aa = (*(a + ia)), ba = (*(b + ia)), am = (*(a + im)), bm = (*(b + im));
-    real dummy = 0;
-    Site s_al = site_fwd(z(ia), alp + mup, lsa, aa, ba, dummy);
-    Site s_mu = site_fwd(z(im), mup, lsm, am, bm, dummy);
-    const real xt = ldg(m.x1 + t);
-    const real e = (ldg(m.y + t) - s_al.x - be * xt) * inv_obs;
-    const real lik = e * inv_obs;
+    const acc_t aa = A(ia), ba = B(ia), am = A(im), bm = B(im);
+    const acc_t alp = (t > 0) ? (acc_t)xc(ia - 2) + (acc_t)g(ia - 2) : (acc_t)0;
+    const acc_t mup = (t > 0) ? (acc_t)xc(im - 2) + (acc_t)g(im - 2) : (acc_t)0;
+    __syncwarp();   // LPC > 1: every lane has read these slots before lane 0 overwrites them in the next iteration
+    acc_t dummy = 0;
+    SiteA s_al = site_fwd((acc_t)z(ia), alp + mup, lsa, aa, ba, dummy);
+    SiteA s_mu = site_fwd((acc_t)z(im), mup, lsm, am, bm, dummy);
+    const acc_t xt = (acc_t)ldg(m.x1 + t);
+    const acc_t e = ((acc_t)ldg(m.y + t) - s_al.x - be * xt) * inv_obs;
+    const acc_t lik = e * inv_obs;
     acc_be = fma(lik, xt, acc_be);
-    real zb, mb_al, lb, ab;
+    acc_t zb, mb_al, lb, ab;
     site_rev(s_al, lik + carry_al, alp + mup, aa, ba, zb, mb_al, lb, ab);
-    if (wr) { g(ia) = zb; if (WITH_A) { abar(ia) = ab; bbar(ia) = site_bbar(s_al, lik + carry_al, lsa); } }
+    if (wr) { g(ia) = (real)zb; if (WITH_A) { abar(ia) = (real)ab; bbar(ia) = (real)site_bbar(s_al, lik + carry_al, lsa); } }
     acc_lsa += lb;
-    real mb_mu;
+    acc_t mb_mu;
     site_rev(s_mu, carry_mu, mup, am, bm, zb, mb_mu, lb, ab);
-    if (wr) { g(im) = zb; if (WITH_A) { abar(im) = ab; bbar(im) = site_bbar(s_mu, carry_mu, lsm); } }
+    if (wr) { g(im) = (real)zb; if (WITH_A) { abar(im) = (real)ab; bbar(im) = (real)site_bbar(s_mu, carry_mu, lsm); } }
     acc_lsm += lb;
     carry_al = mb_al;
     carry_mu = mb_al + mb_mu;
   }
   if (wr) {
-    real zb, mb, lb, ab;
+    acc_t zb, mb, lb, ab;
     // d log softplus(s) / d s = sigmoid(s) / softplus(s)
-    const real dsa = ((real)1 / ((real)1 + r_exp(-sa))) / sig_a;
-    const real dsm = ((real)1 / ((real)1 + r_exp(-sm))) / sig_m;
-    site_rev(s_sa, acc_lsa * dsa, (real)0, (*(a + 0)), (real)1, zb, mb, lb, ab);
-    g(0) = zb; xc(0) = sa;
-    site_rev(s_sm, acc_lsm * dsm, (real)0, (*(a + 1)), (real)1, zb, mb, lb, ab);
-    g(1) = zb; xc(1) = sm;
-    site_rev(s_be, acc_be, (real)0, (*(a + oBeta)), (real)1, zb, mb, lb, ab);
-    g(oBeta) = zb; xc(oBeta) = be;
+    const acc_t dsa = ((acc_t)1 / ((acc_t)1 + r_exp(-sa))) / sig_a;
+    const acc_t dsm = ((acc_t)1 / ((acc_t)1 + r_exp(-sm))) / sig_m;
+    site_rev(s_sa, acc_lsa * dsa, (acc_t)0, A(0), (acc_t)1, zb, mb, lb, ab);
+    g(0) = (real)zb; xc(0) = (real)sa;
+    site_rev(s_sm, acc_lsm * dsm, (acc_t)0, A(1), (acc_t)1, zb, mb, lb, ab);
+    g(1) = (real)zb; xc(1) = (real)sm;
+    site_rev(s_be, acc_be, (acc_t)0, A(oBeta), (acc_t)1, zb, mb, lb, ab);
+    g(oBeta) = (real)zb; xc(oBeta) = (real)be;
     if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(oBeta) = 0; bbar(0) = 0; bbar(1) = 0; bbar(oBeta) = 0; }
   }
-  return lp;
+  return (real)lp;
 }
 
 // ------------------------------------------------- centred -> rule (a, b) ---

@@ -6,9 +6,10 @@
 // N(loc, softplus(rho))) and the Adam loop of inference.find_best_learning_rate
 // (inference.py:26-154: TF1 Adam, lr/5 after 1/3 and lr/20 after 2/3 of the
 // steps, NaN gradients zeroed).  The reference crosses the host<->runtime
-// boundary once per step (sess.run, inference.py:93); here a CTA owns one
-// learning rate, a thread owns one Monte-Carlo sample, parameters and Adam
-// moments stay in shared memory, and nothing leaves the GPU until the end.
+// boundary once per step (sess.run, inference.py:93); here a cluster of 8 CTAs
+// owns one learning rate, 8 lanes own one Monte-Carlo sample, parameters, Adam
+// moments and per-sample vectors stay in shared memory, and nothing leaves the
+// GPU until the end.
 //
 // ELBO = mean_s [ log_joint(z_s) + sum_d (eps^2/2 + log scale_d + log(2 pi)/2) ],
 // z_s = loc + scale * eps_s; gradients of -ELBO:
@@ -70,14 +71,46 @@ __device__ __forceinline__ real discrete_prior_logp(real p, real& dlogp) {
   return r_log(mix);
 }
 
+// One learning rate = one thread-block CLUSTER of ARP_VI_NCTA CTAs (8 SMs): the S Monte-Carlo samples are dealt to the
+// CTAs, ARP_VI_LPC lanes cooperate on one sample (S = 256: 32 samples per CTA x 8 lanes = 256 threads), and the
+// per-sample state vectors live in shared memory.  Every CTA keeps its OWN copy of the parameters and Adam moments; per
+// step each CTA reduces the gradient over its samples into a partial block in its shared memory, one cluster barrier
+// later every CTA reads all partial blocks through distributed shared memory in the same (rank) order -- so all copies
+// take bit-identical Adam steps and nothing has to be broadcast.  The partial blocks are double-buffered by step
+// parity, which makes ONE cluster barrier per optimisation step sufficient.
+// (Round 1 ran one CTA per learning rate with one thread per sample: 5 of 148 SMs, every log-joint serial in a thread.)
+#define ARP_VI_NCTA 8
+#define ARP_VI_LPC 8
+#define ARP_VI_SPB (ARP_VI_BLOCK / ARP_VI_LPC)   // samples per CTA per pass
+
+__device__ __forceinline__ unsigned int vi_cluster_rank() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void vi_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// generic address of `p` (a shared-memory address of this CTA) in CTA `rank` of the cluster
+template <typename T>
+__device__ __forceinline__ const T* vi_map_rank(const T* p, unsigned int rank) {
+  uint64_t out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<uint64_t>(p)), "r"(rank));
+  return reinterpret_cast<const T*>(out);
+}
+
 template <int KIND, bool LEARN, int FP>
-__global__ void __launch_bounds__(ARP_VI_BLOCK)
-k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
-  extern __shared__ unsigned char smem_raw[];
+__global__ void __cluster_dims__(ARP_VI_NCTA, 1, 1) __launch_bounds__(ARP_VI_BLOCK)
+k_vi(DevModel m, ViArgs v, real* ws_all, int spc, int Dpad, int ws_in_smem) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   real* sm = reinterpret_cast<real*>(smem_raw);
-  const int D = v.D, S = v.S, P = v.P, nthr = blockDim.x;  // Spad = samples rounded up to a multiple of nthr
+  constexpr int LPC = ARP_VI_LPC, NCTA = ARP_VI_NCTA, nthr = ARP_VI_BLOCK;
+  const int D = v.D, S = v.S, P = v.P;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
-  const int run = blockIdx.x;
+  const int sub = tid % LPC, slot = tid / LPC;
+  const unsigned int crank = vi_cluster_rank();
+  const int run = blockIdx.x / NCTA;
+  // ---- shared memory: parameters, Adam moments, partial gradient blocks, (per-sample vectors)
   real* loc = sm;          real* rho = loc + D;    real* scale = rho + D;
   real* a_s = scale + D;   real* b_s = a_s + D;
   real* gl = b_s + D;      real* gs = gl + D;      real* ga = gs + D;   real* gb = ga + D;
@@ -85,9 +118,15 @@ k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
   real* up = mom + 4 * D;  // [P] unconstrained parameters; pv [P] values; gu [P] gradient sums; pm [2][P] Adam moments
   real* pv = up + P;       real* gu = pv + P;      real* pm = gu + P;
   real* red = pm + 2 * P;  // [32] block-reduction scratch
-  int* ia = reinterpret_cast<int*>(red + 32);
+  real* part = red + 32;   // [2][4 D + 4] this CTA's partial sums (loc, scale, a, b gradients; ELBO), by step parity
+  const int PB = 4 * D + 4;
+  int* ia = reinterpret_cast<int*>(part + 2 * PB);
   int* ib = ia + D;
-  real* ws = ws_all + (size_t)run * 6 * D * Spad;
+  real* wsm = reinterpret_cast<real*>(ib + D);   // [ARP_VI_SPB][6][Dpad] per-sample vectors of the current pass
+  real* ws_g = ws_all + (size_t)blockIdx.x * ARP_VI_SPB * 6 * Dpad;
+  real* wbase = (ws_in_smem ? wsm : ws_g) + (size_t)slot * 6 * Dpad;
+  Vec Z{wbase, 1}, G{wbase + Dpad, 1}, XC{wbase + 2 * Dpad, 1}, AB{wbase + 3 * Dpad, 1}, E{wbase + 4 * Dpad, 1},
+      BB{wbase + 5 * Dpad, 1};
   for (int d = tid; d < D; d += nthr) {
     loc[d] = v.loc[(size_t)run * D + d];
     rho[d] = v.rho[(size_t)run * D + d];
@@ -113,19 +152,19 @@ k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
         if (ia[d] >= 0) a_s[d] = pv[ia[d]];
         if (ib[d] >= 0) b_s[d] = pv[ib[d]];
       }
+      gl[d] = 0; gs[d] = 0; ga[d] = 0; gb[d] = 0;
     }
     __syncthreads();
-    // ---- reparameterised samples: thread tid owns samples tid, tid + nthr, ...
+    // ---- this CTA's samples crank * spc .. + spc, ARP_VI_SPB per pass, LPC lanes each
     real el = 0;
-    for (int smp = tid; smp < Spad; smp += nthr) {
-      const bool live = smp < S;
-      Vec Z{ws + smp, Spad}, G{ws + (size_t)D * Spad + smp, Spad}, XC{ws + (size_t)2 * D * Spad + smp, Spad};
-      Vec AB{ws + (size_t)3 * D * Spad + smp, Spad}, E{ws + (size_t)4 * D * Spad + smp, Spad};
-      Vec BB{ws + (size_t)5 * D * Spad + smp, Spad};
+    for (int s0 = 0; s0 < spc; s0 += ARP_VI_SPB) {
+      const int sl = s0 + slot;                       // sample index inside this CTA's share
+      const int smp = (int)crank * spc + sl;          // global sample index: keys the Philox stream
+      const bool live = sl < spc && smp < S;
       real ent = 0;
       if (v.ext_eps) {
         const real* e = v.ext_eps + ((size_t)step * S + (live ? smp : 0)) * D;
-        for (int d = 0; d < D; ++d) {
+        for (int d = sub; d < D; d += LPC) {
           const real ee = live ? e[d] : (real)0;
           E(d) = ee;
           Z(d) = loc[d] + scale[d] * ee;
@@ -133,7 +172,7 @@ k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
         }
       } else {
         const int nb = (D + 3) >> 2;
-        for (int j = 0; j < nb; ++j) {
+        for (int j = sub; j < nb; j += LPC) {
           real n4[4];
           philox_normal4(v.seed, (unsigned int)smp, (unsigned int)step, (unsigned int)j, ARP_STREAM_VI, n4);
 #pragma unroll
@@ -147,43 +186,60 @@ k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
           }
         }
       }
-      const real lp = vg<KIND, 1, LEARN, FP>(m, a_s, b_s, Z, G, XC, AB, BB, 0, true);
-      if (live) el += lp + ent;
+      ent = group_sum<LPC>(ent);
+      __syncwarp();
+      const real lp = vg<KIND, LPC, LEARN, FP>(m, a_s, b_s, Z, G, XC, AB, BB, sub, true);
+      if (live && sub == 0) el += lp + ent;
+      __syncthreads();   // G / E / AB / BB of the pass are visible to the block
+      // ---- gradient sums over the samples of this pass: one thread per coordinate, samples in slot order
+      for (int d = tid; d < D; d += nthr) {
+        const real* base = ws_in_smem ? wsm : ws_g;
+        const bool la = LEARN && ia[d] >= 0, lb = LEARN && ib[d] >= 0;
+        real s_l = 0, s_s = 0, s_a = 0, s_b = 0;
+        const int nlive = min(ARP_VI_SPB, min(spc - s0, S - ((int)crank * spc + s0)));
+        for (int q = 0; q < nlive; ++q) {
+          const real* w = base + (size_t)q * 6 * Dpad;
+          const real gg = w[Dpad + d];
+          s_l += gg;
+          s_s = fma(gg, w[4 * Dpad + d], s_s);
+          if (la) s_a += w[3 * Dpad + d];
+          if (lb) s_b += w[5 * Dpad + d];
+        }
+        gl[d] += s_l; gs[d] += s_s; ga[d] += s_a; gb[d] += s_b;
+      }
+      __syncthreads();
     }
-    // ---- ELBO: block sum
+    // ---- this CTA's partial block (step parity), then one cluster barrier
     el = group_sum<32>(el);
     if (lane == 0) red[warp] = el;
-    __syncthreads();  // also publishes G / E / AB / BB of every sample to the block
+    real* mine = part + (step & 1) * PB;
+    for (int d = tid; d < D; d += nthr) { mine[d] = gl[d]; mine[D + d] = gs[d]; mine[2 * D + d] = ga[d]; mine[3 * D + d] = gb[d]; }
+    __syncthreads();
     if (tid == 0) {
       real tot = 0;
       for (int w = 0; w < nwarp; ++w) tot += red[w];
+      mine[4 * D] = tot;
+    }
+    vi_cluster_sync();
+    // ---- totals: every CTA sums the NCTA partial blocks in rank order (identical results in every CTA)
+    for (int i = tid; i < 4 * D + 1; i += nthr) {
+      real tot = 0;
+#pragma unroll
+      for (unsigned int r = 0; r < NCTA; ++r) tot += vi_map_rank(mine, r)[i];
+      if (i < D) gl[i] = tot;
+      else if (i < 2 * D) gs[i - D] = tot;
+      else if (i < 3 * D) ga[i - 2 * D] = tot;
+      else if (i < 4 * D) gb[i - 3 * D] = tot;
+      else red[0] = tot;
+    }
+    __syncthreads();
+    if (tid == 0 && crank == 0) {
       real plp = 0;
       if (LEARN && v.discrete_prior)
         for (int p = 0; p < P; ++p) { real dl; plp += discrete_prior_logp(pv[p], dl); }
-      v.elbo[(size_t)run * v.steps + step] = tot / (real)S + plp;   // elbo_with_prior (inference.py:54)
+      v.elbo[(size_t)run * v.steps + step] = red[0] / (real)S + plp;   // elbo_with_prior (inference.py:54)
       if (v.prior_logp) v.prior_logp[(size_t)run * v.steps + step] = plp;
     }
-    // ---- gradient sums over the S samples: one warp per coordinate
-    for (int d = warp; d < D; d += nwarp) {
-      const real* gd = ws + (size_t)D * Spad + (size_t)d * Spad;
-      const real* ed = ws + (size_t)4 * D * Spad + (size_t)d * Spad;
-      const real* ad = ws + (size_t)3 * D * Spad + (size_t)d * Spad;
-      const real* bd = ws + (size_t)5 * D * Spad + (size_t)d * Spad;
-      const bool la = LEARN && ia[d] >= 0, lb = LEARN && ib[d] >= 0;
-      real s_l = 0, s_s = 0, s_a = 0, s_b = 0;
-      for (int s = lane; s < S; s += 32) {
-        const real gg = gd[s];
-        s_l += gg;
-        s_s = fma(gg, ed[s], s_s);
-        if (la) s_a += ad[s];
-        if (lb) s_b += bd[s];
-      }
-      s_l = group_sum<32>(s_l);
-      s_s = group_sum<32>(s_s);
-      if (LEARN) { s_a = group_sum<32>(s_a); s_b = group_sum<32>(s_b); }
-      if (lane == 0) { gl[d] = s_l; gs[d] = s_s; ga[d] = s_a; gb[d] = s_b; }
-    }
-    __syncthreads();
     if (LEARN) {
       // a parameter may be shared by several coordinates (untied: `a` has the shape of the site's loc, `b` of its
       // scale) and by a and b (tied b = a): sum the coordinate adjoints per slot, in coordinate order (deterministic)
@@ -220,32 +276,39 @@ k_vi(DevModel m, ViArgs v, real* ws_all, int Spad) {
       }
     __syncthreads();
   }
-  for (int d = tid; d < D; d += nthr) {
-    v.loc[(size_t)run * D + d] = loc[d];
-    v.rho[(size_t)run * D + d] = rho[d];
+  vi_cluster_sync();   // no CTA may exit while another still reads its partial block
+  if (crank == 0) {
+    for (int d = tid; d < D; d += nthr) {
+      v.loc[(size_t)run * D + d] = loc[d];
+      v.rho[(size_t)run * D + d] = rho[d];
+    }
+    if (LEARN)
+      for (int p = tid; p < P; p += nthr) v.u[(size_t)run * P + p] = up[p];
   }
-  if (LEARN)
-    for (int p = tid; p < P; p += nthr) v.u[(size_t)run * P + p] = up[p];
 }
 
 static inline int vi_launch(const DevModel& dm, int fp, const ViArgs& v, cudaStream_t st, DevBuf* ws,
                             std::atomic<long long>* launches, std::string* err) {
-  const int nthr = v.S >= ARP_VI_BLOCK ? ARP_VI_BLOCK : (v.S + 31) / 32 * 32;
-  const int Spad = (v.S + nthr - 1) / nthr * nthr;
-  const size_t ws_bytes = (size_t)v.R * 6 * v.D * Spad * sizeof(real);
+  const int spc = (v.S + ARP_VI_NCTA - 1) / ARP_VI_NCTA;             // samples per CTA
+  const int Dpad = (v.D + 3) / 4 * 4 + 1;                             // + 1: the samples of a warp start in different banks
+  const size_t fixed = (size_t)(13 * v.D + 5 * v.P + 32 + 2 * (4 * v.D + 4)) * sizeof(real) + (size_t)2 * v.D * sizeof(int);
+  const size_t wsb = (size_t)ARP_VI_SPB * 6 * Dpad * sizeof(real);
+  const int ws_in_smem = fixed + wsb <= 200 * 1024;
+  const size_t smem = fixed + (ws_in_smem ? wsb : 0);
+  if (smem > 200 * 1024) { *err = "vi: model too large for the shared-memory parameter block"; return 1; }
+  const size_t ws_bytes = ws_in_smem ? 256 : (size_t)v.R * ARP_VI_NCTA * wsb;
   cudaError_t e = ws->alloc(ws_bytes);
   if (e != cudaSuccess) { *err = std::string("vi workspace: ") + cudaGetErrorString(e); return 1; }
   cudaMemsetAsync(ws->p, 0, ws_bytes, st);
-  const size_t smem = (size_t)(13 * v.D + 5 * v.P + 32) * sizeof(real) + (size_t)2 * v.D * sizeof(int);
-  if (smem > 200 * 1024) { *err = "vi: model too large for the shared-memory parameter block"; return 1; }
+  const dim3 grid((unsigned)(v.R * ARP_VI_NCTA));
 #define ARP_VI_GO(KIND, FP)                                                                              \
   do {                                                                                                   \
     if (v.P > 0) {                                                                                       \
       cudaFuncSetAttribute(k_vi<KIND, true, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      k_vi<KIND, true, FP><<<v.R, nthr, smem, st>>>(dm, v, ws->as<real>(), Spad);                              \
+      k_vi<KIND, true, FP><<<grid, ARP_VI_BLOCK, smem, st>>>(dm, v, ws->as<real>(), spc, Dpad, ws_in_smem); \
     } else {                                                                                             \
       cudaFuncSetAttribute(k_vi<KIND, false, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      k_vi<KIND, false, FP><<<v.R, nthr, smem, st>>>(dm, v, ws->as<real>(), Spad);                             \
+      k_vi<KIND, false, FP><<<grid, ARP_VI_BLOCK, smem, st>>>(dm, v, ws->as<real>(), spc, Dpad, ws_in_smem); \
     }                                                                                                    \
   } while (0)
   switch (dm.kind) {

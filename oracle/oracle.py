@@ -832,3 +832,121 @@ def german_hmc_cpu(X, y, z0, eps0, L, T, a, b, seed=0, num_adapt=0):
             log_avg = eta * ls + (1 - eta) * log_avg
             mult = torch.exp(ls) if t1 < num_adapt else torch.exp(log_avg)
     return n_evals, z.numpy()
+
+
+# --------------------------------------------------------------------------- #
+# Batched CPU baseline for ANY model (float32, all cores): the model bodies above
+# (dense one-hot matmuls, as the reference writes them) vectorised over the chain
+# axis with torch.func.vmap -- the role pfor plays in inference.py:172-195 -- and
+# differentiated with autograd at every leapfrog step, as tf.gradients does.
+# --------------------------------------------------------------------------- #
+def _m_radon_gather(tr, d):
+    """models.py:826-837 with the county look-up as a gather (the dense one-hot of a 10^6 x 10^4 problem would be
+    4 x 10^10 floats; SURVEY.md 8d allows the gather variant for the CPU baseline)."""
+    dt = tr.dtype
+    u = torch.as_tensor(d["u"], dtype=dt)
+    x = torch.as_tensor(d["x"], dtype=dt)
+    y = torch.as_tensor(d["y"], dtype=dt)
+    county = torch.as_tensor(np.asarray(d["county"]), dtype=torch.int64)
+    J = u.shape[0]
+    mua = tr.site("mua", 0.0, 1.0)
+    b1 = tr.site("b1", 0.0, 1.0)
+    b2 = tr.site("b2", 0.0, 1.0)
+    m = tr.site("m", mua + u * b1, torch.ones(J, dtype=dt))
+    tr.add(normal_lp(y, m[county] + x * b2, torch.ones((), dtype=dt)).sum())
+
+
+def batched_value_and_grad(model, d, a, b, dtype=torch.float32, gather=False):
+    """Z [C, D] tensor -> (lp [C], grad [C, D]) for all chains at once."""
+    a_t = _as_flat(model, d, a, dtype, 1.0)
+    b_t = _as_flat(model, d, b, dtype, 1.0)
+    body = _m_radon_gather if (gather and model == "radon") else _BODIES[model]
+
+    def f(z):
+        tr = Tracer(_split(model, d, z, dtype), _split(model, d, a_t, dtype), _split(model, d, b_t, dtype), dtype)
+        body(tr, d)
+        return tr.lp
+
+    vg = torch.func.vmap(torch.func.grad_and_value(f))
+
+    def call(Z):
+        g, lp = vg(Z)
+        return lp, g
+    return call
+
+
+def hmc_cpu_batched(model, d, z0, eps0, L, T, a, b, seed=0, num_adapt=0, gather=False):
+    """float32 batched HMC of any model for the CPU baseline: returns (#grad evals, final z).  Same transition as
+    hmc_chain (TFP op order, per-chain dual averaging) with torch's own RNG."""
+    torch.manual_seed(seed)
+    vg = batched_value_and_grad(model, d, a, b, torch.float32, gather)
+    z = torch.as_tensor(np.asarray(z0), dtype=torch.float32)
+    eps = torch.as_tensor(np.asarray(eps0), dtype=torch.float32)[None, :]
+    C = z.shape[0]
+    lp, g = vg(z)
+    H, log_avg, mult = torch.zeros(C), torch.zeros(C), torch.ones(C)
+    n_evals = C
+    for t in range(T):
+        e = eps * mult[:, None]
+        v0 = torch.randn_like(z)
+        v, x, gx = v0.clone(), z.clone(), g.clone()
+        for _ in range(L):
+            v = v + 0.5 * e * gx
+            x = x + e * v
+            lpx, gx = vg(x)
+            v = v + 0.5 * e * gx
+        n_evals += C * L
+        la = lpx - lp + 0.5 * (v0 * v0).sum(1) - 0.5 * (v * v).sum(1)
+        la = torch.where(torch.isnan(la), torch.full_like(la, -float("inf")), la)
+        acc = torch.log(torch.rand(C)) < la
+        z = torch.where(acc[:, None], x, z)
+        g = torch.where(acc[:, None], gx, g)
+        lp = torch.where(acc, lpx, lp)
+        t1 = t + 1
+        if t1 <= num_adapt:
+            H = H + 0.75 - torch.exp(torch.clamp(la, max=0.0))
+            ls = math.log(10.0) - H * math.sqrt(t1) / ((t1 + 10.0) * 0.05)
+            eta = t1 ** -0.75
+            log_avg = eta * ls + (1 - eta) * log_avg
+            mult = torch.exp(ls) if t1 < num_adapt else torch.exp(log_avg)
+    return n_evals, z.numpy()
+
+
+def vi_cpu_batched(model, d, S, num_steps, lr, a, b, seed=0):
+    """float32 mean-field VI for the CPU baseline (fixed (a, b): CP / NCP / dVIP): the S Monte-Carlo samples of a
+    step evaluated as one batch, total-gradient estimator and TF1 Adam as in vi_run.  Returns the ELBO timeline."""
+    torch.manual_seed(seed)
+    dtype = torch.float32
+    D = num_coords(model, d)
+    a_t = _as_flat(model, d, a, dtype, 1.0)
+    b_t = _as_flat(model, d, b, dtype, 1.0)
+
+    def f(z):
+        tr = Tracer(_split(model, d, z, dtype), _split(model, d, a_t, dtype), _split(model, d, b_t, dtype), dtype)
+        _BODIES[model](tr, d)
+        return tr.lp
+
+    fb = torch.func.vmap(f)
+    loc = (0.01 * torch.randn(D)).requires_grad_(True)
+    rho = torch.full((D,), -2.0, requires_grad=True)
+    st = [(torch.zeros(D), torch.zeros(D)), (torch.zeros(D), torch.zeros(D))]
+    timeline = []
+    for step in range(num_steps):
+        eps = torch.randn(S, D)
+        scale = torch.nn.functional.softplus(rho)
+        z = loc + scale * eps
+        elbo = (fb(z) - normal_lp(z, loc, scale).sum(1)).mean()
+        grads = torch.autograd.grad(-elbo, [loc, rho])
+        timeline.append(float(elbo.detach()))
+        cur = lr_schedule(step, lr, num_steps)
+        with torch.no_grad():
+            for i, (p, g) in enumerate(zip((loc, rho), grads)):
+                g = torch.nan_to_num(g, nan=0.0)
+                m, v = st[i]
+                m = 0.9 * m + 0.1 * g
+                v = 0.999 * v + 0.001 * g * g
+                st[i] = (m, v)
+                t = step + 1
+                lr_t = cur * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+                p -= lr_t * m / (torch.sqrt(v) + 1e-8)
+    return np.array(timeline)

@@ -93,6 +93,30 @@ def test_vi_steps_match_oracle_fp64(model, method):
         assert np.abs(out["u"][0]).max() > 1e-3   # the parameterisation really moved
 
 
+@pytest.mark.parametrize("model,S", [("8schools", 20), ("8schools", 70), ("election", 37), ("radon", 300)])
+def test_vi_ragged_sample_counts_match_oracle_fp64(model, S):
+    """The cluster kernel deals the S Monte-Carlo samples to 8 CTAs x 32 sample slots: sample counts that leave CTAs
+    empty (S = 20: 3 per CTA, the last CTA idle), partly filled, or that need a second pass per CTA (S = 300: 38 per
+    CTA) give the same ELBO / Adam steps as the oracle."""
+    mc = common.model_config(model, "MN")
+    raw = common.raw_data(model, "MN")
+    D = mc.num_coords
+    steps, lr = 3, 0.05
+    rng = np.random.default_rng(23)
+    eps = rng.standard_normal((steps, S, D))
+    loc0 = 0.01 * rng.standard_normal(D)
+    rho0 = np.full(D, -2.0)
+    a, b, al0 = np.full(D, 0.5), np.ones(D), np.zeros(D)
+    ref = O.vi_run(model, raw, loc0, rho0, eps, lr, steps, a=a, b=b, a_logit0=al0)
+    out = engine.vi_run(mc, a, b, loc0[None], rho0[None], [lr], num_mc_samples=S, num_optimization_steps=steps,
+                        ext_eps=eps, precision="f64", u=al0[None], a_index=np.arange(D), b_index=np.full(D, -1),
+                        num_params=D)
+    assert np.abs(out["elbo"][0] / ref["elbo"] - 1).max() < 1e-8, np.abs(out["elbo"][0] / ref["elbo"] - 1).max()
+    assert np.abs(out["loc"][0] - ref["loc"]).max() < 1e-7
+    assert np.abs(out["rho"][0] - ref["rho"]).max() < 1e-7
+    assert np.abs(out["u"][0] - ref["a_logit"]).max() < 1e-7
+
+
 @pytest.mark.parametrize("model", ["8schools", "german_credit_lognormalcentered", "german_credit_gammascale", "election",
                                    "electric", "time_series", "radon_stddvs"])
 @pytest.mark.parametrize("mode", ["tied_b_eq_a", "untied", "untied_prior"])
