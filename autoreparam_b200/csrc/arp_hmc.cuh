@@ -145,9 +145,12 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
   const bool valid = chain < p.C;
   const int D = p.D;
   const size_t co = (size_t)row * ws.sc;
-  Vec Z{ws.z + co, ws.sd}, G{ws.g + co, ws.sd}, XC{ws.xc + co, ws.sd};
-  Vec X{ws.x + co, ws.sd}, GX{ws.gx + co, ws.sd}, XCX{ws.xcx + co, ws.sd};
-  Vec V{ws.v + co, ws.sd};
+  // The seven state vectors of a chain: z, g, xc (current state, its gradient and centred values), x, gx, xcx (the
+  // proposal's) and v, at Bv + k VS + d sd.  The two buffer sets swap roles when a proposal is accepted (`cur` = offset
+  // of the current set: 0 or 3 VS), so nothing is copied.
+  real* Bv = ws.z + co;
+  size_t VS = (size_t)(ws.g - ws.z);   // the host lays the seven vectors out at equal distances
+  int sd = ws.sd;
   // The seven state vectors of the block's chains fit in shared memory (oc_dpad > 0): the whole run works on a
   // shared-memory copy -- north_star's "state on chip"; the global workspace is touched at the start and at the end
   // only.  LPC > 1: chain-major (stride 1 inside a vector, oc_stride floats between chains, chosen = LPC mod 32 so
@@ -159,25 +162,28 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
   const bool on_chip = oc_dpad > 0 && (LPC > 1 || KIND == MODEL_8SCHOOLS);
   if (on_chip) {
     real* base;
-    int sd, vs;   // element stride, vector stride
-    if (LPC > 1) { base = reinterpret_cast<real*>(hmc_smem_raw) + (size_t)(threadIdx.x / LPC) * oc_stride; sd = 1; vs = oc_dpad; }
-    else { base = reinterpret_cast<real*>(hmc_smem_raw) + threadIdx.x; sd = (int)blockDim.x; vs = oc_dpad * (int)blockDim.x; }
+    int osd, vs;   // element stride, vector stride
+    if (LPC > 1) { base = reinterpret_cast<real*>(hmc_smem_raw) + (size_t)(threadIdx.x / LPC) * oc_stride; osd = 1; vs = oc_dpad; }
+    else { base = reinterpret_cast<real*>(hmc_smem_raw) + threadIdx.x; osd = (int)blockDim.x; vs = oc_dpad * (int)blockDim.x; }
     for (int d = sub; d < D; d += LPC) {
-      base[d * sd] = Z(d); base[vs + d * sd] = G(d); base[2 * vs + d * sd] = XC(d);
+      base[d * osd] = Bv[(size_t)d * sd]; base[vs + d * osd] = Bv[VS + (size_t)d * sd];
+      base[2 * vs + d * osd] = Bv[2 * VS + (size_t)d * sd];
     }
-    Z = Vec{base, sd}; G = Vec{base + vs, sd}; XC = Vec{base + 2 * vs, sd};
-    X = Vec{base + 3 * vs, sd}; GX = Vec{base + 4 * vs, sd}; XCX = Vec{base + 5 * vs, sd};
-    V = Vec{base + 6 * vs, sd};
+    Bv = base; VS = (size_t)vs; sd = osd;
     __syncwarp();
   }
+  size_t cur = 0;
+  const Vec V{Bv + 6 * VS, sd};
   const real* __restrict__ eps0 = ARP_RUN(eps0);
   real lp_cur = ws.lp[row], Hc = ws.H[row], lavg = ws.lavg[row], mult = ws.mult[row];
   int nacc = ws.nacc[row];
   const unsigned int gchain = p.chain_offset + (unsigned int)chain;
-  bool flipped = false;   // the current state lives in the proposal buffers (odd number of accepted proposals)
 
   for (int t = 0; t < ARP_RUN(T); ++t) {
     const int tg = p.t_begin + t;
+    const size_t oth = 3 * VS - cur;
+    const Vec Z{Bv + cur, sd}, G{Bv + VS + cur, sd}, XC{Bv + 2 * VS + cur, sd};
+    const Vec X{Bv + oth, sd}, GX{Bv + VS + oth, sd}, XCX{Bv + 2 * VS + oth, sd};
     // ---- momenta v0 ~ N(0, I); proposal starts at the current state
     real ke0 = 0;
     if (p.ext_momenta) {
@@ -251,12 +257,10 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
     if (p.ext_log_u) log_u = p.ext_log_u[(size_t)tg * p.C + (valid ? chain : 0)];
     else log_u = philox_log_uniform(p.seed, gchain, (unsigned int)tg);
     const bool acc = log_u < log_alpha;
-    if (acc) {   // the proposal's buffers become the current state (every lane of the chain takes the same decision)
-      Vec t;
-      t = Z; Z = X; X = t;
-      t = G; G = GX; GX = t;
-      t = XC; XC = XCX; XCX = t;
-      flipped = !flipped;
+    // an accepted proposal: its buffers become the current state (every lane of the chain takes the same decision)
+    const Vec Zc = acc ? X : Z, XCc = acc ? XCX : XC;
+    if (acc) {
+      cur = oth;
       lp_cur = lpx;
       ++nacc;
     }
@@ -276,15 +280,15 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
       const int s = since / p.stride;
       if (s < ARP_RUN(S)) {
         const size_t o = ((size_t)s * p.C + chain) * D;
-        if (ARP_RUN(samples)) for (int d = sub; d < D; d += LPC) ARP_RUN(samples)[o + d] = XC(d);
-        if (ARP_RUN(samples_orig)) for (int d = sub; d < D; d += LPC) ARP_RUN(samples_orig)[o + d] = Z(d);
+        if (ARP_RUN(samples)) for (int d = sub; d < D; d += LPC) ARP_RUN(samples)[o + d] = XCc(d);
+        if (ARP_RUN(samples_orig)) for (int d = sub; d < D; d += LPC) ARP_RUN(samples_orig)[o + d] = Zc(d);
         if (ARP_RUN(is_accepted) && sub == 0) ARP_RUN(is_accepted)[(size_t)s * p.C + chain] = acc ? 1 : 0;
         if (p.stream_W > 0) {
           const int W = p.stream_W, slot = s % W, kmax = s < W - 1 ? s : W - 1;
           const size_t plane = p.stream_plane;
           for (int d = sub; d < D; d += LPC) {
             const size_t e = (size_t)d * ws.sd + co;
-            const real xv = XC(d);
+            const real xv = XCc(d);
             real piv;
             if (s == 0) { piv = xv; p.stream_pivot[e] = xv; } else piv = p.stream_pivot[e];
             const real y = xv - piv;
@@ -304,10 +308,10 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
     }
     __syncwarp();
   }
-  if (on_chip || flipped) {   // final state back to (z, g, xc) of the workspace: final_z, and the contract that they describe the chain
+  if (on_chip || cur != 0) {   // final state back to (z, g, xc) of the workspace: final_z, and the contract that they describe the chain
     __syncwarp();
     for (int d = sub; d < D; d += LPC) {
-      const real zv = Z(d), gv = G(d), xv = XC(d);
+      const real zv = Bv[cur + (size_t)d * sd], gv = Bv[VS + cur + (size_t)d * sd], xv = Bv[2 * VS + cur + (size_t)d * sd];
       ws.z[co + (size_t)d * ws.sd] = zv; ws.g[co + (size_t)d * ws.sd] = gv; ws.xc[co + (size_t)d * ws.sd] = xv;
     }
   }

@@ -474,8 +474,8 @@ __device__ real vg_electric(const DevModel& m, const real* a, const real* b,
 // recurrences and the residual in double the fp32 build meets 1e-5.  ~2e3 flop per evaluation: the double rate is
 // irrelevant next to the state traffic.
 template <int LPC, bool WITH_A>
-__device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
-                               Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
+__device__ real vg_time_series_seq(const DevModel& m, const real* a, const real* b,
+                                   Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
   typedef double acc_t;
   typedef SiteT<acc_t> SiteA;
   const int T = m.K;
@@ -552,6 +552,159 @@ __device__ real vg_time_series(const DevModel& m, const real* a, const real* b,
     if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(oBeta) = 0; bbar(0) = 0; bbar(1) = 0; bbar(oBeta) = 0; }
   }
   return (real)lp;
+}
+
+// Lane-parallel evaluation (LPC > 1).  Under ANY rule (a, b) the centred values obey an AFFINE recurrence in the previous
+// centred values, because the scales do not depend on them: with r = sigma^(1 - b), c = 1 - r a, d = r z,
+//   alpha_t = c_a (alpha_{t-1} + mu_{t-1}) + d_a,      mu_t = c_m mu_{t-1} + d_m,
+// i.e. a map (alpha, mu) -> (p alpha + q mu + u, s mu + w), and such maps compose.  Lane `sub` owns K = ceil(T / LPC)
+// consecutive time steps: it composes its steps, an inclusive Hillis-Steele scan over the LPC lanes of the chain gives the
+// state entering every segment, and each lane then walks its own steps.  The adjoint carries obey the transposed
+// recurrence (ca' = c_a (lik + ca) + a_a usb_a,  cm' = ca' + c_m cm + a_m usb_m), scanned from the right the same way.
+// All of it in double (see above): 60 dependent steps become 2 K local steps + 2 log2(LPC) shuffle rounds.
+template <int LPC, bool WITH_A>
+__device__ real vg_time_series_par(const DevModel& m, const real* a, const real* b,
+                                   Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
+  typedef double acc_t;
+  typedef SiteT<acc_t> SiteA;
+  constexpr int KMAX = 64 / LPC;            // the caller guarantees T <= 64
+  constexpr unsigned FULL = 0xffffffffu;
+  const int T = m.K;
+  const int oBeta = 2 + 2 * T;
+  const int K = (T + LPC - 1) / LPC;
+  const int t0 = sub * K, t1 = (t0 + K < T) ? t0 + K : T;
+  auto A = [&](int i) { return (acc_t)(*(a + i)); };
+  auto B = [&](int i) { return (acc_t)(*(b + i)); };
+  acc_t lp_top = 0;
+  SiteA s_sa = site_fwd_unit((acc_t)z(0), (acc_t)0, A(0), lp_top);
+  SiteA s_sm = site_fwd_unit((acc_t)z(1), (acc_t)0, A(1), lp_top);
+  SiteA s_be = site_fwd_unit((acc_t)z(oBeta), (acc_t)0, A(oBeta), lp_top);
+  const acc_t sa = s_sa.x, sm = s_sm.x, be = s_be.x;
+  const acc_t sig_a = r_softplus(sa), sig_m = r_softplus(sm);
+  const acc_t lsa = r_log(sig_a), lsm = r_log(sig_m);
+  const acc_t obs_sd = (acc_t)0.12f;
+  const acc_t inv_obs = (acc_t)1 / obs_sd;
+  const acc_t log_obs = r_log(obs_sd);
+  auto rfac = [&](acc_t bb, acc_t ls, acc_t sig) {
+    return bb == (acc_t)1 ? (acc_t)1 : (bb == (acc_t)0 ? sig : r_exp(((acc_t)1 - bb) * ls));
+  };
+  // ---- 1. this lane's steps as one affine map (alpha, mu) -> (p alpha + q mu + u, s mu + w)
+  acc_t p = 1, q = 0, s = 1, u = 0, w = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int ia = 2 + 2 * t, im = 3 + 2 * t;
+    const acc_t ra = rfac(B(ia), lsa, sig_a), rm = rfac(B(im), lsm, sig_m);
+    const acc_t ca = (acc_t)1 - ra * A(ia), cm = (acc_t)1 - rm * A(im);
+    const acc_t da = ra * (acc_t)z(ia), dm = rm * (acc_t)z(im);
+    u = ca * (u + w) + da; q = ca * (q + s); p = ca * p;
+    w = cm * w + dm; s = cm * s;
+  }
+  // ---- 2. inclusive scan over the lanes of the chain: (mine) o (everything to my left)
+#pragma unroll
+  for (int o = 1; o < LPC; o <<= 1) {
+    const acc_t pE = __shfl_up_sync(FULL, p, o, LPC), qE = __shfl_up_sync(FULL, q, o, LPC);
+    const acc_t sE = __shfl_up_sync(FULL, s, o, LPC), uE = __shfl_up_sync(FULL, u, o, LPC);
+    const acc_t wE = __shfl_up_sync(FULL, w, o, LPC);
+    if (sub >= o) {
+      u = p * uE + q * wE + u; q = p * qE + q * sE; p = p * pE;
+      w = s * wE + w; s = s * sE;
+    }
+  }
+  acc_t al = __shfl_up_sync(FULL, u, 1, LPC), mu = __shfl_up_sync(FULL, w, 1, LPC);   // state entering my segment
+  if (sub == 0) { al = 0; mu = 0; }
+  // ---- 3. walk my steps: centred values, log-density terms, and the adjoint map of the segment
+  //         (ca, cm) -> (P ca + U, R ca + S cm + W), built left to right: F <- F o B_t (B_t is applied first)
+  acc_t m_al[KMAX], m_mu[KMAX];
+  acc_t P = 1, U = 0, R = 0, S = 1, W = 0;
+  acc_t lp = 0;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int t = t0 + k;
+    m_al[k] = 0; m_mu[k] = 0;
+    if (t < t1) {
+      const int ia = 2 + 2 * t, im = 3 + 2 * t;
+      const acc_t aa = A(ia), am = A(im);
+      m_al[k] = al + mu; m_mu[k] = mu;
+      SiteA s_al = site_fwd((acc_t)z(ia), m_al[k], lsa, aa, B(ia), lp);
+      SiteA s_mu = site_fwd((acc_t)z(im), m_mu[k], lsm, am, B(im), lp);
+      xc(ia) = (real)s_al.x; xc(im) = (real)s_mu.x;
+      al = s_al.x; mu = s_mu.x;
+      const acc_t e = ((acc_t)ldg(m.y + t) - al - be * (acc_t)ldg(m.x1 + t)) * inv_obs;
+      lp += (acc_t)-0.5 * e * e - log_obs - (acc_t)ARP_HALF_LOG_2PI_D;
+      const acc_t lik = e * inv_obs;
+      const acc_t c_al = (acc_t)1 - s_al.r * aa, c_mu = (acc_t)1 - s_mu.r * am;
+      const acc_t h_al = c_al * lik + aa * s_al.usb, h_mu = am * s_mu.usb;
+      W = R * h_al + S * (h_al + h_mu) + W; R = (R + S) * c_al; S = S * c_mu;
+      U = P * h_al + U; P = P * c_al;
+    }
+  }
+  // ---- 4. inclusive scan from the right: (mine) o (everything to my right, applied first)
+#pragma unroll
+  for (int o = 1; o < LPC; o <<= 1) {
+    const acc_t PE = __shfl_down_sync(FULL, P, o, LPC), UE = __shfl_down_sync(FULL, U, o, LPC);
+    const acc_t RE = __shfl_down_sync(FULL, R, o, LPC), SE = __shfl_down_sync(FULL, S, o, LPC);
+    const acc_t WE = __shfl_down_sync(FULL, W, o, LPC);
+    if (sub + o < LPC) {
+      W = R * UE + S * WE + W; R = R * PE + S * RE; S = S * SE;
+      U = P * UE + U; P = P * PE;
+    }
+  }
+  acc_t ca = __shfl_down_sync(FULL, U, 1, LPC), cm = __shfl_down_sync(FULL, W, 1, LPC);   // carries entering from the right
+  if (sub == LPC - 1) { ca = 0; cm = 0; }
+  // ---- 5. walk my steps backwards
+  acc_t acc_lsa = 0, acc_lsm = 0, acc_be = 0;
+#pragma unroll
+  for (int k = KMAX - 1; k >= 0; --k) {
+    const int t = t0 + k;
+    if (t < t1) {
+      const int ia = 2 + 2 * t, im = 3 + 2 * t;
+      const acc_t aa = A(ia), ba = B(ia), am = A(im), bm = B(im);
+      acc_t dummy = 0;
+      SiteA s_al = site_fwd((acc_t)z(ia), m_al[k], lsa, aa, ba, dummy);
+      SiteA s_mu = site_fwd((acc_t)z(im), m_mu[k], lsm, am, bm, dummy);
+      const acc_t xt = (acc_t)ldg(m.x1 + t);
+      const acc_t e = ((acc_t)ldg(m.y + t) - s_al.x - be * xt) * inv_obs;
+      const acc_t lik = e * inv_obs;
+      acc_be = fma(lik, xt, acc_be);
+      acc_t zb, mb_al, lb, ab;
+      site_rev(s_al, lik + ca, m_al[k], aa, ba, zb, mb_al, lb, ab);
+      g(ia) = (real)zb;
+      if (WITH_A) { abar(ia) = (real)ab; bbar(ia) = (real)site_bbar(s_al, lik + ca, lsa); }
+      acc_lsa += lb;
+      acc_t mb_mu;
+      site_rev(s_mu, cm, m_mu[k], am, bm, zb, mb_mu, lb, ab);
+      g(im) = (real)zb;
+      if (WITH_A) { abar(im) = (real)ab; bbar(im) = (real)site_bbar(s_mu, cm, lsm); }
+      acc_lsm += lb;
+      ca = mb_al;
+      cm = mb_al + mb_mu;
+    }
+  }
+  acc_lsa = group_sum<LPC>(acc_lsa);
+  acc_lsm = group_sum<LPC>(acc_lsm);
+  acc_be = group_sum<LPC>(acc_be);
+  lp = group_sum<LPC>(lp) + lp_top;
+  if (sub == 0) {
+    acc_t zb, mb, lb, ab;
+    const acc_t dsa = ((acc_t)1 / ((acc_t)1 + r_exp(-sa))) / sig_a;
+    const acc_t dsm = ((acc_t)1 / ((acc_t)1 + r_exp(-sm))) / sig_m;
+    site_rev(s_sa, acc_lsa * dsa, (acc_t)0, A(0), (acc_t)1, zb, mb, lb, ab);
+    g(0) = (real)zb; xc(0) = (real)sa;
+    site_rev(s_sm, acc_lsm * dsm, (acc_t)0, A(1), (acc_t)1, zb, mb, lb, ab);
+    g(1) = (real)zb; xc(1) = (real)sm;
+    site_rev(s_be, acc_be, (acc_t)0, A(oBeta), (acc_t)1, zb, mb, lb, ab);
+    g(oBeta) = (real)zb; xc(oBeta) = (real)be;
+    if (WITH_A) { abar(0) = 0; abar(1) = 0; abar(oBeta) = 0; bbar(0) = 0; bbar(1) = 0; bbar(oBeta) = 0; }
+  }
+  return (real)lp;
+}
+
+template <int LPC, bool WITH_A>
+__device__ __forceinline__ real vg_time_series(const DevModel& m, const real* a, const real* b,
+                                               Vec z, Vec g, Vec xc, Vec abar, Vec bbar, int sub, bool want_lp) {
+  if constexpr (LPC > 1) {
+    if (m.K <= 64) return vg_time_series_par<LPC, WITH_A>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
+  }
+  return vg_time_series_seq<LPC, WITH_A>(m, a, b, z, g, xc, abar, bbar, sub, want_lp);
 }
 
 // ------------------------------------------------- centred -> rule (a, b) ---

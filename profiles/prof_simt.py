@@ -46,8 +46,6 @@ if __name__ == "__main__":
             for lpc in (1, 8, 32):
                 if C * lpc > 1048576 * 8:
                     continue
-                if model == "time_series" and lpc != 1:
-                    continue
                 try:
                     r, ms, acc = run(model, C, lpc, S=10 if C > 100000 else 20, burn=10 if C > 100000 else 20)
                     print("%-14s C %8d lpc %2d: %.3e grad-evals/s  (%.2f ms, accept %.2f)" % (model, C, lpc, r, ms, acc), flush=True)

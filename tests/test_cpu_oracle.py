@@ -146,3 +146,36 @@ def test_oracle_hmc_samples_8schools_posterior():
     # CP mixes poorly in the funnel (the point of the paper), so it only gets a loose bound here
     assert abs(out["CP"].mean() - out["NCP"].mean()) < 3.5
     assert 3.0 < out["NCP"].mean() < 6.0   # posterior mean of mu for eight schools is about 4.4
+
+
+@pytest.mark.parametrize("model", ["8schools", "radon", "election", "electric", "time_series"])
+def test_batched_cpu_baseline_equals_per_chain_oracle(model):
+    """The CPU-baseline leg of bench.py (model bodies vectorised over chains with vmap, autograd gradient) evaluates
+    the same function as the per-chain oracle the parity tests use."""
+    import torch
+    raw = common.raw_data(model)
+    D = O.num_coords(model, raw)
+    a, b = common.ab_for("VIP_ab", D)
+    Z = common.random_states(model, D, 5, seed=2)
+    lp_ref, g_ref = O.log_joint_and_grad(model, raw, Z, a, b)
+    lp, g = O.batched_value_and_grad(model, raw, a, b, torch.float64)(torch.as_tensor(Z))
+    assert np.abs(lp.numpy() - lp_ref).max() < 1e-9 * np.abs(lp_ref).max()
+    assert common.rel_err(g.numpy(), g_ref).max() < 1e-10
+
+
+def test_batched_cpu_baseline_gather_variant_and_samplers():
+    """County look-up as a gather (the variant used for the 10^6 x 10^4 synthetic radon) == the dense one-hot body;
+    the batched HMC / VI baselines run and do what they claim (accepting sampler, improving ELBO)."""
+    import torch
+    from autoreparam_b200 import data
+    raw = data.synthetic_radon(n=3000, j=40, seed=3)
+    D = 43
+    Z = 0.2 * np.random.default_rng(0).standard_normal((4, D))
+    lp1, g1 = O.batched_value_and_grad("radon", raw, 0.0, 0.0, torch.float64, gather=True)(torch.as_tensor(Z))
+    lp2, g2 = O.log_joint_and_grad("radon", raw, Z, 0.0, 0.0)
+    assert np.abs(lp1.numpy() - lp2).max() < 1e-9 * np.abs(lp2).max() and np.abs(g1.numpy() - g2).max() < 1e-8
+    n, z = O.hmc_cpu_batched("radon", raw, Z.astype(np.float32), np.full(D, 0.01), 3, 6, 0.0, 0.0, num_adapt=6,
+                             gather=True)
+    assert n == 4 + 4 * 3 * 6 and np.isfinite(z).all() and np.abs(z - Z).max() > 0      # chains moved
+    tl = O.vi_cpu_batched("8schools", common.raw_data("8schools"), 64, 60, 0.1, 0.0, 0.0)
+    assert np.isfinite(tl).all() and tl[-10:].mean() > tl[:5].mean()

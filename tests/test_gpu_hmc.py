@@ -69,7 +69,7 @@ def test_fixed_momenta_trajectory_fp32(model, method, eps):
         # an accept decision may legitimately flip only if log_alpha is within fp32 noise of log_u
         same = out["is_accepted"].astype(bool) == ref["is_accepted"]
         assert same.all(), (lpc, np.argwhere(~same))
-        tol = {"time_series": 5e-3, "german_credit_gammascale": 2e-2}.get(model, 2e-4)  # exp(10 z0 + v) amplifies fp32 round-off
+        tol = {"time_series": 5e-4, "german_credit_gammascale": 2e-2}.get(model, 2e-4)  # exp(10 z0 + v) amplifies fp32 round-off
         err = common.rel_err(out["samples"].reshape(S * C, D), ref["samples_centered"].reshape(S * C, D)).max()
         assert err < tol, (lpc, err)
 

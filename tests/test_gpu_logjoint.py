@@ -15,9 +15,10 @@ pytestmark = pytest.mark.gpu
 
 METHODS = ["CP", "NCP", "VIP_a", "VIP_ab"]
 TOL = {"f32": 1e-5, "f64": 1e-10}
-# time_series: be * year (~1e3) against an observation scale of 0.12 amplifies fp32 rounding of the
-# residual by ~1e4 (SURVEY.md appendix B note ii); the fp64 build is the arbiter for that model.
-TOL_F32_OVERRIDE = {"time_series": 2e-4}
+# (Round 1 waived time_series to 2e-4: be * year (~1e3) against an observation scale of 0.12 amplifies fp32 rounding of
+# the residual by ~1e4, SURVEY.md appendix B note ii.  Its scans now run in double inside the fp32 build and it meets
+# the same 1e-5 as every other model.)
+TOL_F32_OVERRIDE = {}
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])

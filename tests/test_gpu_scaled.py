@@ -78,7 +78,7 @@ def test_time_series_many_chains():
     z = np.tile(z_small, (C // 8, 1))
     lp, g, xc = engine.log_joint_grad(mc, z, a, b)
     lp_ref, g_ref = O.log_joint_and_grad("time_series", raw, z_small.astype(np.float64), a, b)
-    assert common.rel_err(lp[:8], lp_ref).max() < 2e-4 and common.rel_err(g[:8], g_ref).max() < 2e-4
+    assert common.rel_err(lp[:8], lp_ref).max() < 1e-5 and common.rel_err(g[:8], g_ref).max() < 1e-5
     assert np.array_equal(lp[:8], lp[-8:]) and np.array_equal(g[:8], g[-8:])      # periodic input, periodic output
     out = engine.hmc_run(mc, z, np.full(D, 2e-4), a, b, num_leapfrog_steps=4, num_results=4, num_burnin_steps=20,
                          num_adaptation_steps=10, seed=6, want_samples=True)
