@@ -134,8 +134,20 @@ k_hmc_init(DevModel m, HmcWs ws, HmcArgs p, const real* z0) {
   }
 }
 
+// Resident blocks per SM ptxas is asked to make room for (register budget = 65536 / (128 threads x blocks)).  Left to
+// itself ptxas gave the radon kernels 80 or 128 registers and the electric kernel 168 or 240 depending on unrelated
+// details of the surrounding code (measured: radon_synth 3.5e6 vs 2.75e6 grad-evals/s, electric 6.7e8 vs 5.3e8), so the
+// occupancy each model needs is stated: six blocks for the light models (HBM-resident or 32 KB of shared-memory
+// state per block), three for electric / time_series.
+template <int KIND, int LPC>
+constexpr int hmc_min_blocks() {
+  return (KIND == MODEL_8SCHOOLS || KIND == MODEL_RADON || KIND == MODEL_RADON_STDDVS) ? 6
+       : (KIND == MODEL_ELECTION) ? 4
+       : (KIND == MODEL_ELECTRIC || KIND == MODEL_TIME_SERIES) ? 3 : 1;
+}
+
 template <int KIND, int LPC, int FP, bool MULTI = false>
-__global__ void __launch_bounds__(ARP_BLOCK)
+__global__ void __launch_bounds__(ARP_BLOCK, hmc_min_blocks<KIND, LPC>())
 k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = gtid / LPC;

@@ -207,8 +207,8 @@ static int pick_lpc(const arp_model* m, long long C, int forced) {
   return 1;
 #endif
   if (forced == 1 || forced == 8 || forced == 32) return forced;
-  if (m->dev.kind == MODEL_TIME_SERIES)   // lane-parallel scan with the state on chip; sequential scan once the chip is full
-    return C >= 100000 ? 1 : (C >= 2048 ? 8 : 32);   // measured: 3.1e8 / 2.2e8 / 1.7e7 (C = 100) grad-evals/s
+  if (m->dev.kind == MODEL_TIME_SERIES)   // lane-parallel scan with the state on chip: measured 2.0e8 (C = 4096) .. 3.3e8
+    return C >= 2048 ? 8 : 32;            // (131 072) grad-evals/s with 8 lanes; 32 lanes for a few hundred chains
   const long long target = 148LL * 4 * 32 * 4;      // ~4 warps per SM sub-partition
   size_t b; int st, blk;
   const bool onchip8 = hmc_onchip_dpad(m->dev.kind, 8, m->dev.D, &b, &st, &blk) > 0;

@@ -142,12 +142,13 @@ def main():
             T = out["num_transitions"]
             evals_all = world * C * L * T
             # ---- ESS / R-hat / acceptance through the public call (collectives inside)
+            ekw = dict(num_leapfrog_steps=L, num_samples=S, num_burnin_steps=args.num_burnin_steps,
+                       num_adaptation_steps=int(0.6 * args.num_burnin_steps), chain_offset=rank * C, device=dev,
+                       return_is_accepted=False)
+            inference.hmc(hmc_target, mc, step0, z0, seed=8, **ekw)    # warm-up: pinned staging buffers, pooled scratch
             barrier()
             t0 = time.perf_counter()
-            res = inference.hmc(hmc_target, mc, step0, z0, num_leapfrog_steps=L, num_samples=S,
-                                num_burnin_steps=args.num_burnin_steps,
-                                num_adaptation_steps=int(0.6 * args.num_burnin_steps), seed=9, chain_offset=rank * C,
-                                device=dev, return_is_accepted=False)
+            res = inference.hmc(hmc_target, mc, step0, z0, seed=9, **ekw)
             barrier()
             e2e_s = max_over_ranks(time.perf_counter() - t0)
             min_ess = torch.as_tensor(np.nan_to_num(res.ess_flat).min(axis=1), device=dev)

@@ -221,7 +221,7 @@ int arp_ess(const arp_real* samples, int64_t S, int64_t C, int64_t D, arp_real* 
 
 /* VI: replaces util.get_mean_field_elbo (util.py:232-268) + the Adam loops of
  * inference.find_best_learning_rate (inference.py:26-154): all `num_runs`
- * learning rates are optimised concurrently (one CTA each) in one launch.
+ * learning rates are optimised concurrently (one 8-CTA thread-block cluster each) in one launch.
  *
  * Learnable reparameterisation (cVIP; make_learnable_parametrisation, program_transformations.py:475-533): `num_params`
  * unconstrained parameters u_p with value sigmoid(u_p) (tau = 1).  Coordinate d takes its `a` from slot a_index[d] and its

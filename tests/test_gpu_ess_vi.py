@@ -17,11 +17,13 @@ def _ar1(S, shape, phi, rng):
     return x
 
 
-@pytest.mark.parametrize("S", [50, 1000, 4097])
+@pytest.mark.parametrize("S", [50, 1000, 1024, 1025, 4097, 50000])
 @pytest.mark.parametrize("precision", ["f32", "f64"])
 def test_ess_matches_fft_oracle(S, precision):
+    """S <= 1024: the shared-memory FFT kernel; longer traces: the direct lag-sum kernels; 50 000 is the reference's
+    --num_samples default (main.py:95)."""
     rng = np.random.default_rng(S)
-    C, D = 5, 7
+    C, D = (5, 7) if S < 50000 else (3, 4)
     phi = rng.uniform(-0.5, 0.95, (C, D))
     x = _ar1(S, (C, D), phi, rng) + 3.0
     x = x.astype(np.float32).astype(np.float64)
