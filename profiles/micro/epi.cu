@@ -26,6 +26,48 @@ __device__ __forceinline__ void split_trunc(float x0, float x1, uint32_t& hi, ui
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+
+// packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2): a 64-bit register holds two floats
+__device__ __forceinline__ uint64_t pk(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// V7: the current epilogue on packed pairs: pair i = elements (2i, 2i + 1); each lane of a pair belongs to its own group
+// of four (pairs 4g .. 4g + 3), so every product / sum is one packed instruction for two elements
+__device__ __forceinline__ void epi32_packed(const uint32_t* hv, uint32_t* r1, uint32_t* r2) {
+  uint64_t d[16];
+  const uint64_t one2 = pk(1.0f, 1.0f), mone2 = pk(-1.0f, -1.0f);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float e0 = ex2a(fminf(__uint_as_float(hv[2 * i]), 30.f)), e1 = ex2a(fminf(__uint_as_float(hv[2 * i + 1]), 30.f));
+    d[i] = add2(pk(e0, e1), one2);
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint64_t a = d[4 * g], b = d[4 * g + 1], c = d[4 * g + 2], e = d[4 * g + 3];
+    const uint64_t p01 = mul2(a, b), p23 = mul2(c, e), pr = mul2(p01, p23);
+    float x, y;
+    upk(pr, x, y);
+    const uint64_t inv = pk(rcpa(x), rcpa(y));
+    const uint64_t i01 = mul2(inv, p23), i23 = mul2(inv, p01);
+    uint64_t q[4] = {mul2(i01, b), mul2(i01, a), mul2(i23, e), mul2(i23, c)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float q0, q1;
+      upk(q[k], q0, q1);
+      const __half2 h = __floats2half2_rn(q0, q1);
+      const float2 hf = __half22float2(h);
+      float t0, t1;
+      upk(fma2(pk(hf.x, hf.y), mone2, q[k]), t0, t1);     // q - head, exact
+      const __half2 l = __floats2half2_rn(t0, t1);
+      r1[4 * g + k] = *reinterpret_cast<const uint32_t*>(&h);
+      r2[4 * g + k] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+  }
+}
+
 template <int V>
 __device__ __forceinline__ void epi32(const uint32_t* hv, uint32_t* r1, uint32_t* r2) {
   float d[32];
@@ -77,6 +119,8 @@ __global__ void __launch_bounds__(512, 1) k(uint32_t* out, long long* clk, float
     if (V == 6) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) split_pack(__uint_as_float(hv[2 * i]), __uint_as_float(hv[2 * i + 1]), r1[i], r2[i]);
+    } else if (V == 7) {
+      epi32_packed(hv, r1, r2);
     } else {
       epi32<V>(hv, r1, r2);
     }
@@ -111,5 +155,6 @@ int main() {
   run<4>("V4 share2");
   run<5>("V5 no split");
   run<6>("V6 split only");
+  run<7>("V7 packed fp32x2 (FADD2 / FMUL2 / FFMA2)");
   return 0;
 }

@@ -3,6 +3,7 @@
 #   bench.py (BASELINE configs[1], weak and strong scaling), configs[4] (radon_synth + time_series, 8192 chains per GPU),
 #   per-model table (bench_models.py)
 N=${1:-8}
+ONLY=${2:-all}     # "german": only the configs[1] lines (re-run after a change of the tcgen05 kernel)
 mkdir -p gpurun_out
 run() {  # run NAME args...: bench.py on N ranks, JSON line -> gpurun_out/r02s_NAME_nN.json
   name=$1; shift
@@ -25,6 +26,7 @@ PY
 }
 run german_weak --steps 3 --warmup 3 --no_cpu_baseline
 run german_strong --steps 3 --warmup 3 --no_cpu_baseline --scaling strong --chains 16384
+[ "$ONLY" = german ] && exit 0
 run radon_synth --model radon_synth --chains 8192 --num_samples 100 --num_burnin_steps 100 --num_adaptation_steps 80 --steps 2 --warmup 1 --no_cpu_baseline
 run time_series --model time_series --chains 8192 --steps 2 --warmup 1 --no_cpu_baseline
 if [ "$N" = 1 ]; then
