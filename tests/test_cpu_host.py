@@ -277,3 +277,96 @@ def test_discrete_prior_density_known_values():
     ref = np.log(w[0] * lap(p.numpy(), 0.0) + w[1] * 1.0 + w[2] * lap(p.numpy(), 1.0))
     assert np.allclose(got, ref, atol=1e-12)
     assert got[0] > got[2] and abs(got[0] - got[4]) < 1e-12     # mass piles up at 0 and 1, symmetric
+
+
+GLOO_CLI_WORKER = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import torch
+from autoreparam_b200 import distributed, inference, main, models
+from tests import common
+distributed.init_if_needed("gloo")
+rank, world = distributed.rank_world()
+seen = {}
+
+def fake_hmc(target, mc, step_size_init, z0, reparam=None, *, num_leapfrog_steps, num_samples, num_burnin_steps,
+             num_adaptation_steps, num_chains_to_save=0, seed=0, chain_offset=0, device="cpu", precision="f32",
+             return_is_accepted=True, stream_window=0, **kw):
+    # stands in for the CUDA engine: deterministic per GLOBAL chain id, so the gathered result can be checked
+    C, D = z0.shape
+    gid = chain_offset + np.arange(C)
+    seen.update(C=C, chain_offset=chain_offset, n_save=num_chains_to_save)
+    ess_flat = (100.0 + gid[:, None] + 0.01 * np.arange(D)[None, :]).astype(np.float32)
+    mean = torch.as_tensor(np.tile(gid[:, None] * 0.001, (1, D)))
+    var = torch.ones((C, D), dtype=torch.float64)
+    stats = distributed.rhat_stats(mean, var)
+    acc = torch.tensor([float(num_samples * C) * 0.5, 1.0, float(C)], dtype=torch.float64)
+    distributed.allreduce_sum_(stats)        # the collectives of the real inference.hmc
+    distributed.allreduce_sum_(acc)
+    rhat = distributed.rhat_from_stats(stats, num_samples).numpy()
+    samples = None
+    if num_chains_to_save > 0:
+        samples = mc.split(np.zeros((num_samples, num_chains_to_save, D), np.float32))
+    return inference.HmcResult(ess=mc.split(ess_flat), is_accepted=None, samples=samples, rhat=rhat,
+                               step_mult=np.ones(C), accept_count=np.ones(C), num_transitions=1, ess_flat=ess_flat,
+                               accept_stats=tuple(float(v) for v in acc))
+
+inference.hmc = fake_hmc
+models.load_raw = lambda model, dataset=None, data_dir=None: common.raw_data(model, dataset or "MN")
+rd = os.path.join(sys.argv[2], "8schools_")
+os.makedirs(rd, exist_ok=True)
+if rank == 0:     # what a VI run leaves behind
+    json.dump({"initial_step_size": [0.1, 0.1, [0.1] * 8],
+               "learned_variational_params": {"mu_loc": 0.0, "mu_scale": 1.0, "log_tau_loc": 0.0, "log_tau_scale": 1.0,
+                                              "theta_loc": [0.0] * 8, "theta_scale": [1.0] * 8}},
+              open(os.path.join(rd, "NCP_tied.json"), "w"))
+distributed.barrier()
+C = 11
+main.main(["--model=8schools", "--results_dir=" + rd, "--inference=HMC", "--method=NCP", "--num_leapfrog_steps=4",
+           "--num_samples=50", "--num_burnin_steps=10", "--num_adaptation_steps=5", "--num_chains=%d" % C,
+           "--num_chains_to_save=3"])
+lo, hi = distributed.shard_range(C, rank, world)
+assert (seen["C"], seen["chain_offset"]) == (hi - lo, lo), seen          # contiguous shard, global chain ids
+assert seen["n_save"] == (3 if rank == 0 else 0)                          # traces live on rank 0
+distributed.barrier()
+if rank == 0:
+    out = json.load(open(os.path.join(rd, "NCP_tied.json")))
+    assert abs(out["acceptance_rate"][0] - 50.0) < 1e-9, out["acceptance_rate"]     # over the chains of ALL ranks
+    ess = np.load(os.path.join(rd, "NCP_tied_ess.npz"))
+    assert ess["theta"].shape == (C, 8)                                             # gathered over the ranks
+    want = 1000.0 * (100.0 + np.arange(C)[:, None] + 0.01 * (2 + np.arange(8))[None, :]) / (50 * 4)
+    assert np.allclose(ess["theta"], want, rtol=1e-6)
+    from autoreparam_b200 import util
+    ref = util.rhat_from_moments(np.tile(np.arange(C)[:, None] * 0.001, (1, 10)), np.ones((C, 10)), 50)
+    assert abs(out["rhat_max"][0] - float(np.max(ref))) < 1e-9 and len(out["ess_min"]) == 1      # all 11 chains
+else:
+    assert not os.path.exists(os.path.join(rd, "NCP_tied_ess_rank1.npz"))
+# more ranks than chains: refused on every rank before any work (no rank is left waiting in a collective)
+import types
+try:
+    main._check_sharding(types.SimpleNamespace(num_chains=1), world)
+    raise SystemExit("expected ValueError")
+except ValueError as e:
+    assert "smaller than the number of ranks" in str(e)
+distributed.barrier(); distributed.shutdown()
+open(os.path.join(sys.argv[2], "cli_ok_%d" % rank), "w").write("ok")
+"""
+
+
+def test_cli_hmc_path_world_size_2_gloo(tmp_path):
+    """The drop-in driver under torchrun (2 processes, gloo, engine stubbed on the CPU): chains sharded contiguously
+    with their global ids, ESS gathered over the ranks, acceptance / R-hat reduced over all ranks, files written by
+    rank 0 only, and the more-ranks-than-chains case refused on every rank."""
+    script = tmp_path / "cli_worker.py"
+    script.write_text(GLOO_CLI_WORKER)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), str(script), root, str(tmp_path)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert (tmp_path / "cli_ok_0").exists() and (tmp_path / "cli_ok_1").exists()
