@@ -195,8 +195,7 @@ __device__ __forceinline__ void tcs_epilogue32(const uint32_t* hv, uint32_t* r1,
 // fp16 head / tail of a pair is exactly one packed half2 of the A operand.  Each lane of a pair belongs to its own group
 // of four (pairs 4G .. 4G + 3), so the shared-reciprocal trick runs on both lanes at once: per 32 elements 16 FADD2 +
 // 36 FMUL2 + 16 FFMA2 replace 64 FADD + 72 FMUL (204 instead of 272 instructions).  TCS_PACKED selects it.
-// (bit mask for A/B measurements: 1 = packed adds, 2 = packed multiplies, 4 = packed head subtraction; 7 = all;
-// 16 = a quarter of the exponentials on the FMA pipe)
+// (bit mask for A/B measurements: 1 = packed adds, 2 = packed multiplies, 4 = packed head subtraction; 7 = all)
 #ifndef TCS_PACKED
 #define TCS_PACKED 7
 #endif
@@ -230,28 +229,7 @@ __device__ __forceinline__ void tcs_epilogue32_packed(const uint32_t* hv, uint32
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = 4 * G + k;
-      float m0 = fminf(__uint_as_float(hv[2 * i]), 30.f), m1 = fminf(__uint_as_float(hv[2 * i + 1]), 30.f);
-#if TCS_PACKED & 16
-      if (k == 3) {
-        // one pair in four takes 2^m from the FMA pipe instead of MUFU.EX2 (the XU pipe is what binds the epilogue once
-        // the packed instructions have freed issue slots): m = n + f, n = round(m) by the magic-number add, 2^f by a
-        // degree-5 polynomial on [-1/2, 1/2] (3.7e-7, MUFU.EX2: 2.4e-7), 2^n added into the exponent field
-        m0 = fmaxf(m0, -120.f); m1 = fmaxf(m1, -120.f);
-        const uint64_t mm = f2_pack(m0, m1), magic = f2_pack(12582912.f, 12582912.f), nmagic = f2_pack(-12582912.f, -12582912.f);
-        const uint64_t t = f2_add(mm, magic);
-        const uint64_t f = f2_fma(f2_add(t, nmagic), f2_pack(-1.f, -1.f), mm);      // m - n
-        uint64_t pz = f2_fma(f2_pack(1.3395279801e-3f, 1.3395279801e-3f), f, f2_pack(9.6707631287e-3f, 9.6707631287e-3f));
-        pz = f2_fma(pz, f, f2_pack(5.5503406807e-2f, 5.5503406807e-2f));
-        pz = f2_fma(pz, f, f2_pack(2.4022211737e-1f, 2.4022211737e-1f));
-        pz = f2_fma(pz, f, f2_pack(6.9314720006e-1f, 6.9314720006e-1f));
-        pz = f2_fma(pz, f, f2_pack(1.0000000523f, 1.0000000523f));
-        float p0, p1, t0, t1;
-        f2_unpack(pz, p0, p1);
-        f2_unpack(t, t0, t1);
-        d[G][k] = f2_pack(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),
-                          __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
-      } else
-#endif
+      const float m0 = fminf(__uint_as_float(hv[2 * i]), 30.f), m1 = fminf(__uint_as_float(hv[2 * i + 1]), 30.f);
       d[G][k] = f2_pack(ex2_approx(m0), ex2_approx(m1));
       if (LAST) ms[G] = k == 0 ? f2_pack(m0, m1) : f2_add(ms[G], f2_pack(m0, m1));
     }

@@ -54,7 +54,7 @@ struct HmcArgs {
   size_t stream_plane;             // elements per plane
   real* stream_pivot;              // [plane]
   real* stream_sum;                // [plane]
-  real* stream_ring;               // [W][plane]
+  real* stream_ring;               // [2 W][plane]: the last two blocks of W kept values
   real* stream_head;               // [W][plane]
   real* stream_acc;                // [W][plane]
 };
@@ -93,6 +93,41 @@ __device__ __forceinline__ HmcRun hmc_run_view(const HmcArgs& p, int row) {
   return r;
 }
 #define ARP_RUN(f) (MULTI ? rv.f : p.f)
+
+// Streaming lag products, one BLOCK of kept samples at a time.  The ring holds the last two blocks of W values of
+// y = x - pivot (slots [cb, cb + W) = the block that just completed, [pb, pb + W) = the one before it).  For every lag
+// k < W:  acc_k += sum_{t in block} y_t y_{t-k}, with y_{t-k} taken from the previous block where t - k falls there.
+// Done per block instead of per kept sample, the W ring values and W lag sums of a coordinate cross HBM once per W
+// samples instead of once per sample: (3 W + 6) -> ~6 plane accesses per kept sample and coordinate (the re-reads inside
+// the block hit L1).  `len` < W only for the last, partial block (k_stream_finalize).  Returns the block's sum of y.
+__device__ __forceinline__ real stream_block(const HmcArgs& p, size_t e, int cb, int len, bool has_prev) {
+  const int W = p.stream_W;
+  const size_t plane = p.stream_plane;
+  const int pb = cb == 0 ? W : 0;
+  const real* ring = p.stream_ring;
+  real bsum = 0;
+  for (int t = 0; t < len; ++t) bsum += ring[(size_t)(cb + t) * plane + e];
+  for (int k0 = 0; k0 < W; k0 += 16) {
+    real a16[16];
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) a16[kk] = 0;
+    for (int t = 0; t < len; ++t) {
+      const real yt = ring[(size_t)(cb + t) * plane + e];
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        const int k = k0 + kk, j = t - k;
+        if (k < W) {
+          if (j >= 0) a16[kk] = fma(yt, ring[(size_t)(cb + j) * plane + e], a16[kk]);
+          else if (has_prev) a16[kk] = fma(yt, ring[(size_t)(pb + W + j) * plane + e], a16[kk]);
+        }
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk)
+      if (k0 + kk < W) p.stream_acc[(size_t)(k0 + kk) * plane + e] += a16[kk];
+  }
+  return bsum;
+}
 
 template <int KIND, int LPC, bool WITH_A, int FP>
 __global__ void __launch_bounds__(ARP_BLOCK)
@@ -134,6 +169,9 @@ k_hmc_init(DevModel m, HmcWs ws, HmcArgs p, const real* z0) {
   }
 }
 
+#ifndef ARP_RADON_FUSED
+#define ARP_RADON_FUSED 1   // 0: the generic sweeps for the radon models too (A/B measurements)
+#endif
 // Resident blocks per SM ptxas is asked to make room for (register budget = 65536 / (128 threads x blocks)).  Left to
 // itself ptxas gave the radon kernels 80 or 128 registers and the electric kernel 168 or 240 depending on unrelated
 // details of the surrounding code (measured: radon_synth 3.5e6 vs 2.75e6 grad-evals/s, electric 6.7e8 vs 5.3e8), so the
@@ -240,6 +278,11 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
     for (int l = 0; l < ARP_RUN(L); ++l) {
       __syncwarp();
       const bool last = (l == ARP_RUN(L) - 1);
+      if constexpr (ARP_RADON_FUSED && (KIND == MODEL_RADON || KIND == MODEL_RADON_STDDVS)) {
+        // radon: the gradient sweep applies the kicks itself (arp_models.cuh: vg_radon_kick)
+        lpx = vg_radon_kick<LPC, KIND == MODEL_RADON_STDDVS>(m, p.a, p.b, X, GX, XCX, V, eps0, mult, sub, last, ke1);
+        continue;
+      }
       lpx = vg<KIND, LPC, false, FP>(m, p.a, p.b, X, GX, XCX, Vec{nullptr, 1}, Vec{nullptr, 1}, sub, last);
       __syncwarp();
       if (last) {
@@ -296,24 +339,18 @@ k_hmc_run(DevModel m, HmcWs ws, HmcArgs p, int oc_dpad, int oc_stride) {
         if (ARP_RUN(samples_orig)) for (int d = sub; d < D; d += LPC) ARP_RUN(samples_orig)[o + d] = Zc(d);
         if (ARP_RUN(is_accepted) && sub == 0) ARP_RUN(is_accepted)[(size_t)s * p.C + chain] = acc ? 1 : 0;
         if (p.stream_W > 0) {
-          const int W = p.stream_W, slot = s % W, kmax = s < W - 1 ? s : W - 1;
+          const int W = p.stream_W, slot = s % (2 * W);
           const size_t plane = p.stream_plane;
+          const bool block_done = (s % W) == W - 1;
           for (int d = sub; d < D; d += LPC) {
             const size_t e = (size_t)d * ws.sd + co;
             const real xv = XCc(d);
             real piv;
             if (s == 0) { piv = xv; p.stream_pivot[e] = xv; } else piv = p.stream_pivot[e];
             const real y = xv - piv;
-            p.stream_sum[e] += y;
             p.stream_ring[(size_t)slot * plane + e] = y;
             if (s < W) p.stream_head[(size_t)s * plane + e] = y;
-            p.stream_acc[e] = fma(y, y, p.stream_acc[e]);
-            for (int k = 1; k <= kmax; ++k) {
-              int sl = slot - k;
-              if (sl < 0) sl += W;
-              real* a = p.stream_acc + (size_t)k * plane + e;
-              *a = fma(y, p.stream_ring[(size_t)sl * plane + e], *a);
-            }
+            if (block_done) p.stream_sum[e] += stream_block(p, e, slot - (W - 1), W, s >= W);
           }
         }
       }
@@ -349,6 +386,12 @@ __global__ void k_stream_finalize(HmcWs ws, HmcArgs p, int S, real* mean_cd, rea
   const int c = (int)(i / p.D), d = (int)(i % p.D);
   const size_t e = (size_t)d * ws.sd + (size_t)c * ws.sc, plane = p.stream_plane;
   const int W = p.stream_W;
+  // the last, partial block of kept samples (S is not a multiple of W in general)
+  const int rem = S % W;
+  if (rem > 0) {
+    const int s0 = S - rem;
+    p.stream_sum[e] += stream_block(p, e, s0 % (2 * W), rem, s0 >= W);
+  }
   const double sum = (double)p.stream_sum[e], m = sum / S;
   if (mean_cd) mean_cd[i] = (real)((double)p.stream_pivot[e] + m);
   const int K = W < S ? W : S;
@@ -357,7 +400,7 @@ __global__ void k_stream_finalize(HmcWs ws, HmcArgs p, int S, real* mean_cd, rea
   for (int k = 0; k < K; ++k) {
     if (k > 0) {
       head += (double)p.stream_head[(size_t)(k - 1) * plane + e];
-      int sl = (S - k) % W;                      // slot of kept sample S - k
+      int sl = (S - k) % (2 * W);                // slot of kept sample S - k
       tail += (double)p.stream_ring[(size_t)sl * plane + e];
     }
     const double ck = (double)p.stream_acc[(size_t)k * plane + e] - m * ((sum - head) + (sum - tail)) + (double)(S - k) * m * m;

@@ -519,13 +519,13 @@ extern "C" int arp_hmc_run(arp_model* m, const arp_hmc_config* cfg, const arp_re
     ws.nacc = nacc.as<int>();
     if (lpc == 1) { ws.sd = (int)Cpad; ws.sc = 1; } else { ws.sd = 1; ws.sc = (int)Dpad; }
     const int W = cfg->stream_window;
-    if (W > 0) {   // streaming statistics: (3 W + 2) planes in the workspace layout, zero-initialised
-      ARP_CUDA(dstream.alloc((size_t)(3 * W + 2) * vec * sizeof(real)));
-      ARP_CUDA(cudaMemsetAsync(dstream.p, 0, (size_t)(3 * W + 2) * vec * sizeof(real), st));
+    if (W > 0) {   // streaming statistics: (4 W + 2) planes in the workspace layout, zero-initialised
+      ARP_CUDA(dstream.alloc((size_t)(4 * W + 2) * vec * sizeof(real)));
+      ARP_CUDA(cudaMemsetAsync(dstream.p, 0, (size_t)(4 * W + 2) * vec * sizeof(real), st));
       real* sbase = dstream.as<real>();
       p.stream_W = W; p.stream_plane = vec;
-      p.stream_pivot = sbase; p.stream_sum = sbase + vec; p.stream_ring = sbase + 2 * vec;
-      p.stream_head = sbase + (size_t)(2 + W) * vec; p.stream_acc = sbase + (size_t)(2 + 2 * W) * vec;
+      p.stream_pivot = sbase; p.stream_sum = sbase + vec; p.stream_ring = sbase + 2 * vec;      // ring: 2 W planes
+      p.stream_head = sbase + (size_t)(2 + 2 * W) * vec; p.stream_acc = sbase + (size_t)(2 + 3 * W) * vec;
     }
     const dim3 grid((unsigned)(Cpad / cpb)), block(ARP_BLOCK);
     const DevModel dm = m->dev;

@@ -303,6 +303,88 @@ __device__ real vg_radon(const DevModel& m, const real* a, const real* b,
   return lp;
 }
 
+// Gradient sweep FUSED with the leapfrog kicks (SIMT HMC kernel, radon models).  The gradient of a per-county
+// coordinate is local to its county, so the sweep that computes it can apply the kick on the spot instead of storing
+// it for a second sweep: on a non-final leapfrog step `v += e g / 2` (end of this step), `v += e g / 2; x += e v` (start
+// of the next) with the SAME two separately rounded half kicks as the unfused path, and neither the gradient nor the
+// centred value is stored; on the final step the half kick only feeds the kinetic energy and (g, xc) are stored for
+// the accept decision.  Per coordinate and leapfrog step: read x, v + write x, v instead of read x, v, g, x + write
+// g, xc, v, x -- the synthetic 10^6 x 10^4 radon streams its state through HBM, so this is what it pays for.
+// `z` is the proposal position (updated in place), `ke` accumulates this lane's share of |v|^2 on the final step.
+template <int LPC, bool STDDVS>
+__device__ real vg_radon_kick(const DevModel& m, const real* a, const real* b, Vec z, Vec g, Vec xc, Vec v,
+                              const real* __restrict__ eps0, real mult, int sub, bool last, real& ke) {
+  const int J = m.J;
+  real lp_top = 0;
+  const real a0 = (*a), a1 = (*(a + 1)), a2 = (*(a + 2));
+  Site smua = site_fwd_unit(z(0), (real)0, a0, lp_top);
+  Site sb1 = site_fwd_unit(z(1), (real)0, a1, lp_top);
+  Site sb2 = site_fwd_unit(z(2), (real)0, a2, lp_top);
+  const real mua = smua.x, b1 = sb1.x, b2 = sb2.x;
+  auto kick = [&](int d, real grad, real centred) {
+    const real e = ldg(eps0 + d) * mult;
+    real vv = v(d) + (real)0.5 * e * grad;
+    if (last) {
+      ke = fma(vv, vv, ke);
+      g(d) = grad;
+      xc(d) = centred;
+    } else {
+      vv = vv + (real)0.5 * e * grad;
+      v(d) = vv;
+      z(d) = z(d) + e * vv;
+    }
+  };
+  __syncwarp();   // every lane has read the three top-level coordinates before lane 0 moves them (below)
+  real lp = 0, acc_mua = 0, acc_b1 = 0, acc_b2 = 0;
+  double lik_d = 0;
+  for (int j = sub; j < J; j += LPC) {
+    const real uj = ldg(m.u + j);
+    const real mu_j = mua + uj * b1;
+    const real aj = (*(a + 3 + j));
+    Site sm = site_fwd_unit(z(3 + j), mu_j, aj, lp);
+    const real mj = sm.x;
+    real lsj = 0, inv = 1, inv2 = 1;
+    Site sl;
+    if (STDDVS) {
+      sl = site_fwd_unit(z(3 + J + j), (real)0, (*(a + 3 + J + j)), lp);
+      lsj = sl.x;
+      inv = r_exp(-lsj);
+      inv2 = inv * inv;
+    }
+    const real* st = m.w + (size_t)6 * j;
+    const real cnt = ldg(st), ybar = ldg(st + 1), xbar = ldg(st + 2), Cyy = ldg(st + 3), Cxy = ldg(st + 4), Cxx = ldg(st + 5);
+    const real dj = ybar - mj - xbar * b2;
+    const real se = cnt * dj;
+    const real sex = Cxy - b2 * Cxx + cnt * xbar * dj;
+    const real see = Cyy - (real)2 * b2 * Cxy + b2 * b2 * Cxx + cnt * dj * dj;
+    lik_d += (double)((real)-0.5 * see * inv2 - cnt * (lsj + ARP_HALF_LOG_2PI));
+    acc_b2 += sex * inv2;
+    real zb, mb, lb, ab;
+    site_rev(sm, se * inv2, mu_j, aj, (real)1, zb, mb, lb, ab);
+    kick(3 + j, zb, mj);
+    acc_mua += mb;
+    acc_b1 += uj * mb;
+    if (STDDVS) {
+      site_rev(sl, see * inv2 - cnt, (real)0, (real)0, (real)1, zb, mb, lb, ab);
+      kick(3 + J + j, zb, lsj);
+    }
+  }
+  acc_mua = group_sum<LPC>(acc_mua);
+  acc_b1 = group_sum<LPC>(acc_b1);
+  acc_b2 = group_sum<LPC>(acc_b2);
+  lp = (real)(group_sum<LPC>((double)lp + lik_d)) + lp_top;
+  if (sub == 0) {
+    real zb, mb, lb, ab;
+    site_rev(smua, acc_mua, (real)0, a0, (real)1, zb, mb, lb, ab);
+    kick(0, zb, mua);
+    site_rev(sb1, acc_b1, (real)0, a1, (real)1, zb, mb, lb, ab);
+    kick(1, zb, b1);
+    site_rev(sb2, acc_b2, (real)0, a2, (real)1, zb, mb, lb, ab);
+    kick(2, zb, b2);
+  }
+  return lp;
+}
+
 // --------------------------------------------------------------- election ---
 // reference models.py:969-982.  z = [mua, log_sigma_a, a[K], b1, b2].
 // Observations are grouped by the one-hot index of `state` (group K = "no

@@ -7,7 +7,7 @@ BASELINE configs through --model / --inference.
     python bench.py --model 8schools --method CP --chains 1048576                # configs[0] shape, throughput
     python bench.py --model radon --method NCP                                   # configs[2]
     python bench.py --model election --inference VI --method dVIP                # configs[3]: 5 lrs x 3000 steps x S=256
-    torchrun ... bench.py --gpus 8 --model radon_synth --chains 8192 --stream_window 16    # configs[4], 65 536 chains
+    torchrun ... bench.py --gpus 8 --model radon_synth --chains 8192 --stream_window 64    # configs[4], 65 536 chains
     torchrun ... bench.py --gpus 8 --model time_series --chains 8192                       # configs[4], 65 536 chains
 
 One "step" = one full pass of the hot path over one batch of chains: a complete
@@ -60,7 +60,7 @@ def parse():
     p.add_argument("--method", default="NCP", choices=["CP", "NCP", "cVIP", "dVIP"])
     p.add_argument("--features", type=int, default=25, help="german_synth: 25 = BASELINE synthetic shape")
     p.add_argument("--stream_window", type=int, default=0,
-                   help="W > 0: no [S,C,D] trace, ESS / R-hat from in-kernel streaming statistics (radon_synth default 16)")
+                   help="W > 0: no [S,C,D] trace, ESS / R-hat from in-kernel streaming statistics (radon_synth default 64)")
     p.add_argument("--num_optimization_steps", type=int, default=3000)
     p.add_argument("--num_mc_samples", type=int, default=256)
     p.add_argument("--num_leapfrog_steps", type=int, default=4)
@@ -245,7 +245,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.model == "radon_synth" and args.stream_window == 0:
-        args.stream_window = 16
+        args.stream_window = 64
     vi = args.inference == "VI"
     name, raw, mc, D, a, b, desc = workload(args)
     metric = "elbo_iterations_per_sec" if vi else "leapfrog_grad_evals_per_sec"
@@ -422,8 +422,9 @@ def main():
                                              "SM clock sampled under load" % (mufu_per_obs, n_pad, sms_used)}}
         elif bound == "hbm":
             by = float(MODEL_TABLE[args.model]["bytes"](raw, D))
-            if W:   # streaming statistics: per kept sample read W ring values, read-modify-write W + 1 lag sums, ...
-                by += (S / float(L * T)) * D * 4.0 * (3 * W + 6)
+            if W:   # streaming statistics, per kept sample and coordinate: pivot read + ring write, and once per block of W
+                    # kept samples 2 W ring reads + W lag sums read-modify-written + the running sum
+                by += (S / float(L * T)) * D * 4.0 * (2.0 + (4.0 * W + 2.0) / W)
             achieved = rate * by / 1e9
             peak = pk.get("hbm_gbs_sustained", pk["hbm_gbs"])
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -149,7 +149,8 @@ typedef struct arp_hmc_buffers {
   int32_t* accept_count;
   /* streaming statistics (cfg.stream_window = W > 0; each pointer optional), for runs whose [S,C,D] traces cannot be
    * stored (BASELINE configs[4]: 65 536 chains x 10 003 coordinates): the kernel keeps, per (chain, coordinate), a ring
-   * of the last W kept values and W lag-product sums instead of the trace -- (3 W + 2) floats instead of S. */
+   * of the last 2 W kept values, the first W values and W lag-product sums (updated once per block of W kept samples)
+   * instead of the trace -- (4 W + 2) floats instead of S. */
   arp_real* stream_mean;      /* [C,D] out  mean of the kept centred samples */
   arp_real* stream_var;       /* [C,D] out  their biased variance */
   arp_real* stream_ess;       /* [C,D] out  ESS (same estimator as arp_ess) from the lags inside the window */

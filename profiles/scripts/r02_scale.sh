@@ -3,7 +3,7 @@
 #   bench.py (BASELINE configs[1], weak and strong scaling), configs[4] (radon_synth + time_series, 8192 chains per GPU),
 #   per-model table (bench_models.py)
 N=${1:-8}
-ONLY=${2:-all}     # "german": only the configs[1] lines (re-run after a change of the tcgen05 kernel)
+ONLY=${2:-all}     # "german": only the configs[1] lines; "configs4": only radon_synth + time_series (re-runs after kernel changes)
 mkdir -p gpurun_out
 run() {  # run NAME args...: bench.py on N ranks, JSON line -> gpurun_out/r02s_NAME_nN.json
   name=$1; shift
@@ -24,11 +24,14 @@ except Exception as e:
     print(name, "failed", e, open("gpurun_out/r02s_%s_n%s.err" % (name, n)).read()[-800:])
 PY
 }
+if [ "$ONLY" != configs4 ]; then
 run german_weak --steps 3 --warmup 3 --no_cpu_baseline
 run german_strong --steps 3 --warmup 3 --no_cpu_baseline --scaling strong --chains 16384
+fi
 [ "$ONLY" = german ] && exit 0
-run radon_synth --model radon_synth --chains 8192 --num_samples 100 --num_burnin_steps 100 --num_adaptation_steps 80 --steps 2 --warmup 1 --no_cpu_baseline
+run radon_synth --model radon_synth --chains 8192 --num_samples 100 --num_burnin_steps 100 --num_adaptation_steps 80 --stream_window 64 --steps 2 --warmup 1 --no_cpu_baseline
 run time_series --model time_series --chains 8192 --steps 2 --warmup 1 --no_cpu_baseline
+[ "$ONLY" = configs4 ] && exit 0
 if [ "$N" = 1 ]; then
   timeout 1500 python bench_models.py --out gpurun_out/r02_models_n$N.json > gpurun_out/r02_models_n$N.log 2>&1
 else
