@@ -626,6 +626,44 @@ def effective_sample_size(states):
         return S / (-1.0 + 2.0 * np.sum((S - k) / S * rho, axis=0))
 
 
+def windowed_ess(states, W):
+    """Bounded-memory ESS as the streaming statistics of arp_hmc_run compute it (stream_window = W): the same estimator as
+    effective_sample_size, but only the lags k < W are available -- the sum stops at the first lag with rho < 0 or, if
+    none lies inside the window, uses all W lags (then `truncated` is True and the value is an upper bound).  Restated
+    from the centred lag products directly (no FFT), in the streaming form: y = x - pivot (pivot = first sample),
+    A_k = sum_t y_t y_{t-k},  c_k = A_k - m [(sum - head_k) + (sum - tail_k)] + (S - k) m^2 with m = mean(y).
+    states [S, ...] -> (ess [...], truncated [...] bool)."""
+    x = np.asarray(states, dtype=np.float64)
+    S = x.shape[0]
+    y = x - x[:1]
+    tot = y.sum(axis=0)
+    m = tot / S
+    K = min(W, S)
+    ess = np.full(x.shape[1:], np.nan)
+    trunc = np.zeros(x.shape[1:], dtype=bool)
+    acc = np.zeros(x.shape[1:])
+    alive = np.ones(x.shape[1:], dtype=bool)
+    acov0 = None
+    for k in range(K):
+        A = (y[k:] * y[:S - k]).sum(axis=0)
+        head = y[:k].sum(axis=0)           # sum of the first k values
+        tail = y[S - k:].sum(axis=0) if k > 0 else 0.0
+        ck = A - m * ((tot - head) + (tot - tail)) + (S - k) * m * m
+        if k == 0:
+            acov0 = ck / S
+            alive &= acov0 > 0
+        with np.errstate(invalid="ignore", divide="ignore"):
+            rho = (ck / (S - k)) / acov0
+        neg = alive & (rho < 0)
+        alive &= ~neg
+        acc = np.where(alive, acc + (S - k) / S * rho, acc)
+    ok = acov0 > 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ess = np.where(ok, S / (-1.0 + 2.0 * acc), np.nan)
+    trunc = ok & alive & (K < S)
+    return ess, trunc
+
+
 def get_min_ess(ess_parts, num_chains):
     """util.py:445-460: nan->0, per-chain min over all coordinates, mean and
     std/sqrt(n) over chains.  ess_parts: list of [C, *site]."""

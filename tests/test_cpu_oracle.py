@@ -179,3 +179,26 @@ def test_batched_cpu_baseline_gather_variant_and_samplers():
     assert n == 4 + 4 * 3 * 6 and np.isfinite(z).all() and np.abs(z - Z).max() > 0      # chains moved
     tl = O.vi_cpu_batched("8schools", common.raw_data("8schools"), 64, 60, 0.1, 0.0, 0.0)
     assert np.isfinite(tl).all() and tl[-10:].mean() > tl[:5].mean()
+
+
+def test_windowed_ess_restatement():
+    """The bounded-memory ESS the streaming statistics compute (oracle restatement): equal to the FFT ESS wherever the
+    first negative autocorrelation lies inside the window, an upper bound (and flagged) elsewhere."""
+    rng = np.random.default_rng(3)
+    S, n = 600, 40
+    phi = rng.uniform(-0.3, 0.97, n)
+    x = np.zeros((S, n))
+    cur = rng.standard_normal(n)
+    for t in range(S):
+        cur = phi * cur + rng.standard_normal(n)
+        x[t] = cur + 5.0
+    ref = O.effective_sample_size(x)
+    full, tr_full = O.windowed_ess(x, S)           # window = everything: the same estimator, no FFT
+    assert not tr_full.any() and np.abs(full / ref - 1).max() < 1e-9
+    win, tr = O.windowed_ess(x, 32)
+    assert tr.any() and (~tr).any()                # slowly mixing series are truncated, fast ones resolved
+    assert np.abs(win[~tr] / ref[~tr] - 1).max() < 1e-9
+    assert (win[tr] >= ref[tr] * (1 - 1e-12)).all()
+    const = np.ones((50, 2))
+    e, t = O.windowed_ess(const, 8)
+    assert np.isnan(e).all() and not t.any()       # constant series: NaN, as TFP

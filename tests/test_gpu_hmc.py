@@ -188,3 +188,15 @@ def test_streaming_statistics_match_stored_trace(model, lpc, precision):
     if tr.any():                                    # truncated window: upper bound
         sel = tr & np.isfinite(ref)
         assert (out["stream_ess"][sel] >= ref[sel] * (1 - 1e-3)).all()
+    # and against the oracle's restatement of the windowed estimator on the same trace: values AND truncation flags
+    # (the block-wise lag accumulation, the partial last block -- S = 400 is not a multiple of 48 / 256 -- and the
+    # head / tail corrections of the mean)
+    ess_o, tr_o = O.windowed_ess(x, W)
+    flips = (tr_o != tr) & okv                      # rho ~ 0 at the window edge may flip by round-off
+    assert flips.mean() < (0.02 if precision == "f32" else 1e-3), flips.mean()
+    same = (tr_o == tr) & okv & np.isfinite(ess_o)
+    rel = np.abs(out["stream_ess"][same] / ess_o[same] - 1)
+    if precision == "f64":
+        assert rel.max() < 1e-6, rel.max()
+    else:
+        assert np.median(rel) < 1e-3 and np.quantile(rel, 0.98) < 0.1, (np.median(rel), np.quantile(rel, 0.98))
