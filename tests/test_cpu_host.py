@@ -370,3 +370,26 @@ def test_cli_hmc_path_world_size_2_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert (tmp_path / "cli_ok_0").exists() and (tmp_path / "cli_ok_1").exists()
+
+
+def test_bench_workload_table():
+    """bench.py's per-model bookkeeping: every in-scope model has a roofline bound and an algorithmic flop count that
+    follows SURVEY.md 8d; the method -> (a, b) map; the reference arm needs no GPU."""
+    import argparse
+    import bench as B
+    from tests import common
+    assert set(B.MODEL_TABLE) >= set(common.MODELS) | {"german_synth", "radon_synth"}
+    raw = common.raw_data("radon", "PA")
+    D = 3 + len(raw["u"])
+    assert B.flop_per_grad(argparse.Namespace(model="radon"), raw, D) == 6.0 * 2389 + 8.0 * 68       # 6N + 8J
+    rawg = common.raw_data("german_synth")
+    assert B.flop_per_grad(argparse.Namespace(model="german_synth"), rawg, 51) == 1.06e5              # 4NF + 12F + 6N
+    rawr = common.raw_data("german_credit_lognormalcentered")
+    assert B.flop_per_grad(argparse.Namespace(model="german_credit_lognormalcentered"), rawr, 125) == 2.55e5
+    a, b = B.method_ab("NCP", 7)
+    assert not a.any() and not b.any()
+    a, b = B.method_ab("CP", 7)
+    assert a.all() and b.all()
+    a, b = B.method_ab("dVIP", 7)
+    assert set(a) == {0.0, 1.0} and b.all()
+    assert B.MODEL_TABLE["radon_synth"]["bound"] == "hbm" and B.MODEL_TABLE["german_synth"]["bound"] == "tensor"
