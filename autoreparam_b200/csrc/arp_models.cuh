@@ -694,73 +694,98 @@ __device__ real vg_time_series_par(const DevModel& m, const real* a, const real*
   acc_t al = __shfl_up_sync(FULL, u, 1, LPC), mu = __shfl_up_sync(FULL, w, 1, LPC);   // state entering my segment
   if (sub == 0) { al = 0; mu = 0; }
   // ---- 3. walk my steps: centred values, log-density terms, and the adjoint map of the segment
-  //         (ca, cm) -> (P ca + U, R ca + S cm + W), built left to right: F <- F o B_t (B_t is applied first)
-  acc_t m_al[KMAX], m_mu[KMAX];
-  acc_t P = 1, U = 0, R = 0, S = 1, W = 0;
-  acc_t lp = 0;
+  //         (ca, cm) -> (P ca + U, R ca + S cm + W), built left to right: F <- F o B_t (B_t is applied first).
+  // MIXED PRECISION from here on: only what lives on the scale of the level (|alpha| ~ 2e3: the means m, the site
+  // offsets dz = z - a m where z ~ m cancels, the centred values and the residual) is formed in double; everything
+  // derived from dz and the residual (standardised offsets, log-density terms, adjoints and their scan) is `real`.
+  typedef real lo_t;
+  typedef SiteT<lo_t> SiteL;
+  const lo_t lsa_l = (lo_t)lsa, lsm_l = (lo_t)lsm, sig_a_l = (lo_t)sig_a, sig_m_l = (lo_t)sig_m;
+  const lo_t inv_obs_l = (lo_t)inv_obs;
+  // one site from its (double) offset: scales in `real`
+  auto site_lo = [&](acc_t dz_acc, lo_t ls, lo_t sig, lo_t bb, lo_t& lpl) {
+    SiteL sl;
+    lo_t sb_inv;
+    if (bb == (lo_t)1) { sb_inv = (lo_t)1 / sig; sl.r = (lo_t)1; }
+    else if (bb == (lo_t)0) { sb_inv = (lo_t)1; sl.r = sig; }
+    else { sb_inv = r_exp(-bb * ls); sl.r = r_exp(((lo_t)1 - bb) * ls); }
+    sl.dz = (lo_t)dz_acc;
+    const lo_t uu = sl.dz * sb_inv;
+    sl.usb = uu * sb_inv;
+    sl.x = 0;   // the centred value is kept in double by the caller
+    lpl += (lo_t)-0.5 * uu * uu - bb * ls - ARP_HALF_LOG_2PI;
+    return sl;
+  };
+  lo_t dz_al[KMAX], dz_mu[KMAX], lik_k[KMAX], mm_al[KMAX], mm_mu[KMAX];
+  lo_t P = 1, U = 0, R = 0, S = 1, W = 0;
+  lo_t lp_l = 0;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int t = t0 + k;
-    m_al[k] = 0; m_mu[k] = 0;
+    dz_al[k] = 0; dz_mu[k] = 0; lik_k[k] = 0; mm_al[k] = 0; mm_mu[k] = 0;
     if (t < t1) {
       const int ia = 2 + 2 * t, im = 3 + 2 * t;
-      const acc_t aa = A(ia), am = A(im);
-      m_al[k] = al + mu; m_mu[k] = mu;
-      SiteA s_al = site_fwd((acc_t)z(ia), m_al[k], lsa, aa, B(ia), lp);
-      SiteA s_mu = site_fwd((acc_t)z(im), m_mu[k], lsm, am, B(im), lp);
-      xc(ia) = (real)s_al.x; xc(im) = (real)s_mu.x;
-      al = s_al.x; mu = s_mu.x;
-      const acc_t e = ((acc_t)ldg(m.y + t) - al - be * (acc_t)ldg(m.x1 + t)) * inv_obs;
-      lp += (acc_t)-0.5 * e * e - log_obs - (acc_t)ARP_HALF_LOG_2PI_D;
-      const acc_t lik = e * inv_obs;
-      const acc_t c_al = (acc_t)1 - s_al.r * aa, c_mu = (acc_t)1 - s_mu.r * am;
-      const acc_t h_al = c_al * lik + aa * s_al.usb, h_mu = am * s_mu.usb;
+      const lo_t aa = (*(a + ia)), am = (*(a + im));
+      const acc_t m_a = al + mu, m_m = mu;
+      const acc_t dza = (acc_t)z(ia) - (acc_t)aa * m_a, dzm = (acc_t)z(im) - (acc_t)am * m_m;
+      SiteL s_al = site_lo(dza, lsa_l, sig_a_l, (*(b + ia)), lp_l);
+      SiteL s_mu = site_lo(dzm, lsm_l, sig_m_l, (*(b + im)), lp_l);
+      al = m_a + (acc_t)s_al.r * dza;
+      mu = m_m + (acc_t)s_mu.r * dzm;
+      xc(ia) = (real)al; xc(im) = (real)mu;
+      const lo_t e = (lo_t)(((acc_t)ldg(m.y + t) - al - be * (acc_t)ldg(m.x1 + t)) * inv_obs);
+      lp_l += (lo_t)-0.5 * e * e - (lo_t)log_obs - ARP_HALF_LOG_2PI;
+      const lo_t lik = e * inv_obs_l;
+      dz_al[k] = s_al.dz; dz_mu[k] = s_mu.dz; lik_k[k] = lik;
+      if (WITH_A) { mm_al[k] = (lo_t)m_a; mm_mu[k] = (lo_t)m_m; }
+      const lo_t c_al = (lo_t)1 - s_al.r * aa, c_mu = (lo_t)1 - s_mu.r * am;
+      const lo_t h_al = c_al * lik + aa * s_al.usb, h_mu = am * s_mu.usb;
       W = R * h_al + S * (h_al + h_mu) + W; R = (R + S) * c_al; S = S * c_mu;
       U = P * h_al + U; P = P * c_al;
     }
   }
+  acc_t lp = (acc_t)lp_l;
   // ---- 4. inclusive scan from the right: (mine) o (everything to my right, applied first)
 #pragma unroll
   for (int o = 1; o < LPC; o <<= 1) {
-    const acc_t PE = __shfl_down_sync(FULL, P, o, LPC), UE = __shfl_down_sync(FULL, U, o, LPC);
-    const acc_t RE = __shfl_down_sync(FULL, R, o, LPC), SE = __shfl_down_sync(FULL, S, o, LPC);
-    const acc_t WE = __shfl_down_sync(FULL, W, o, LPC);
+    const lo_t PE = __shfl_down_sync(FULL, P, o, LPC), UE = __shfl_down_sync(FULL, U, o, LPC);
+    const lo_t RE = __shfl_down_sync(FULL, R, o, LPC), SE = __shfl_down_sync(FULL, S, o, LPC);
+    const lo_t WE = __shfl_down_sync(FULL, W, o, LPC);
     if (sub + o < LPC) {
       W = R * UE + S * WE + W; R = R * PE + S * RE; S = S * SE;
       U = P * UE + U; P = P * PE;
     }
   }
-  acc_t ca = __shfl_down_sync(FULL, U, 1, LPC), cm = __shfl_down_sync(FULL, W, 1, LPC);   // carries entering from the right
+  lo_t ca = __shfl_down_sync(FULL, U, 1, LPC), cm = __shfl_down_sync(FULL, W, 1, LPC);   // carries entering from the right
   if (sub == LPC - 1) { ca = 0; cm = 0; }
   // ---- 5. walk my steps backwards
-  acc_t acc_lsa = 0, acc_lsm = 0, acc_be = 0;
+  lo_t acc_lsa_l = 0, acc_lsm_l = 0, acc_be_l = 0;
 #pragma unroll
   for (int k = KMAX - 1; k >= 0; --k) {
     const int t = t0 + k;
     if (t < t1) {
       const int ia = 2 + 2 * t, im = 3 + 2 * t;
-      const acc_t aa = A(ia), ba = B(ia), am = A(im), bm = B(im);
-      acc_t dummy = 0;
-      SiteA s_al = site_fwd((acc_t)z(ia), m_al[k], lsa, aa, ba, dummy);
-      SiteA s_mu = site_fwd((acc_t)z(im), m_mu[k], lsm, am, bm, dummy);
-      const acc_t xt = (acc_t)ldg(m.x1 + t);
-      const acc_t e = ((acc_t)ldg(m.y + t) - s_al.x - be * xt) * inv_obs;
-      const acc_t lik = e * inv_obs;
-      acc_be = fma(lik, xt, acc_be);
-      acc_t zb, mb_al, lb, ab;
-      site_rev(s_al, lik + ca, m_al[k], aa, ba, zb, mb_al, lb, ab);
+      const lo_t aa = (*(a + ia)), ba = (*(b + ia)), am = (*(a + im)), bm = (*(b + im));
+      lo_t dummy = 0;
+      SiteL s_al = site_lo((acc_t)dz_al[k], lsa_l, sig_a_l, ba, dummy);
+      SiteL s_mu = site_lo((acc_t)dz_mu[k], lsm_l, sig_m_l, bm, dummy);
+      const lo_t lik = lik_k[k];
+      acc_be_l = fma(lik, (lo_t)ldg(m.x1 + t), acc_be_l);
+      lo_t zb, mb_al, lb, ab;
+      site_rev(s_al, lik + ca, mm_al[k], aa, ba, zb, mb_al, lb, ab);
       g(ia) = (real)zb;
-      if (WITH_A) { abar(ia) = (real)ab; bbar(ia) = (real)site_bbar(s_al, lik + ca, lsa); }
-      acc_lsa += lb;
-      acc_t mb_mu;
-      site_rev(s_mu, cm, m_mu[k], am, bm, zb, mb_mu, lb, ab);
+      if (WITH_A) { abar(ia) = (real)ab; bbar(ia) = (real)site_bbar(s_al, lik + ca, lsa_l); }
+      acc_lsa_l += lb;
+      lo_t mb_mu;
+      site_rev(s_mu, cm, mm_mu[k], am, bm, zb, mb_mu, lb, ab);
       g(im) = (real)zb;
-      if (WITH_A) { abar(im) = (real)ab; bbar(im) = (real)site_bbar(s_mu, cm, lsm); }
-      acc_lsm += lb;
+      if (WITH_A) { abar(im) = (real)ab; bbar(im) = (real)site_bbar(s_mu, cm, lsm_l); }
+      acc_lsm_l += lb;
       ca = mb_al;
       cm = mb_al + mb_mu;
     }
   }
+  acc_t acc_lsa = (acc_t)acc_lsa_l, acc_lsm = (acc_t)acc_lsm_l, acc_be = (acc_t)acc_be_l;
   acc_lsa = group_sum<LPC>(acc_lsa);
   acc_lsm = group_sum<LPC>(acc_lsm);
   acc_be = group_sum<LPC>(acc_be);
