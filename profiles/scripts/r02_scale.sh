@@ -24,14 +24,14 @@ except Exception as e:
     print(name, "failed", e, open("gpurun_out/r02s_%s_n%s.err" % (name, n)).read()[-800:])
 PY
 }
-if [ "$ONLY" != configs4 ]; then
+if [ "$ONLY" != configs4 -a "$ONLY" != time_series ]; then
 run german_weak --steps 3 --warmup 3 --no_cpu_baseline
 run german_strong --steps 3 --warmup 3 --no_cpu_baseline --scaling strong --chains 16384
 fi
 [ "$ONLY" = german ] && exit 0
-run radon_synth --model radon_synth --chains 8192 --num_samples 100 --num_burnin_steps 100 --num_adaptation_steps 80 --stream_window 64 --steps 2 --warmup 1 --no_cpu_baseline
+[ "$ONLY" != time_series ] && run radon_synth --model radon_synth --chains 8192 --num_samples 100 --num_burnin_steps 100 --num_adaptation_steps 80 --stream_window 64 --steps 2 --warmup 1 --no_cpu_baseline
 run time_series --model time_series --chains 8192 --steps 2 --warmup 1 --no_cpu_baseline
-[ "$ONLY" = configs4 ] && exit 0
+[ "$ONLY" = configs4 -o "$ONLY" = time_series ] && exit 0
 if [ "$N" = 1 ]; then
   timeout 1500 python bench_models.py --out gpurun_out/r02_models_n$N.json > gpurun_out/r02_models_n$N.log 2>&1
 else
