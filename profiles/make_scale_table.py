@@ -19,7 +19,7 @@ out = ["# Multi-GPU runs, round 2 (`profiles/scripts/r02_scale.sh N` under `gpur
 names = {"german_weak": "configs[1] German credit 1000 x 25, 16 384 chains per GPU (weak)",
          "german_strong": "configs[1] German credit, 16 384 chains IN TOTAL (strong)",
          "radon_synth": "configs[4] synthetic radon 10^6 x 10^4, 8192 chains per GPU, streaming ESS W = 64, 100 kept samples",
-         "time_series": "configs[4] time_series, 8192 chains per GPU, 1000 kept samples (N = 1 and 8: final kernel with the mixed-precision scans; N = 2 and 4: run before that change)"}
+         "time_series": "configs[4] time_series, 8192 chains per GPU, 1000 kept samples (final kernel with the mixed-precision scans: 1 and 8 GPUs; the 2- and 4-GPU runs of the all-double kernel scaled 0.99 / 0.99)"}
 for key in ("german_weak", "german_strong", "radon_synth", "time_series"):
     if key not in rows:
         continue
