@@ -202,3 +202,94 @@ def test_windowed_ess_restatement():
     const = np.ones((50, 2))
     e, t = O.windowed_ess(const, 8)
     assert np.isnan(e).all() and not t.any()       # constant series: NaN, as TFP
+
+
+def _ts_affine_scan(raw, z, a, b, nlanes=8):
+    """numpy restatement of the lane-parallel time-series evaluation (csrc/arp_models.cuh: vg_time_series_par): the
+    centred values obey (alpha, mu)_t = M_t (alpha, mu)_{t-1} with affine maps that compose, the adjoint carries obey the
+    transposed recurrence; both are evaluated here exactly as the kernel does it -- per-lane composition, a scan over
+    lanes, then a local walk -- and return (centred [2T], gradient wrt the 2T level / trend coordinates)."""
+    x, y = np.asarray(raw["x"], float), np.asarray(raw["y"], float)
+    T = len(x)
+    sp = lambda v: np.logaddexp(v, 0.0)
+    sig_a, sig_m, be = sp(z[0] * 1.0), sp(z[1] * 1.0), z[2 + 2 * T]          # the three top sites are N(0, 1): x = z
+    # (a, b) of the top-level unit-scale sites do not move the centred value when loc = 0: x = 0 + 1 * (z - a * 0) = z
+    obs = float(np.float32(0.12))
+    ia = lambda t: 2 + 2 * t
+    im = lambda t: 3 + 2 * t
+    r = lambda bb, sig: sig ** (1.0 - bb)
+    K = -(-T // nlanes)
+    # 1. per-lane maps, 2. inclusive scan (sequential here: composition is associative)
+    maps = []
+    for lane in range(nlanes):
+        p = s = 1.0; q = u = w = 0.0
+        for t in range(lane * K, min(T, lane * K + K)):
+            ra, rm = r(b[ia(t)], sig_a), r(b[im(t)], sig_m)
+            ca, cm = 1 - ra * a[ia(t)], 1 - rm * a[im(t)]
+            da, dm = ra * z[ia(t)], rm * z[im(t)]
+            u, q, p = ca * (u + w) + da, ca * (q + s), ca * p
+            w, s = cm * w + dm, cm * s
+        maps.append((p, q, s, u, w))
+    state_in = [(0.0, 0.0)]
+    al = mu = 0.0
+    for (p, q, s, u, w) in maps[:-1]:
+        al, mu = p * al + q * mu + u, s * mu + w
+        state_in.append((al, mu))
+    # 3. local forward walk + adjoint maps of the segments
+    cen = np.zeros(2 * T); lik = np.zeros(T); site = {}
+    seg = []
+    for lane in range(nlanes):
+        al, mu = state_in[lane]
+        P = S = 1.0; U = R = W = 0.0
+        for t in range(lane * K, min(T, lane * K + K)):
+            out = []
+            for (idx, m, sig) in ((ia(t), al + mu, sig_a), (im(t), mu, sig_m)):
+                rr, sbi = sig ** (1 - b[idx]), sig ** (-b[idx])
+                dz = z[idx] - a[idx] * m
+                out.append(dict(r=rr, usb=dz * sbi * sbi, dz=dz, x=m + rr * dz, a=a[idx], b=b[idx]))
+            site[t] = out
+            al, mu = out[0]["x"], out[1]["x"]
+            cen[2 * t], cen[2 * t + 1] = al, mu
+            lik[t] = (y[t] - al - be * x[t]) / obs / obs
+            c_al, c_mu = 1 - out[0]["r"] * out[0]["a"], 1 - out[1]["r"] * out[1]["a"]
+            h_al, h_mu = c_al * lik[t] + out[0]["a"] * out[0]["usb"], out[1]["a"] * out[1]["usb"]
+            W, R, S = R * h_al + S * (h_al + h_mu) + W, (R + S) * c_al, S * c_mu
+            U, P = P * h_al + U, P * c_al
+        seg.append((P, U, R, S, W))
+    # 4. carries entering every segment from the right, 5. local backward walk
+    carry_in = [None] * nlanes
+    ca = cm = 0.0
+    for lane in range(nlanes - 1, -1, -1):
+        carry_in[lane] = (ca, cm)
+        P, U, R, S, W = seg[lane]
+        ca, cm = P * ca + U, R * ca + S * cm + W
+    g = np.zeros(2 * T)
+    for lane in range(nlanes):
+        ca, cm = carry_in[lane]
+        for t in range(min(T, lane * K + K) - 1, lane * K - 1, -1):
+            sa_, sm_ = site[t]
+            xb = lik[t] + ca
+            g[2 * t] = xb * sa_["r"] - sa_["usb"]
+            mb_al = xb * (1 - sa_["r"] * sa_["a"]) + sa_["a"] * sa_["usb"]
+            g[2 * t + 1] = cm * sm_["r"] - sm_["usb"]
+            mb_mu = cm * (1 - sm_["r"] * sm_["a"]) + sm_["a"] * sm_["usb"]
+            ca, cm = mb_al, mb_al + mb_mu
+    return cen, g
+
+
+@pytest.mark.parametrize("method", ["CP", "NCP", "VIP_ab"])
+@pytest.mark.parametrize("nlanes", [8, 32])
+def test_time_series_affine_scan_algebra(method, nlanes):
+    """The algebra behind the lane-parallel time-series kernel (affine-map composition of the centred values, transposed
+    recurrence of the adjoint carries) against the sequential oracle: centred values and the gradient with respect to
+    the 120 level / trend coordinates."""
+    raw = common.raw_data("time_series")
+    D = O.num_coords("time_series", raw)
+    a, b = common.ab_for(method, D)
+    z = common.random_states("time_series", D, 2, seed=9)
+    for c in range(2):
+        cen, g = _ts_affine_scan(raw, z[c], a, b, nlanes)
+        xc_ref = O.to_centered("time_series", raw, z[c:c + 1], a, b)[0]
+        _, g_ref = O.log_joint_and_grad("time_series", raw, z[c:c + 1], a, b)
+        assert np.abs(cen - xc_ref[2:-1]).max() < 1e-9 * max(1.0, np.abs(xc_ref).max())
+        assert np.abs(g - g_ref[0][2:-1]).max() < 1e-9 * np.abs(g_ref).max()
