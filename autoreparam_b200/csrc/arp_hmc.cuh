@@ -47,9 +47,10 @@ struct HmcArgs {
   int slice_rows;
   // streaming statistics of the kept (centred) samples, for runs whose [S, C, D] traces cannot be stored
   // (BASELINE configs[4]: 65 536 chains x 10 003 coordinates): per (chain, coordinate) a pivot (the first kept
-  // sample), the sum of y = x - pivot, a ring of the last W values of y, the first W values, and the W lag products
-  // sum_t y_t y_{t-k}.  All planes share the workspace layout (element (d, row) at d * sd + row * sc); k_stream_finalize
-  // turns them into mean / variance / ESS.  W = 0: off.
+  // sample), the sum of y = x - pivot, a ring of the last 2 W values of y (two blocks of W), the first W values, and
+  // the W lag products sum_t y_t y_{t-k}, updated once per block of W kept samples (stream_block).  All planes share
+  // the workspace layout (element (d, row) at d * sd + row * sc); k_stream_finalize adds the last, partial block and
+  // turns the sums into mean / variance / ESS.  W = 0: off.
   int stream_W;
   size_t stream_plane;             // elements per plane
   real* stream_pivot;              // [plane]
